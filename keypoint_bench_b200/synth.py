@@ -1,0 +1,186 @@
+"""Seeded synthetic inputs of the shapes the CNN backbones hand to the post-network path.
+
+The backbones themselves (ALIKE, SuperPoint, XFeat, DISK ...) are out of scope; what
+matters is the shape / value range of their outputs (e.g.
+models/ALike.py:159-164, models/SuperPoint.py:61-71, models/XFeat.py:136-140,
+models/disk.py:309-313) and the ``warp01_params`` schema of datasets/hpatches.py:76-81.
+
+Everything is generated from ``torch.Generator`` seeds so the oracle, the tests and the
+benchmark see identical inputs.  CPU generation is bit-reproducible across hosts for the
+iid kinds ('uniform', 'ties', 'ramp', 'negative'); the blurred 'alike' kind goes through a
+convolution and is only used where inputs are copied, not regenerated.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import torch
+import torch.nn.functional as F
+
+
+@dataclass(frozen=True)
+class PathConfig:
+    """One of BASELINE.json's five configs, reduced to what the hot path sees."""
+    name: str
+    height: int
+    width: int
+    desc_dim: int          # 0 = no descriptor stage (repeatability only)
+    desc_stride: int       # descriptor map is (H/stride, W/stride)
+    desc_normalized: bool
+    nms_dist: int
+    top_k: int
+    border_dist: int = 8
+    threshold: float = 0.0
+    min_score: float = 0.0
+    max_distance: float = 5.0
+    cross_check: bool = True
+    task: str = "match"    # 'repeatability' | 'mha' | 'match' | 'stream'
+    pairs_per_gpu: int = 64
+
+    @property
+    def extractor_params(self) -> dict:
+        return {'nms_dist': self.nms_dist, 'threshold': self.threshold, 'border_dist': self.border_dist,
+                'top_k': self.top_k, 'min_score': self.min_score}
+
+    @property
+    def matcher_params(self) -> dict:
+        return {'metric': 'euclidean', 'max_distance': self.max_distance, 'cross_check': self.cross_check}
+
+
+# config/config.yaml:17-22,38 ; config/config_MHA.yaml:82-85 ; SURVEY.md section 8(d)
+CONFIGS = {
+    'cfg1': PathConfig('cfg1-alike-t-repeatability-480x640', 480, 640, 0, 1, False, 6, 1000, task='repeatability'),
+    'cfg2': PathConfig('cfg2-superpoint256-mha-480x640', 480, 640, 256, 8, True, 6, 1000, task='mha'),
+    # nms_dist=4 (config_vo.yaml:88) so that top_k=4096 binds on a 480x640 map (SURVEY 8(d) warning)
+    'cfg3': PathConfig('cfg3-xfeat64-top4096-480x640', 480, 640, 64, 8, True, 4, 4096, task='match'),
+    'cfg4': PathConfig('cfg4-disk128-top2048-1024x1024', 1024, 1024, 128, 1, True, 6, 2048, task='match',
+                       pairs_per_gpu=4),
+    'cfg5': PathConfig('cfg5-alike-t-stream-376x1241', 376, 1241, 64, 1, False, 6, 1000, task='stream',
+                       pairs_per_gpu=32),
+}
+
+
+def pair_seed(cfg_index: int, pair_idx: int) -> int:
+    return 1234 + 1000 * cfg_index + pair_idx
+
+
+def _gen(seed: int, device="cpu") -> torch.Generator:
+    g = torch.Generator(device=device)
+    g.manual_seed(int(seed))
+    return g
+
+
+def _gauss_kernel(sigma: float, device) -> torch.Tensor:
+    r = int(math.ceil(3 * sigma))
+    x = torch.arange(-r, r + 1, dtype=torch.float32, device=device)
+    k = torch.exp(-(x * x) / (2 * sigma * sigma))
+    return k / k.sum()
+
+
+def score_map(kind: str, h: int, w: int, seed: int, device="cpu", sigma: float = 2.0) -> torch.Tensor:
+    """[1,1,h,w] float32 score map.
+
+    'uniform'  U(0,1) iid (6-8 NMS rounds)              'alike'   sigmoid(2*blur(N(0,1))/std)
+    'ties'     floor(8U)/8 (heavy ties)                 'ramp'    increasing along x (W/r rounds)
+    'negative' U(-1,0)                                  'mixed'   U(-0.5,0.5)
+    'relu'     max(U(-1,1),0) (exact zeros, KeyNet-like)
+    """
+    g = _gen(seed, device)
+    if kind == 'uniform':
+        return torch.rand(1, 1, h, w, generator=g, device=device)
+    if kind == 'ties':
+        return torch.floor(torch.rand(1, 1, h, w, generator=g, device=device) * 8) / 8
+    if kind == 'ramp':
+        row = (torch.arange(w, dtype=torch.float32, device=device) + 1) / (w + 1)
+        return row.view(1, 1, 1, w).expand(1, 1, h, w).contiguous()
+    if kind == 'negative':
+        return torch.rand(1, 1, h, w, generator=g, device=device) - 1.0
+    if kind == 'mixed':
+        return torch.rand(1, 1, h, w, generator=g, device=device) - 0.5
+    if kind == 'relu':
+        return torch.clamp(torch.rand(1, 1, h, w, generator=g, device=device) * 2 - 1, min=0)
+    if kind == 'alike':
+        z = torch.randn(1, 1, h, w, generator=g, device=device)
+        k = _gauss_kernel(sigma, device)
+        r = k.numel() // 2
+        z = F.conv2d(F.pad(z, (r, r, 0, 0), mode='reflect'), k.view(1, 1, 1, -1))
+        z = F.conv2d(F.pad(z, (0, 0, r, r), mode='reflect'), k.view(1, 1, -1, 1))
+        return torch.sigmoid(2 * z / z.std())
+    raise ValueError(f'unknown score-map kind {kind!r}')
+
+
+def homography(seed: int, jitter: float = 0.10) -> torch.Tensor:
+    """Pixel-unit 3x3 homography near identity, jittered +-``jitter`` per pair."""
+    g = _gen(seed)
+    base = torch.tensor([[1.02, 0.03, 5.0], [-0.02, 0.98, 3.0], [1e-5, -2e-5, 1.0]], dtype=torch.float64)
+    ident = torch.eye(3, dtype=torch.float64)
+    j = 1 + jitter * (2 * torch.rand(3, 3, generator=g, dtype=torch.float64) - 1)
+    hm = ident + (base - ident) * j
+    hm[2, 2] = 1.0
+    return hm.to(torch.float32)
+
+
+def _inverse_grid(hm: torch.Tensor, h: int, w: int, device) -> torch.Tensor:
+    """Normalised sampling grid that pulls image B's pixel (u,v) from A at H^-1 (u,v)."""
+    hinv = torch.linalg.inv(hm.double()).to(device)
+    ys, xs = torch.meshgrid(torch.arange(h, dtype=torch.float64, device=device),
+                            torch.arange(w, dtype=torch.float64, device=device), indexing='ij')
+    q = torch.stack([xs, ys, torch.ones_like(xs)], dim=-1) @ hinv.T
+    q = q[..., :2] / q[..., 2:]
+    gx = q[..., 0] / (w - 1) * 2 - 1
+    gy = q[..., 1] / (h - 1) * 2 - 1
+    return torch.stack([gx, gy], dim=-1).float().unsqueeze(0)
+
+
+def warp_map(src: torch.Tensor, hm: torch.Tensor, mode: str = 'nearest') -> torch.Tensor:
+    """Image-B view of a [1,C,h,w] map under pixel homography ``hm`` (of ITS OWN resolution)."""
+    _, _, h, w = src.shape
+    grid = _inverse_grid(hm, h, w, src.device)
+    return F.grid_sample(src, grid, mode=mode, padding_mode='zeros', align_corners=True)
+
+
+def rescale_homography(hm: torch.Tensor, stride: int) -> torch.Tensor:
+    """Same homography expressed in the pixel units of a 1/stride-resolution map."""
+    if stride == 1:
+        return hm
+    s = torch.diag(torch.tensor([1.0 / stride, 1.0 / stride, 1.0], dtype=torch.float64))
+    return (s @ hm.double() @ torch.linalg.inv(s)).float()
+
+
+def desc_map(c: int, h: int, w: int, seed: int, normalized: bool, device="cpu") -> torch.Tensor:
+    """[1,c,h,w]: unit-norm per pixel (SuperPoint/XFeat/DISK) or raw ~2.67-norm (ALIKE)."""
+    g = _gen(seed, device)
+    d = torch.randn(1, c, h, w, generator=g, device=device)
+    d = F.normalize(d, dim=1)
+    return d if normalized else 2.67 * d
+
+
+def warp_params(hm: torch.Tensor, h: int, w: int, resize: int = 512, as_tensors: bool = True):
+    """warp01 / warp10 dicts with the schema of datasets/hpatches.py:76-81 after the collate
+    unwrapping of models/model_interface.py:176-180 (0-dim int64 tensors)."""
+    def wrap(v):
+        return torch.tensor(v, dtype=torch.int64) if as_tensors else int(v)
+    inv = torch.linalg.inv(hm.double()).float()
+    w01 = {'mode': 'homo', 'width': wrap(w), 'height': wrap(h), 'homography_matrix': hm.clone(), 'resize': wrap(resize)}
+    w10 = {'mode': 'homo', 'width': wrap(w), 'height': wrap(h), 'homography_matrix': inv, 'resize': wrap(resize)}
+    return w01, w10
+
+
+def make_pair(cfg: PathConfig, cfg_index: int, pair_idx: int, kind: str = 'uniform', device="cpu") -> dict:
+    """One synthetic image pair for ``cfg``: score maps, descriptor maps, warp dicts."""
+    seed = pair_seed(cfg_index, pair_idx)
+    h, w = cfg.height, cfg.width
+    hm = homography(seed + 7)
+    s0 = score_map(kind, h, w, seed, device)
+    s1 = warp_map(s0, hm.to(device), 'nearest')
+    out = {'score0': s0, 'score1': s1, 'H': hm}
+    out['warp01'], out['warp10'] = warp_params(hm, h, w)
+    if cfg.desc_dim:
+        dh, dw = h // cfg.desc_stride, w // cfg.desc_stride
+        d0 = desc_map(cfg.desc_dim, dh, dw, seed + 13, cfg.desc_normalized, device)
+        hd = rescale_homography(hm, cfg.desc_stride).to(device)
+        g = _gen(seed + 17, device)
+        d1 = warp_map(d0, hd, 'bilinear') + 0.05 * torch.randn(d0.shape, generator=g, device=device)
+        out['desc0'], out['desc1'] = d0, d1
+    return out
