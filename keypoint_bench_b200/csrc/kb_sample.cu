@@ -1,0 +1,113 @@
+// Bilinear descriptor sampling at keypoints, optional fused L2 normalisation.
+// Reference: utils/matcher.py:221-226 (grid_sample, align_corners=True, no normalisation) and
+// models/lightglue.py:24-41 (pixel keypoints, F.normalize).
+//
+// Descriptor maps arrive NCHW, so one keypoint's C taps are C strided 4-byte reads; a warp owns
+// one keypoint, lanes stride over channels (each lane reads the 2x2 taps of its channel, the two
+// x-neighbours share a 32-byte sector), and the [n,C] output row is written coalesced.  The L2
+// norm is a warp-shuffle reduction over the lanes' partial sums.
+#include "kb_common.cuh"
+
+namespace {
+
+constexpr int NT = 256;   // 8 warps = 8 keypoints per block
+
+struct SampleParams {
+    const float* desc;   // [B,C,h,w]
+    const float* pts;    // [B,n_max,stride]
+    const int* count;    // [B] or null
+    float* out;          // [B,n_max,C]
+    int B, C, h, w, n_max, stride, normalize, coord_mode, s;
+};
+
+__global__ void __launch_bounds__(NT) sample_kernel(SampleParams p) {
+    const int warp = (blockIdx.x * NT + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.y;
+    if (warp >= p.n_max) return;
+    const int n = p.count ? p.count[b] : p.n_max;
+    if (warp >= n) return;
+    const float* pt = p.pts + ((size_t)b * p.n_max + warp) * p.stride;
+    const float kx = pt[0], ky = pt[1];
+    float gx, gy;
+    if (p.coord_mode == 0) {                        // matcher.py:221-222
+        gx = (kx - 0.5f) * 2.0f;
+        gy = (ky - 0.5f) * 2.0f;
+    } else {                                        // lightglue.py:27-33
+        const float s = (float)p.s;
+        const float ax = kx - s / 2.0f + 0.5f, ay = ky - s / 2.0f + 0.5f;
+        gx = ax / ((float)p.w * s - s / 2.0f - 0.5f) * 2.0f - 1.0f;
+        gy = ay / ((float)p.h * s - s / 2.0f - 0.5f) * 2.0f - 1.0f;
+    }
+    // grid_sample un-normalisation with align_corners=True: ((g+1)/2)*(size-1)
+    const float ix = ((gx + 1.0f) / 2.0f) * (float)(p.w - 1);
+    const float iy = ((gy + 1.0f) / 2.0f) * (float)(p.h - 1);
+    const float fx0 = floorf(ix), fy0 = floorf(iy);
+    const float fx1 = fx0 + 1.0f, fy1 = fy0 + 1.0f;
+    const float w_nw = (fx1 - ix) * (fy1 - iy);
+    const float w_ne = (ix - fx0) * (fy1 - iy);
+    const float w_sw = (fx1 - ix) * (iy - fy0);
+    const float w_se = (ix - fx0) * (iy - fy0);
+    // out-of-range coordinates (incl. NaN/inf) sample zeros
+    const bool finite = (ix > -2.0f) && (ix < (float)p.w + 1.0f) && (iy > -2.0f) && (iy < (float)p.h + 1.0f);
+    const int x0 = finite ? (int)fx0 : -8, y0 = finite ? (int)fy0 : -8;
+    const int x1 = x0 + 1, y1 = y0 + 1;
+    const bool in_x0 = x0 >= 0 && x0 < p.w, in_x1 = x1 >= 0 && x1 < p.w;
+    const bool in_y0 = y0 >= 0 && y0 < p.h, in_y1 = y1 >= 0 && y1 < p.h;
+    const size_t plane = (size_t)p.h * p.w;
+    const float* base = p.desc + (size_t)b * p.C * plane;
+    float* o = p.out + ((size_t)b * p.n_max + warp) * p.C;
+    float ss = 0.0f;
+    for (int c0 = 0; c0 < p.C; c0 += 32) {
+        const int c = c0 + lane;
+        float val = 0.0f;
+        if (c < p.C) {
+            const float* m = base + (size_t)c * plane;
+            const float nw = (in_x0 && in_y0) ? __ldg(m + (size_t)y0 * p.w + x0) : 0.0f;
+            const float ne = (in_x1 && in_y0) ? __ldg(m + (size_t)y0 * p.w + x1) : 0.0f;
+            const float sw = (in_x0 && in_y1) ? __ldg(m + (size_t)y1 * p.w + x0) : 0.0f;
+            const float se = (in_x1 && in_y1) ? __ldg(m + (size_t)y1 * p.w + x1) : 0.0f;
+            val = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(nw, w_nw), __fmul_rn(ne, w_ne)), __fmul_rn(sw, w_sw)),
+                            __fmul_rn(se, w_se));
+            if (!p.normalize) o[c] = val;
+        }
+        ss += val * val;
+    }
+    if (p.normalize) {
+        for (int d = 16; d > 0; d >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, d);
+        const float denom = fmaxf(sqrtf(ss), 1e-12f);          // F.normalize eps (lightglue.py:38-40)
+        // second pass re-reads the taps from L1/L2 (C <= 256: a few lines per lane)
+        for (int c0 = 0; c0 < p.C; c0 += 32) {
+            const int c = c0 + lane;
+            if (c < p.C) {
+                const float* m = base + (size_t)c * plane;
+                const float nw = (in_x0 && in_y0) ? __ldg(m + (size_t)y0 * p.w + x0) : 0.0f;
+                const float ne = (in_x1 && in_y0) ? __ldg(m + (size_t)y0 * p.w + x1) : 0.0f;
+                const float sw = (in_x0 && in_y1) ? __ldg(m + (size_t)y1 * p.w + x0) : 0.0f;
+                const float se = (in_x1 && in_y1) ? __ldg(m + (size_t)y1 * p.w + x1) : 0.0f;
+                const float val = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(nw, w_nw), __fmul_rn(ne, w_ne)),
+                                                      __fmul_rn(sw, w_sw)), __fmul_rn(se, w_se));
+                o[c] = val / denom;
+            }
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int kb_sample_desc(const float* desc, int B, int C, int h, int w, const float* pts, int pts_stride,
+                              const int* count, int n_max, int normalize, int coord_mode, int s, float* out,
+                              kb_stream_t stream) {
+    if (!desc || !pts || !out || B <= 0 || C <= 0 || h <= 0 || w <= 0 || n_max <= 0 || pts_stride < 2)
+        return KB_ERR_BAD_ARG;
+    if (coord_mode != 0 && coord_mode != 1) return KB_ERR_BAD_ARG;
+    if (B > 65535) return KB_ERR_UNSUPPORTED;
+    SampleParams p;
+    p.desc = desc; p.pts = pts; p.count = count; p.out = out;
+    p.B = B; p.C = C; p.h = h; p.w = w; p.n_max = n_max; p.stride = pts_stride;
+    p.normalize = normalize; p.coord_mode = coord_mode; p.s = s;
+    dim3 grid((n_max * 32 + NT - 1) / NT, B);
+    sample_kernel<<<grid, NT, 0, (cudaStream_t)stream>>>(p);
+    KB_LAUNCH_CHECK();
+    return KB_OK;
+}

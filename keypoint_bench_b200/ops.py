@@ -1,0 +1,262 @@
+"""Batched device-resident ops over the C ABI (include/kb_b200.h).
+
+These are the throughput entry points: every function takes and returns CUDA tensors, launches
+asynchronously on the current stream and never synchronises the host.  The per-image drop-ins
+with the reference's own signatures live in ``keypoint_bench_b200.utils`` / ``.tasks`` and are
+thin wrappers over these.
+
+PyTorch is used for device memory and streams only.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import _lib
+from ._lib import check, lib
+
+_launches = 0          # kernels launched through this module (bench.py reports it)
+
+
+def launches() -> int:
+    return _launches
+
+
+def _count(n: int) -> None:
+    global _launches
+    _launches += n
+
+
+def _require_cuda(t: torch.Tensor, name: str) -> None:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.KbError(f'{name} must be a CUDA tensor (keypoint_bench_b200 has no CPU path)')
+
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    return t.contiguous() if t.dtype == torch.float32 else t.to(torch.float32).contiguous()
+
+
+def _i32(t):
+    if t is None:
+        return None
+    return t.contiguous() if t.dtype == torch.int32 else t.to(torch.int32).contiguous()
+
+
+def _ptr(t) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ws(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def _maps3(score: torch.Tensor) -> torch.Tensor:
+    """[B,1,H,W] / [B,H,W] / [H,W] -> contiguous float32 [B,H,W] (channels fold into the batch)."""
+    s = _f32(score)
+    if s.dim() == 2:
+        s = s[None]
+    elif s.dim() == 4:
+        s = s.reshape(-1, s.shape[-2], s.shape[-1])
+    elif s.dim() != 3:
+        raise _lib.KbError(f'score map must have 2-4 dims, got {tuple(score.shape)}')
+    return s
+
+
+# ------------------------------------------------------------------------------------------------
+# Stage 1
+# ------------------------------------------------------------------------------------------------
+
+def fast_nms_batched(score: torch.Tensor, nms_dist: int = 4, max_iter: int = -1, min_value: float = 0.0,
+                     return_rounds: bool = False):
+    """Round-faithful ``fast_nms`` (utils/extracter.py:6-100) on every map of the batch jointly."""
+    _require_cuda(score, 'score')
+    s = _maps3(score)
+    b, h, w = s.shape
+    out = torch.empty_like(s)
+    rounds = torch.zeros(1, dtype=torch.int32, device=s.device)
+    ws = _ws(lib.kb_fast_nms_workspace_bytes(b, h, w), s.device)
+    with torch.cuda.device(s.device):
+        check(lib.kb_fast_nms(s.data_ptr(), out.data_ptr(), b, h, w, int(nms_dist), int(max_iter), float(min_value),
+                              rounds.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), 'kb_fast_nms')
+    _count(1)
+    out = out.reshape(score.shape) if score.dim() != 2 else out[0]
+    return (out, rounds) if return_rounds else out
+
+
+def select_batched(nms_map: torch.Tensor, border_dist: int, threshold: float, min_score: float, top_k: int,
+                   cap: int | None = None):
+    """Border + threshold + (top-k) + min_score on already-suppressed maps
+    (utils/extracter.py:164-190, 129-161, 217-220).  -> xyp[B,cap,3], count[B], raster[B,cap], total[B]."""
+    _require_cuda(nms_map, 'nms_map')
+    s = _maps3(nms_map)
+    b, h, w = s.shape
+    if cap is None:
+        cap = top_k if top_k > 0 else h * w
+    xyp = torch.zeros(b, cap, 3, dtype=torch.float32, device=s.device)
+    raster = torch.zeros(b, cap, dtype=torch.int32, device=s.device)
+    count = torch.zeros(b, dtype=torch.int32, device=s.device)
+    total = torch.zeros(b, dtype=torch.int32, device=s.device)
+    ws = _ws(lib.kb_select_workspace_bytes(b, h, w, int(top_k)), s.device)
+    with torch.cuda.device(s.device):
+        check(lib.kb_select(s.data_ptr(), b, h, w, int(border_dist), float(threshold), float(min_score), int(top_k),
+                            int(cap), xyp.data_ptr(), raster.data_ptr(), count.data_ptr(), total.data_ptr(),
+                            ws.data_ptr(), ws.numel(), _stream()), 'kb_select')
+    _count(1)
+    return xyp, count, raster, total
+
+
+def detect_batched(score: torch.Tensor, params: dict | None = None):
+    """``detection`` (utils/extracter.py:193-221) for every map of the batch independently.
+    -> xyp[B,top_k,3] (x,y,p), count[B], raster[B,top_k], path[B]."""
+    _require_cuda(score, 'score')
+    if params is None:
+        nms_dist, threshold, border_dist, top_k, min_score = 4, 0.0, 8, 300, 0.0   # extracter.py:200-205
+    else:
+        nms_dist, threshold, border_dist = params['nms_dist'], params['threshold'], params['border_dist']
+        top_k, min_score = params['top_k'], params['min_score']
+    s = _maps3(score)
+    b, h, w = s.shape
+    xyp = torch.zeros(b, top_k, 3, dtype=torch.float32, device=s.device)
+    raster = torch.zeros(b, top_k, dtype=torch.int32, device=s.device)
+    count = torch.zeros(b, dtype=torch.int32, device=s.device)
+    path = torch.zeros(b, dtype=torch.int32, device=s.device)
+    ws = _ws(lib.kb_detect_workspace_bytes(b, h, w, int(nms_dist), int(top_k), float(threshold)), s.device)
+    with torch.cuda.device(s.device):
+        check(lib.kb_detect(s.data_ptr(), b, h, w, int(nms_dist), int(border_dist), float(threshold),
+                            float(min_score), int(top_k), xyp.data_ptr(), raster.data_ptr(), count.data_ptr(),
+                            path.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), 'kb_detect')
+    _count(2)
+    return xyp, count, raster, path
+
+
+# ------------------------------------------------------------------------------------------------
+# Stage 2
+# ------------------------------------------------------------------------------------------------
+
+def sample_batched(desc: torch.Tensor, pts: torch.Tensor, count: torch.Tensor | None = None, normalize: bool = False,
+                   coord_mode: int = 0, s: int = 8) -> torch.Tensor:
+    """Bilinear descriptor sampling (utils/matcher.py:221-226; models/lightglue.py:24-41 with
+    ``normalize=True, coord_mode=1``).  desc [B,C,h,w]; pts [B,n,>=2]  ->  [B,n,C]."""
+    _require_cuda(desc, 'desc')
+    _require_cuda(pts, 'pts')
+    d = _f32(desc)
+    p = _f32(pts)
+    b, c, h, w = d.shape
+    if p.dim() != 3 or p.shape[0] != b or p.shape[2] < 2:
+        raise _lib.KbError(f'pts must be [B,n,>=2] with B={b}, got {tuple(p.shape)}')
+    n = p.shape[1]
+    out = torch.zeros(b, max(n, 1), c, dtype=torch.float32, device=d.device)
+    if n == 0:
+        return out[:, :0]
+    cnt = _i32(count)
+    with torch.cuda.device(d.device):
+        check(lib.kb_sample_desc(d.data_ptr(), b, c, h, w, p.data_ptr(), p.shape[2], _ptr(cnt), n, int(bool(normalize)),
+                                 int(coord_mode), int(s), out.data_ptr(), _stream()), 'kb_sample_desc')
+    _count(1)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# Stage 3
+# ------------------------------------------------------------------------------------------------
+
+def match_batched(d0: torch.Tensor, d1: torch.Tensor, n0: torch.Tensor | None = None, n1: torch.Tensor | None = None,
+                  max_distance: float = math.inf, cross_check: bool = True, algo: int = 0):
+    """Mutual-NN matching (utils/matcher.py:227-234).  d0 [B,n,D], d1 [B,m,D]
+    -> pairs[B,n,2] int32 (sorted by first index), dist[B,n] float64, count[B]."""
+    _require_cuda(d0, 'd0')
+    _require_cuda(d1, 'd1')
+    a, bm = _f32(d0), _f32(d1)
+    b, n, dd = a.shape
+    m = bm.shape[1]
+    if bm.shape[0] != b or bm.shape[2] != dd:
+        raise ValueError('Descriptor length must equal.')
+    pairs = torch.zeros(b, max(n, 1), 2, dtype=torch.int32, device=a.device)
+    dist = torch.zeros(b, max(n, 1), dtype=torch.float64, device=a.device)
+    count = torch.zeros(b, dtype=torch.int32, device=a.device)
+    if n == 0 or m == 0:
+        return pairs[:, :n], dist[:, :n], count
+    c0, c1 = _i32(n0), _i32(n1)
+    ws = _ws(lib.kb_match_workspace_bytes(b, n, m, dd, int(algo)), a.device)
+    with torch.cuda.device(a.device):
+        check(lib.kb_match_mnn(a.data_ptr(), bm.data_ptr(), _ptr(c0), _ptr(c1), b, n, m, dd, float(max_distance),
+                               int(bool(cross_check)), int(algo), pairs.data_ptr(), dist.data_ptr(), count.data_ptr(),
+                               ws.data_ptr(), ws.numel(), _stream()), 'kb_match_mnn')
+    _count(2)
+    return pairs, dist, count
+
+
+# ------------------------------------------------------------------------------------------------
+# Stage 4
+# ------------------------------------------------------------------------------------------------
+
+def warp_batched(pts: torch.Tensor, count: torch.Tensor | None, h33: torch.Tensor, wh: torch.Tensor):
+    """``warp_homography`` (utils/projection.py:137-167) per map.  pts [B,n,>=2]; h33 [B,3,3] or [B,9];
+    wh [B,2] = (width, height).  -> kp_valid[B,n,2], kp_warp[B,n,2], ids[B,n], ids_out[B,n], n_valid[B]."""
+    _require_cuda(pts, 'pts')
+    p = _f32(pts)
+    b, n = p.shape[0], p.shape[1]
+    hm = _f32(h33).reshape(b, 9)
+    whf = _f32(wh).reshape(b, 2)
+    kv = torch.zeros(b, max(n, 1), 2, dtype=torch.float32, device=p.device)
+    kw = torch.zeros_like(kv)
+    ids = torch.zeros(b, max(n, 1), dtype=torch.int32, device=p.device)
+    ids_out = torch.zeros_like(ids)
+    nv = torch.zeros(b, dtype=torch.int32, device=p.device)
+    if n == 0:
+        return kv[:, :0], kw[:, :0], ids[:, :0], ids_out[:, :0], nv
+    cnt = _i32(count)
+    with torch.cuda.device(p.device):
+        check(lib.kb_warp_homography(p.data_ptr(), p.shape[2], _ptr(cnt), b, n, hm.data_ptr(), whf.data_ptr(),
+                                     kv.data_ptr(), kw.data_ptr(), ids.data_ptr(), ids_out.data_ptr(), nv.data_ptr(),
+                                     _stream()), 'kb_warp_homography')
+    _count(1)
+    return kv, kw, ids, ids_out, nv
+
+
+def repeat_batched(k0c, k01c, na, k1c, k10c, nb, scale01: float, scale10: float, th: float, want_errors: bool = True,
+                   pair_cap: int = 0):
+    """Counting core of ``val_key_points`` (tasks/repeatability.py:69-85).
+    -> stats[B,4] float64 (gt_num, sum of errors <= th, n mutual pairs, 0), errors[B,a] or None, pairs or None."""
+    for t, nm in ((k0c, 'k0c'), (k01c, 'k01c'), (k1c, 'k1c'), (k10c, 'k10c')):
+        _require_cuda(t, nm)
+    a0, a1, b0, b1 = _f32(k0c), _f32(k01c), _f32(k1c), _f32(k10c)
+    b, a_max, b_max = a0.shape[0], a0.shape[1], b0.shape[1]
+    stats = torch.zeros(b, 4, dtype=torch.float64, device=a0.device)
+    errors = torch.zeros(b, a_max, dtype=torch.float32, device=a0.device) if want_errors else None
+    pairs = torch.full((b, pair_cap, 2), -1, dtype=torch.int32, device=a0.device) if pair_cap > 0 else None
+    if a_max == 0 or b_max == 0:
+        return stats, errors, pairs
+    ca, cb = _i32(na), _i32(nb)
+    ws = _ws(lib.kb_repeat_workspace_bytes(b, a_max, b_max), a0.device)
+    with torch.cuda.device(a0.device):
+        check(lib.kb_repeat_counts(a0.data_ptr(), a1.data_ptr(), _ptr(ca), b0.data_ptr(), b1.data_ptr(), _ptr(cb), b,
+                                   a_max, b_max, float(scale01), float(scale10), float(th), stats.data_ptr(),
+                                   _ptr(errors), _ptr(pairs), int(pair_cap), ws.data_ptr(), ws.numel(), _stream()),
+              'kb_repeat_counts')
+    _count(3 + (1 if pair_cap > 0 else 0))
+    return stats, errors, pairs
+
+
+def corner_error_batched(h_est: torch.Tensor, h_real: torch.Tensor, valid: torch.Tensor | None, w: int, h: int,
+                         resize_h: int, resize_w: int, th) -> tuple[torch.Tensor, torch.Tensor]:
+    """MHA corner error (tasks/MHA.py:51-72).  h_est/h_real [B,3,3] -> mean_dist[B], flags[B,len(th)] (float64)."""
+    _require_cuda(h_est, 'h_est')
+    he = h_est.to(torch.float64).contiguous().reshape(-1, 9)
+    hr = h_real.to(device=he.device, dtype=torch.float64).contiguous().reshape(-1, 9)
+    b = he.shape[0]
+    tht = torch.as_tensor(list(th), dtype=torch.float64, device=he.device)
+    md = torch.zeros(b, dtype=torch.float64, device=he.device)
+    flags = torch.zeros(b, tht.numel(), dtype=torch.float64, device=he.device)
+    v = _i32(valid)
+    with torch.cuda.device(he.device):
+        check(lib.kb_corner_error(he.data_ptr(), hr.data_ptr(), _ptr(v), b, int(w), int(h), int(resize_h),
+                                  int(resize_w), tht.data_ptr(), tht.numel(), md.data_ptr(), flags.data_ptr(),
+                                  _stream()), 'kb_corner_error')
+    _count(1)
+    return md, flags

@@ -1,0 +1,100 @@
+"""Batched, device-resident composition of the hot path for a batch of image pairs.
+
+This is what the reference's ``MInterface.test_step`` does per pair after the backbone
+(models/model_interface.py:231-253 -> tasks/repeatability.py:95-122 / tasks/MHA.py:11-72), expressed
+over a whole batch with no host synchronisation between stages:
+
+    detection x2 -> warp x2 (covisibility) -> [descriptor sampling x2 -> mutual-NN matching]
+                                           -> [val_key_points counting]
+
+Images 0 and 1 of every pair are stacked along the batch (first P maps = image 0, last P = image 1)
+so each stage is one launch for 2P maps.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+
+from . import ops
+from .synth import PathConfig
+
+
+@dataclass
+class PairBatch:
+    """Device-resident inputs for P pairs (what the backbone + dataset would hand over)."""
+    score: torch.Tensor          # [2P,1,H,W]   first P = image 0, last P = image 1
+    desc: torch.Tensor | None    # [2P,C,h,w]
+    h33: torch.Tensor            # [2P,9]  first P = H01 (pixels of image 1), last P = H10
+    wh: torch.Tensor             # [2P,2]  (width,height) of the TARGET image of each warp
+    resize: int = 512
+
+    @property
+    def pairs(self) -> int:
+        return self.score.shape[0] // 2
+
+
+def extract_match(batch: PairBatch, cfg: PathConfig, algo: int = 0, covisible_only: bool = True, timer=None) -> dict:
+    """detect -> (covisible) -> sample -> match for every pair.  Returns padded device tensors:
+    kpts [2P,top_k,3] + n_kpts [2P]; kcov [2P,top_k,2] + n_cov [2P] (when covisible_only);
+    matches [P,top_k,2] int32 (indices into the rows fed to the matcher) + n_matches [P]."""
+    P = batch.pairs
+    t = timer or (lambda name: None)
+    t('detect')
+    xyp, count, raster, path = ops.detect_batched(batch.score, cfg.extractor_params)
+    out = {'kpts': xyp, 'n_kpts': count, 'raster': raster, 'path': path}
+    pts, n_pts = xyp, count
+    if covisible_only:                                        # tasks/MHA.py:33-34
+        t('warp')
+        kv, kw, ids, ids_out, nv = ops.warp_batched(xyp, count, batch.h33, batch.wh)
+        out.update(kcov=kv, kwarp=kw, cov_ids=ids, n_cov=nv)
+        pts, n_pts = kv, nv
+    if batch.desc is not None:
+        t('sample')
+        d = ops.sample_batched(batch.desc, pts, n_pts)        # utils/matcher.py:221-226
+        t('match')
+        pairs, dist, n_m = ops.match_batched(d[:P], d[P:], n_pts[:P], n_pts[P:], cfg.max_distance, cfg.cross_check,
+                                             algo=algo)       # utils/matcher.py:227-231
+        out.update(desc=d, matches=pairs, match_dist=dist, n_matches=n_m)
+    t(None)
+    return out
+
+
+def repeatability_counts(batch: PairBatch, cfg: PathConfig, th: float = 3.0, timer=None) -> dict:
+    """detect x2 -> warp x2 -> val_key_points counting for every pair (tasks/repeatability.py:95-122).
+    stats[P,4] float64 = (gt_num, sum of errors<=th, n mutual pairs, 0); num_feat[P] = min(n0,n1)."""
+    P = batch.pairs
+    t = timer or (lambda name: None)
+    t('detect')
+    xyp, count, raster, path = ops.detect_batched(batch.score, cfg.extractor_params)
+    t('warp')
+    kv, kw, ids, ids_out, nv = ops.warp_batched(xyp, count, batch.h33, batch.wh)
+    t('repeat')
+    stats, errors, _ = ops.repeat_batched(kv[:P], kw[:P], nv[:P], kv[P:], kw[P:], nv[P:], float(batch.resize),
+                                          float(batch.resize), th, want_errors=True)
+    t(None)
+    num_feat = torch.minimum(count[:P], count[P:])
+    empty = (nv[:P] == 0) | (nv[P:] == 0)                     # repeatability.py:61-67 -> zeros
+    return {'stats': stats, 'errors': errors, 'num_feat': torch.where(empty, torch.zeros_like(num_feat), num_feat),
+            'n_kpts': count, 'n_cov': nv, 'empty': empty}
+
+
+def accumulate_repeatability(res: dict) -> torch.Tensor:
+    """Per-batch contribution to the run accumulators of models/model_interface.py:124-133:
+    float64 [sum repeatability_i, n_pairs, sum mean_error_i over non-NaN pairs, n_nonNaN, sum num_feat_i]."""
+    st = res['stats']
+    nf = res['num_feat'].to(torch.float64)
+    gt = st[:, 0]
+    rep = torch.where(nf > 0, gt / nf.clamp(min=1), torch.zeros_like(gt))
+    has = gt > 0
+    mean_err = torch.where(has, st[:, 1] / gt.clamp(min=1), torch.zeros_like(gt))
+    # pairs with no covisible keypoints report mean_error 0 (not NaN) in the reference
+    counted = has | res['empty']
+    return torch.stack([rep.sum(), torch.tensor(float(st.shape[0]), dtype=torch.float64, device=st.device),
+                        mean_err.sum(), counted.to(torch.float64).sum(), nf.sum()])
+
+
+def accumulate_matches(res: dict) -> torch.Tensor:
+    """float64 [sum matches, n_pairs] (the stream / AUC configs count matches per pair)."""
+    n = res['n_matches'].to(torch.float64)
+    return torch.stack([n.sum(), torch.tensor(float(n.numel()), dtype=torch.float64, device=n.device)])

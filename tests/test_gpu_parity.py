@@ -1,0 +1,302 @@
+"""GPU parity: the sm_100a kernels (through the C ABI) against the CPU oracle and the fixtures minted
+from the reference.  Bit-exact for keypoint sets / indices / match pairs, 1e-5 for float outputs
+(the tolerance BASELINE.json's north_star states)."""
+import ast
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from keypoint_bench_b200 import synth
+from oracle import ref_ops
+
+pytestmark = pytest.mark.gpu
+
+DEV = 'cuda'
+
+
+def ops():
+    from keypoint_bench_b200 import ops as _ops
+    return _ops
+
+
+# ------------------------------------------------------------------------------------------------ NMS
+
+def test_fast_nms_matches_reference_fixtures(golden):
+    g = golden('ref_nms.npz')
+    cases = [ast.literal_eval(str(c)) for c in g['cases']]
+    from keypoint_bench_b200.utils.extracter import fast_nms
+    for i, (kind, h, w, seed, r, mv, mi) in enumerate(cases):
+        s = torch.from_numpy(g[f'in_{i}'])[None, None].to(DEV)
+        out = fast_nms(s, nms_dist=r, max_iter=mi, min_value=mv)
+        assert out.shape == s.shape
+        assert np.array_equal(out.cpu().numpy()[0, 0], g[f'out_{i}']), f'case {i} {kind} r={r} mv={mv} mi={mi}'
+    s = torch.rand(1, 1, 8, 8, device=DEV)
+    assert fast_nms(s, nms_dist=0) is s                      # extracter.py:40-41
+
+
+@pytest.mark.parametrize('kind,h,w,r', [('uniform', 480, 640, 6), ('uniform', 376, 1241, 6), ('alike', 240, 320, 6),
+                                        ('ties', 200, 333, 4), ('mixed', 130, 170, 5), ('negative', 90, 110, 3),
+                                        ('ramp', 64, 640, 6), ('relu', 150, 150, 8)])
+def test_fast_nms_matches_oracle_rounds(kind, h, w, r):
+    s = synth.score_map(kind, h, w, 100 + r)
+    want, rounds = ref_ops.nms_rounds_separable(s.numpy()[0, 0][None], r, return_rounds=True)
+    out, got_rounds = ops().fast_nms_batched(s.to(DEV), r, return_rounds=True)
+    assert np.array_equal(out.cpu().numpy()[0, 0], want[0])
+    assert int(got_rounds.item()) == rounds
+
+
+def test_fast_nms_batch_is_joint_like_the_reference():
+    # the reference counts maxima over the whole batch (extracter.py:73); mixed-sign maps make the
+    # stopping round observable, so the batch must be processed jointly
+    s = torch.cat([synth.score_map('mixed', 60, 80, 1), synth.score_map('negative', 60, 80, 2),
+                   synth.score_map('uniform', 60, 80, 3)], dim=0)
+    want = ref_ops.nms_rounds_separable(s.numpy()[:, 0], 4)
+    out = ops().fast_nms_batched(s.to(DEV), 4)
+    assert np.array_equal(out.cpu().numpy()[:, 0], want)
+
+
+# ------------------------------------------------------------------------------------------------ detection
+
+def _check_detection(pts, want, raster=None, want_raster=None):
+    assert pts.shape == want.shape
+    uniq, cnt = np.unique(want[:, 2], return_counts=True)
+    single = uniq[cnt == 1]
+    tf = np.isin(want[:, 2], single) & np.isin(pts[:, 2], single)
+    assert np.array_equal(pts[tf], want[tf])                  # verbatim incl. order where scores are unique
+    assert np.array_equal(np.sort(pts[:, 2]), np.sort(want[:, 2]))
+    if want_raster is not None:
+        assert np.array_equal(raster, want_raster)             # canonical order (score desc, raster asc)
+
+
+def test_detection_matches_reference_fixtures(golden):
+    from keypoint_bench_b200.utils.extracter import detection
+    from oracle.make_golden import DETECT_CASES
+    g = golden('ref_detect.npz')
+    for tag, kind, h, w, seed, params in DETECT_CASES:
+        s = synth.score_map(kind, h, w, seed).to(DEV)
+        pts = detection(s, dict(params)).cpu().numpy()
+        _check_detection(pts, g[f'{tag}__pts'])
+        xyp, count, raster, _ = ops().detect_batched(s, dict(params))
+        n = int(count[0])
+        assert np.array_equal(raster[0, :n].cpu().numpy().astype(np.int64), g[f'{tag}__raster']), tag
+
+
+def test_detection_1024_and_batched_against_oracle():
+    cfg = synth.CONFIGS['cfg4']
+    s = synth.score_map('uniform', 1024, 1024, 9)
+    want, want_r = ref_ops.detection(s, cfg.extractor_params, nms='greedy')
+    xyp, count, raster, _ = ops().detect_batched(s.to(DEV), cfg.extractor_params)
+    n = int(count[0])
+    _check_detection(xyp[0, :n].cpu().numpy(), want, raster[0, :n].cpu().numpy().astype(np.int64), want_r)
+    # a batch of different maps is processed independently per map
+    maps = [synth.score_map(k, 120, 160, 40 + i) for i, k in enumerate(['uniform', 'ties', 'alike', 'relu', 'uniform'])]
+    params = dict(nms_dist=4, threshold=0.0, border_dist=8, top_k=50, min_score=0.0)
+    xyp, count, raster, _ = ops().detect_batched(torch.cat(maps, 0).to(DEV), params)
+    for i, m in enumerate(maps):
+        want, want_r = ref_ops.detection(m, params)
+        n = int(count[i])
+        assert n == want.shape[0]
+        assert np.array_equal(raster[i, :n].cpu().numpy().astype(np.int64), want_r)
+        assert np.array_equal(xyp[i, :n].cpu().numpy(), want)
+
+
+def test_positions_and_border_dropins():
+    from keypoint_bench_b200.utils.extracter import prob_map_to_positions_with_prob, remove_border_points
+    s = synth.score_map('uniform', 50, 70, 5)
+    want, _ = ref_ops.positions_with_prob(s.numpy(), 0.7)
+    got = prob_map_to_positions_with_prob(s.to(DEV), 0.7).cpu().numpy()
+    assert np.array_equal(got, want)
+    t = s.clone().to(DEV)
+    assert remove_border_points(t, 5) is t
+    assert np.array_equal(t.cpu().numpy(), ref_ops.clear_border(s.numpy(), 5))
+    assert prob_map_to_positions_with_prob(torch.zeros(1, 1, 9, 9, device=DEV)).shape == (0, 3)
+
+
+# ------------------------------------------------------------------------------------------------ sampling
+
+def test_sampling_matches_reference_fixture_and_oracle(golden):
+    from keypoint_bench_b200.utils.matcher import sample_descriptors_at
+    g = golden('ref_match.npz')
+    d0 = torch.from_numpy(g['small32__desc0']).to(DEV)
+    p0 = torch.from_numpy(g['small32__p0']).to(DEV)
+    got = sample_descriptors_at(d0, p0).cpu().numpy()
+    assert np.allclose(got, g['small32__s0'], rtol=1e-5, atol=1e-5)
+    # points on / outside the border, non-multiple-of-32 channel count, batch > 1 with ragged counts
+    gen = torch.Generator().manual_seed(3)
+    d = torch.randn(2, 70, 13, 17, generator=gen)
+    p = torch.rand(2, 90, 3, generator=gen) * 1.2 - 0.1
+    p[0, 0, :2] = torch.tensor([0.0, 0.0]); p[0, 1, :2] = torch.tensor([1.0, 1.0]); p[0, 2, :2] = torch.tensor([1.0, 0.0])
+    cnt = torch.tensor([90, 37], dtype=torch.int32)
+    out = ops().sample_batched(d.to(DEV), p.to(DEV), cnt.to(DEV)).cpu().numpy()
+    for b in range(2):
+        n = int(cnt[b])
+        want = torch.nn.functional.grid_sample(d[b:b + 1], ((p[b, :n, :2] - 0.5) * 2)[None, None],
+                                               align_corners=True)[0, :, 0].T.numpy()
+        assert np.allclose(out[b, :n], want, rtol=1e-5, atol=1e-5)
+        assert np.allclose(out[b, :n], ref_ops.sample_brute_force(d[b].numpy(), p[b, :n].numpy()), rtol=1e-5, atol=1e-5)
+
+
+def test_lightglue_sampling_mode():
+    gen = torch.Generator().manual_seed(8)
+    d = torch.randn(1, 256, 30, 40, generator=gen)
+    kp = torch.rand(1, 200, 2, generator=gen) * torch.tensor([320.0, 240.0])
+    out = ops().sample_batched(d.to(DEV), kp.to(DEV), None, normalize=True, coord_mode=1, s=8)[0].cpu().numpy()
+    want = ref_ops.sample_lightglue(d.numpy(), kp[0].numpy(), 8)
+    assert np.allclose(out, want, rtol=1e-5, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ matching
+
+def _exact_pairs_or_near_tie(got, d0, d1, maxd, cc):
+    """Pairs must equal the float64 oracle except rows/cols whose best and second-best distances are
+    within 1e-5 relative (north_star)."""
+    want = ref_ops.match_descriptors(d0, d1, metric='euclidean', max_distance=maxd, cross_check=cc)
+    if np.array_equal(got, want):
+        return
+    from scipy.spatial.distance import cdist
+    D = cdist(d0, d1)
+    s = np.sort(D, axis=1)
+    t = np.sort(D, axis=0)
+    amb_rows = set(np.flatnonzero((s[:, 1] - s[:, 0]) <= 1e-5 * s[:, 1]).tolist())
+    amb_cols = set(np.flatnonzero((t[1] - t[0]) <= 1e-5 * t[1]).tolist())
+    diff = set(map(tuple, got.tolist())) ^ set(map(tuple, want.tolist()))
+    for i, j in diff:
+        assert i in amb_rows or j in amb_cols or abs(D[i, j] - maxd) <= 1e-5 * maxd, (i, j)
+
+
+@pytest.mark.parametrize('algo', [0])
+def test_matcher_matches_reference_fixtures(golden, algo):
+    g = golden('ref_match.npz')
+    for tag in ('small32', 'sp256', 'nocross', 'tight'):
+        maxd, cc = g[f'{tag}__maxd_cc']
+        s0, s1 = g[f'{tag}__s0'], g[f'{tag}__s1']
+        pairs, dist, count = ops().match_batched(torch.from_numpy(s0)[None].to(DEV), torch.from_numpy(s1)[None].to(DEV),
+                                                 None, None, float(maxd), bool(cc), algo=algo)
+        k = int(count[0])
+        got = pairs[0, :k].cpu().numpy().astype(np.int64)
+        assert np.array_equal(got, g[f'{tag}__pairs']), tag
+        from scipy.spatial.distance import cdist
+        D = cdist(s0, s1)
+        assert np.allclose(dist[0, :k].cpu().numpy(), D[got[:, 0], got[:, 1]], rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize('algo', [0])
+@pytest.mark.parametrize('n,m,dim', [(1000, 1000, 256), (1000, 977, 64), (2048, 2048, 128), (1, 5, 32), (130, 1, 64),
+                                     (257, 511, 48)])
+def test_matcher_against_oracle_sizes(algo, n, m, dim):
+    gen = torch.Generator().manual_seed(n * 7 + m)
+    a = torch.nn.functional.normalize(torch.randn(n, dim, generator=gen), dim=1)
+    b = torch.nn.functional.normalize(torch.randn(m, dim, generator=gen), dim=1)
+    k = min(n, m) // 2
+    b[:k] = a[:k] + 0.05 * torch.randn(k, dim, generator=gen)
+    for maxd, cc in ((5.0, True), (0.9, True), (math.inf, False)):
+        pairs, dist, count = ops().match_batched(a[None].to(DEV), b[None].to(DEV), None, None, maxd, cc, algo=algo)
+        got = pairs[0, :int(count[0])].cpu().numpy().astype(np.int64)
+        _exact_pairs_or_near_tie(got, a.numpy(), b.numpy(), maxd, cc)
+
+
+@pytest.mark.parametrize('algo', [0])
+def test_matcher_ragged_batch_and_ties(algo):
+    gen = torch.Generator().manual_seed(11)
+    a = torch.randn(3, 300, 64, generator=gen)
+    b = torch.randn(3, 280, 64, generator=gen)
+    b[1, 7] = b[1, 3]                      # duplicate columns: first of ties must win (np.argmin)
+    a[2, 9] = a[2, 4]
+    n0 = torch.tensor([300, 123, 64], dtype=torch.int32)
+    n1 = torch.tensor([280, 200, 1], dtype=torch.int32)
+    pairs, dist, count = ops().match_batched(a.to(DEV), b.to(DEV), n0.to(DEV), n1.to(DEV), math.inf, True, algo=algo)
+    for i in range(3):
+        want = ref_ops.match_descriptors(a[i, :n0[i]].numpy(), b[i, :n1[i]].numpy(), cross_check=True)
+        got = pairs[i, :int(count[i])].cpu().numpy().astype(np.int64)
+        assert np.array_equal(got, want), i
+
+
+def test_brute_force_matcher_dropin(golden):
+    from keypoint_bench_b200.utils.matcher import brute_force_matcher
+    g = golden('ref_match.npz')
+    tag = 'small32'
+    maxd, cc = g[f'{tag}__maxd_cc']
+    params = {'metric': 'euclidean', 'max_distance': float(maxd), 'cross_check': bool(cc)}
+    p0, p1 = torch.from_numpy(g[f'{tag}__p0']).to(DEV), torch.from_numpy(g[f'{tag}__p1']).to(DEV)
+    r0, r1 = brute_force_matcher(p0, p1, torch.from_numpy(g[f'{tag}__desc0']).to(DEV),
+                                 torch.from_numpy(g[f'{tag}__desc1']).to(DEV), params)
+    assert np.array_equal(r0.cpu().numpy(), g[f'{tag}__r0'])
+    assert np.array_equal(r1.cpu().numpy(), g[f'{tag}__r1'])
+    with pytest.raises(ValueError):
+        brute_force_matcher(p0[:0], p1, torch.from_numpy(g[f'{tag}__desc0']).to(DEV),
+                            torch.from_numpy(g[f'{tag}__desc1']).to(DEV), params)
+    with pytest.raises(ValueError):
+        brute_force_matcher(p0, p1, torch.from_numpy(g[f'{tag}__desc0']).to(DEV),
+                            torch.from_numpy(g[f'{tag}__desc1']).to(DEV), dict(params, metric='hamming'))
+
+
+# ------------------------------------------------------------------------------------------------ evaluation
+
+def test_warp_and_val_key_points_match_reference_fixtures(golden):
+    from keypoint_bench_b200.tasks.repeatability import val_key_points
+    from keypoint_bench_b200.utils.projection import warp
+    g = golden('ref_eval.npz')
+    for tag in ('rep_480x640', 'rep_small'):
+        h, w = [int(v) for v in g[f'{tag}__hw']]
+        hm = torch.from_numpy(g[f'{tag}__H'])
+        w01, w10 = synth.warp_params(hm, h, w)
+        k0 = torch.from_numpy(g[f'{tag}__k0']).to(DEV)
+        k1 = torch.from_numpy(g[f'{tag}__k1']).to(DEV)
+        a, b, ids, ids_out = warp(k0, w01)
+        assert ids.dtype == torch.int64
+        assert np.array_equal(ids.cpu().numpy(), g[f'{tag}__ids'])
+        assert np.array_equal(ids_out.cpu().numpy(), g[f'{tag}__ids_out'])
+        assert np.allclose(a.cpu().numpy(), g[f'{tag}__warp_valid'], rtol=1e-5, atol=1e-6)
+        assert np.allclose(b.cpu().numpy(), g[f'{tag}__warp_proj'], rtol=1e-5, atol=1e-6)
+        res = val_key_points(k0, k1, w01, w10, th=3, return_pairs=True)
+        assert res['num_feat'] == int(g[f'{tag}__num_feat'])
+        # the reference quantises distances to 2^-7 before its equality test (99999 diagonal), so a
+        # 1-ulp difference in a distance can move one pair across a bucket edge: allow +-1
+        assert abs(res['gt_num'] - int(g[f'{tag}__gt_num'])) <= 1
+        assert abs(float(res['mean_error']) - float(g[f'{tag}__mean_error'])) < 1e-3
+        assert np.allclose(res['errors'].cpu().numpy(), g[f'{tag}__errors'], rtol=1e-5, atol=1e-5 * 512)
+        ora = ref_ops.val_key_points(g[f'{tag}__k0'], g[f'{tag}__k1'], w01, w10, th=3)
+        got_pairs = set(map(tuple, res['pairs'].tolist()))
+        want_pairs = set(map(tuple, ora['pairs'].tolist()))
+        assert len(got_pairs ^ want_pairs) <= 2
+
+
+def test_val_key_points_empty_and_unknown_mode():
+    from keypoint_bench_b200.tasks.repeatability import val_key_points
+    from keypoint_bench_b200.utils.projection import warp
+    hm = torch.tensor([[1.0, 0, 5000.0], [0, 1.0, 0], [0, 0, 1.0]])       # pushes everything out of view
+    w01, w10 = synth.warp_params(hm, 100, 100)
+    k = torch.rand(20, 3, device=DEV)
+    res = val_key_points(k, k, w01, w10)
+    assert res == {'num_feat': 0, 'repeatability': 0, 'mean_error': 0, 'errors': None}
+    with pytest.raises(ValueError):
+        warp(k, {'mode': 'bogus'})
+
+
+def test_corner_error_and_mha(golden):
+    from keypoint_bench_b200.tasks.MHA import mha
+    g = golden('ref_eval.npz')
+    h, w, c = [int(v) for v in g['mha__hwc']]
+    seed = int(g['mha__seed'])
+    hm = synth.homography(seed + 7)
+    s0 = synth.score_map('uniform', h, w, seed)
+    s1 = synth.warp_map(s0, hm, 'nearest')
+    w01, w10 = synth.warp_params(hm, h, w)
+    params = {'extractor_params': dict(nms_dist=6, threshold=0, border_dist=8, top_k=300, min_score=0.0),
+              'matcher_params': {'brute_force_params': {'metric': 'euclidean', 'max_distance': 5, 'cross_check': True}},
+              'MHA_params': {'th': [3, 5, 7]}}
+    img = torch.zeros(1, 3, h, w)
+    flags = mha(0, img, s0.to(DEV), torch.from_numpy(g['mha__d0']).to(DEV), img, s1.to(DEV),
+                torch.from_numpy(g['mha__d1']).to(DEV), w01, w10, params)
+    assert list(flags) == list(g['mha__flags'])
+    # corner error kernel against the float64 restatement
+    rng = np.random.default_rng(0)
+    he = np.stack([hm.numpy().astype(np.float64) + 1e-3 * rng.standard_normal((3, 3)) * [[1, 1, 50], [1, 1, 50], [1e-3, 1e-3, 0]]
+                   for _ in range(5)])
+    md, fl = ops().corner_error_batched(torch.from_numpy(he).to(DEV), hm.double()[None].expand(5, 3, 3).to(DEV), None,
+                                        w, h, h, w, [3, 5, 7])
+    for i in range(5):
+        f, m = ref_ops.corner_error_flags(he[i], hm.numpy().astype(np.float64), w, h, h, w, (3, 5, 7))
+        assert abs(m - float(md[i])) < 1e-9 and f == fl[i].cpu().tolist()

@@ -1,0 +1,151 @@
+"""CPU: the oracle restatements (oracle/ref_ops.py) against the fixtures minted from the reference
+itself by oracle/make_golden.py (tests/golden/*.npz).  No GPU, no /root/reference needed."""
+import ast
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+from keypoint_bench_b200 import synth
+from oracle import ref_ops
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+
+
+def nms_cases(golden):
+    g = golden('ref_nms.npz')
+    cases = [ast.literal_eval(str(c)) for c in g['cases']]
+    return g, cases
+
+
+def test_nms_restatements_match_reference_fixtures(golden):
+    g, cases = nms_cases(golden)
+    assert len(cases) >= 20
+    for i, (kind, h, w, seed, r, mv, mi) in enumerate(cases):
+        s = g[f'in_{i}']
+        want = g[f'out_{i}']
+        got = ref_ops.nms_rounds_separable(s[None], r, mi, mv)[0]
+        assert np.array_equal(got, want), f'separable rounds differ on case {i} {kind}'
+        if h * w <= 64 * 96:
+            im2 = ref_ops.nms_rounds_im2col(torch.from_numpy(s)[None, None].clone(), r, mi, mv).numpy()[0, 0]
+            assert np.array_equal(im2, want), f'im2col rounds differ on case {i} {kind}'
+        if kind in ('uniform', 'ties', 'ramp', 'relu', 'alike') and mv == 0.0 and mi == -1 and r > 0:
+            assert np.array_equal(ref_ops.nms_greedy(s, r), want), f'greedy closed form differs on case {i}'
+
+
+def test_synth_iid_maps_are_bit_reproducible(golden):
+    g, cases = nms_cases(golden)
+    for i, (kind, h, w, seed, r, mv, mi) in enumerate(cases):
+        if kind == 'alike':
+            continue
+        assert np.array_equal(synth.score_map(kind, h, w, seed).numpy()[0, 0], g[f'in_{i}']), (i, kind)
+
+
+@pytest.mark.parametrize('tag', ['raster_order_k_le_topk', 'threshold_minscore', 'no_nms_border0', 'mixed_sign', 'ramp'])
+def test_detection_small_cases_match_reference(golden, tag):
+    from oracle.make_golden import DETECT_CASES
+    g = golden('ref_detect.npz')
+    case = {c[0]: c for c in DETECT_CASES}[tag]
+    _, kind, h, w, seed, params = case
+    s = synth.score_map(kind, h, w, seed)
+    assert sha(s.numpy()) == str(g[f'{tag}__insha'])
+    pts, raster = ref_ops.detection(s, dict(params))
+    want = g[f'{tag}__pts']
+    if len(np.unique(want[:, 2])) == want.shape[0]:
+        assert np.array_equal(pts, want)
+    else:
+        assert np.array_equal(np.sort(pts[:, 2]), np.sort(want[:, 2]))
+    assert np.array_equal(raster, g[f'{tag}__raster'])
+
+
+def test_detection_cfg1_full_size_matches_reference(golden):
+    from oracle.make_golden import DETECT_CASES
+    g = golden('ref_detect.npz')
+    _, kind, h, w, seed, params = DETECT_CASES[0]
+    s = synth.score_map(kind, h, w, seed)
+    assert sha(s.numpy()) == str(g['cfg1_480x640__insha'])
+    pts, raster = ref_ops.detection(s, dict(params), nms='greedy')
+    want = g['cfg1_480x640__pts']
+    assert pts.shape == want.shape == (1000, 3)
+    # rows with a unique score must agree verbatim, position by position (SURVEY 8(c) rule ii)
+    uniq, cnt = np.unique(want[:, 2], return_counts=True)
+    tie_free = np.isin(want[:, 2], uniq[cnt == 1]) & np.isin(pts[:, 2], uniq[cnt == 1])
+    assert tie_free.sum() > 900
+    assert np.array_equal(pts[tie_free], want[tie_free])
+    assert np.array_equal(np.sort(pts[:, 2]), np.sort(want[:, 2]))
+
+
+def test_match_and_sampling_match_reference(golden):
+    g = golden('ref_match.npz')
+    for tag in ('small32', 'sp256', 'nocross', 'tight'):
+        maxd, cc = g[f'{tag}__maxd_cc']
+        pairs = ref_ops.match_descriptors(g[f'{tag}__s0'], g[f'{tag}__s1'], metric='euclidean', max_distance=float(maxd),
+                                          cross_check=bool(cc))
+        assert np.array_equal(pairs, g[f'{tag}__pairs']), tag
+        assert np.array_equal(g[f'{tag}__p0'][pairs[:, 0]], g[f'{tag}__r0']), tag
+        assert np.array_equal(g[f'{tag}__p1'][pairs[:, 1]], g[f'{tag}__r1']), tag
+        if g[f'{tag}__desc0'].size:
+            s0 = ref_ops.sample_brute_force(g[f'{tag}__desc0'], g[f'{tag}__p0'])
+            assert np.allclose(s0, g[f'{tag}__s0'], rtol=1e-5, atol=1e-6), tag
+
+
+def test_lightglue_sampler_is_unit_norm_and_matches_torch():
+    g = torch.Generator().manual_seed(5)
+    d = torch.randn(1, 48, 15, 20, generator=g)
+    kp = torch.rand(1, 70, 2, generator=g) * torch.tensor([160.0, 120.0])
+    s = 8
+    k = kp.clone() - s / 2 + 0.5
+    k = k / torch.tensor([(20 * s - s / 2 - 0.5), (15 * s - s / 2 - 0.5)])[None]
+    want = torch.nn.functional.grid_sample(d, (k * 2 - 1).view(1, 1, -1, 2), mode='bilinear', align_corners=True)
+    want = torch.nn.functional.normalize(want.reshape(1, 48, -1), p=2, dim=1)[0].T.numpy()
+    got = ref_ops.sample_lightglue(d.numpy(), kp[0].numpy(), s)
+    assert np.allclose(got, want, rtol=1e-5, atol=1e-6)
+    assert np.allclose(np.linalg.norm(got, axis=1), 1.0, atol=1e-5)
+
+
+def test_eval_restatements_match_reference(golden):
+    g = golden('ref_eval.npz')
+    for tag in ('rep_480x640', 'rep_small'):
+        h, w = [int(v) for v in g[f'{tag}__hw']]
+        hm = torch.from_numpy(g[f'{tag}__H'])
+        w01, w10 = synth.warp_params(hm, h, w)
+        k0, k1 = g[f'{tag}__k0'], g[f'{tag}__k1']
+        a, b, ids, ids_out = ref_ops.warp(k0, w01)
+        assert np.array_equal(ids, g[f'{tag}__ids']) and np.array_equal(ids_out, g[f'{tag}__ids_out'])
+        assert np.allclose(a, g[f'{tag}__warp_valid'], rtol=1e-5, atol=1e-6)
+        assert np.allclose(b, g[f'{tag}__warp_proj'], rtol=1e-5, atol=1e-6)
+        res = ref_ops.val_key_points(k0, k1, w01, w10, th=3)
+        assert res['num_feat'] == int(g[f'{tag}__num_feat'])
+        assert abs(res['gt_num'] - int(g[f'{tag}__gt_num'])) <= 1
+        assert abs(res['mean_error'] - float(g[f'{tag}__mean_error'])) < 1e-3
+        assert np.allclose(res['errors'], g[f'{tag}__errors'], rtol=1e-5, atol=1e-5 * 512)
+
+
+def test_mha_restatement_matches_reference(golden):
+    g = golden('ref_eval.npz')
+    h, w, c = [int(v) for v in g['mha__hwc']]
+    seed = int(g['mha__seed'])
+    hm = synth.homography(seed + 7)
+    s0 = synth.score_map('uniform', h, w, seed)
+    s1 = synth.warp_map(s0, hm, 'nearest')
+    assert sha(s1.numpy()) == str(g['mha__s1sha'])
+    w01, w10 = synth.warp_params(hm, h, w)
+    params = {'extractor_params': dict(nms_dist=6, threshold=0, border_dist=8, top_k=300, min_score=0.0),
+              'matcher_params': {'brute_force_params': {'metric': 'euclidean', 'max_distance': 5, 'cross_check': True}},
+              'MHA_params': {'th': [3, 5, 7]}}
+    flags, pairs = ref_ops.mha_pair(s0, g['mha__d0'], s1, g['mha__d1'], w01, w10, params, (h, w))
+    assert list(flags) == list(g['mha__flags'])
+    assert np.array_equal(pairs, g['mha__pairs'])
+
+
+def test_greedy_equals_rounds_on_random_positive_maps():
+    rng = np.random.default_rng(3)
+    for r in (1, 3, 6):
+        for trial in range(3):
+            v = rng.random((37, 53), dtype=np.float32)
+            if trial == 1:
+                v = np.floor(v * 6) / 6            # heavy ties, includes exact zeros
+            assert np.array_equal(ref_ops.nms_greedy(v, r), ref_ops.nms_rounds_separable(v, r))
