@@ -8,8 +8,13 @@
 // (extracter.py:217).
 #include "kb_common.cuh"
 
-int kb_nms_rounds_inplace(float* v, int B, int H, int W, int nms_dist, int max_iter, float min_value,
-                          int* rounds, void* ws, size_t ws_bytes, cudaStream_t st);
+int kb_nms_rounds_inplace(float* v, const float* src, int B, int H, int W, int nms_dist, int max_iter,
+                          float min_value, int per_map, const int* active, const int* any_active, int* rounds,
+                          void* ws, size_t ws_bytes, cudaStream_t st);
+size_t kb_sparse_workspace_bytes(int B, int H, int W, int top_k);
+int kb_sparse_detect(const float* score, int B, int H, int W, int nms_dist, int border, float threshold,
+                     float min_score, int top_k, float* xyp, int* raster, int* count, int* path,
+                     int** need_fallback_out, int** any_fallback_out, void* ws, size_t ws_bytes, cudaStream_t st);
 
 namespace {
 
@@ -67,7 +72,7 @@ __global__ void __launch_bounds__(NT) select_kernel(SelectParams p) {
     __shared__ int s_need, s_n;
 
     const int b = blockIdx.x;
-    if (p.skip && p.skip[b] != p.want) return;
+    if (p.skip && p.skip[b] != p.want) return;      // e.g. maps the sparse path already certified
     const int H = p.H, W = p.W;
     const float* img = p.map + (size_t)b * H * W;
     uint64_t* cand = p.cand + (size_t)b * p.cand_cap;
@@ -236,13 +241,18 @@ static size_t detect_cand_cap(int H, int W, int nms_dist, float threshold) {
     return (threshold >= 0.0f) ? nms_keep_bound(H, W, nms_dist) : (size_t)H * W;
 }
 
+static bool detect_uses_sparse(int H, int W, int nms_dist, float threshold, int top_k) {
+    return nms_dist > 0 && threshold >= 0.0f && kb_sparse_workspace_bytes(1, H, W, top_k) > 0;
+}
+
 extern "C" size_t kb_detect_workspace_bytes(int B, int H, int W, int nms_dist, int top_k, float threshold) {
-    (void)top_k;
     if (B <= 0 || H <= 0 || W <= 0) return 0;
     size_t n = 0;
-    n += kb_align_up((size_t)B * H * W * sizeof(float), 256);                    // working map
+    n += kb_align_up((size_t)B * H * W * sizeof(float), 256);                    // working map (fallback maps)
     n += kb_align_up(kb_fast_nms_workspace_bytes(B, H, W), 256);                 // NMS scratch
     n += kb_align_up((size_t)B * detect_cand_cap(H, W, nms_dist, threshold) * sizeof(uint64_t), 256);
+    if (detect_uses_sparse(H, W, nms_dist, threshold, top_k))
+        n += kb_align_up(kb_sparse_workspace_bytes(B, H, W, top_k), 256);
     return n + 1024;
 }
 
@@ -254,6 +264,7 @@ extern "C" int kb_detect(const float* score, int B, int H, int W, int nms_dist, 
         top_k <= 0)
         return KB_ERR_BAD_ARG;
     if (top_k > SORT_CAP) return KB_ERR_UNSUPPORTED;
+    if (B > 2048) return KB_ERR_UNSUPPORTED;         // callers split larger batches
     KbArena arena(ws, ws_bytes);
     float* work = arena.take<float>((size_t)B * H * W);
     const size_t nms_ws_bytes = kb_fast_nms_workspace_bytes(B, H, W);
@@ -261,15 +272,31 @@ extern "C" int kb_detect(const float* score, int B, int H, int W, int nms_dist, 
     SelectParams p;
     p.cand_cap = (int)detect_cand_cap(H, W, nms_dist, threshold);
     p.cand = arena.take<uint64_t>((size_t)B * p.cand_cap);
+    const bool sparse = detect_uses_sparse(H, W, nms_dist, threshold, top_k);
+    const size_t sp_bytes = sparse ? kb_sparse_workspace_bytes(B, H, W, top_k) : 0;
+    char* sp_ws = sparse ? arena.take<char>(sp_bytes) : nullptr;
     if (!arena.ok()) return KB_ERR_WORKSPACE;
-    KB_CUDA_TRY(cudaMemcpyAsync(work, score, (size_t)B * H * W * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    if (nms_dist > 0) {
-        int rc = kb_nms_rounds_inplace(work, B, H, W, nms_dist, -1, 0.0f, nullptr, nms_ws, nms_ws_bytes, st);
+
+    int* need_fallback = nullptr;
+    int* any_fallback = nullptr;
+    if (sparse) {
+        // 1. sparse exact path for every map; maps it cannot certify are flagged on the device
+        int rc = kb_sparse_detect(score, B, H, W, nms_dist, border_dist, threshold, min_score, top_k, xyp, raster,
+                                  count, path, &need_fallback, &any_fallback, sp_ws, sp_bytes, st);
         if (rc != KB_OK) return rc;
     }
-    p.map = work; p.B = B; p.H = H; p.W = W; p.border = border_dist; p.top_k = top_k; p.cap = top_k;
+    // 2. round-faithful NMS (each map on its own stopping rule) for the flagged maps -- all maps when
+    //    the sparse path does not apply.  With nothing flagged both launches exit immediately.
+    const float* sel_map = score;
+    if (nms_dist > 0) {
+        int rc = kb_nms_rounds_inplace(work, score, B, H, W, nms_dist, -1, 0.0f, /*per_map=*/1, need_fallback,
+                                       any_fallback, nullptr, nms_ws, nms_ws_bytes, st);
+        if (rc != KB_OK) return rc;
+        sel_map = work;
+    }
+    p.map = sel_map; p.B = B; p.H = H; p.W = W; p.border = border_dist; p.top_k = top_k; p.cap = top_k;
     p.threshold = threshold; p.min_score = min_score; p.xyp = xyp; p.raster = raster; p.count = count;
-    p.total = nullptr; p.skip = nullptr; p.want = 0;
+    p.total = nullptr; p.skip = need_fallback; p.want = 1;
     p.path = path; p.path_code = 2;      // round-faithful path
     return launch_select(p, st);
 }

@@ -300,3 +300,41 @@ def test_corner_error_and_mha(golden):
     for i in range(5):
         f, m = ref_ops.corner_error_flags(he[i], hm.numpy().astype(np.float64), w, h, h, w, (3, 5, 7))
         assert abs(m - float(md[i])) < 1e-9 and f == fl[i].cpu().tolist()
+
+
+# ------------------------------------------------------------------------------------------------ sparse path
+
+def test_detect_paths_sparse_and_fallback():
+    """uniform maps are certified by the sparse path (path 1); maps with negative scores, heavy ties or
+    a top_k the candidate budget cannot reach fall back to the round-faithful kernel (path 2); both
+    must equal the oracle."""
+    params = dict(nms_dist=6, threshold=0.0, border_dist=8, top_k=1000, min_score=0.0)
+    kinds = ['uniform', 'mixed', 'ties', 'uniform', 'alike', 'relu', 'negative', 'ramp']
+    maps = [synth.score_map(k, 480, 640, 300 + i) for i, k in enumerate(kinds)]
+    xyp, count, raster, path = ops().detect_batched(torch.cat(maps, 0).to(DEV), params)
+    path = path.cpu().tolist()
+    assert path[0] == 1 and path[3] == 1, path
+    assert path[1] == 2 and path[6] == 2, path
+    for i, m in enumerate(maps):
+        want, want_r = ref_ops.detection(m, params)
+        n = int(count[i])
+        assert n == want.shape[0], (kinds[i], n, want.shape[0])
+        assert np.array_equal(raster[i, :n].cpu().numpy().astype(np.int64), want_r), kinds[i]
+        assert np.array_equal(xyp[i, :n].cpu().numpy(), want), kinds[i]
+
+
+@pytest.mark.parametrize('seed', range(8))
+def test_detect_sparse_randomised_against_greedy_oracle(seed):
+    rng = np.random.default_rng(seed)
+    h, w = int(rng.integers(40, 300)), int(rng.integers(40, 400))
+    params = dict(nms_dist=int(rng.integers(1, 9)), threshold=float(rng.choice([0.0, 0.0, 0.3, 0.9])),
+                  border_dist=int(rng.integers(0, 12)), top_k=int(rng.choice([1, 7, 50, 300, 2000])),
+                  min_score=float(rng.choice([0.0, 0.0, 0.5, 0.97])))
+    kind = ['uniform', 'relu', 'alike', 'ties'][seed % 4]
+    m = synth.score_map(kind, h, w, 500 + seed)
+    want, want_r = ref_ops.detection(m, params)
+    xyp, count, raster, path = ops().detect_batched(m.to(DEV), params)
+    n = int(count[0])
+    assert n == want.shape[0], (params, kind, h, w, int(path[0]))
+    assert np.array_equal(raster[0, :n].cpu().numpy().astype(np.int64), want_r), (params, kind, int(path[0]))
+    assert np.array_equal(xyp[0, :n].cpu().numpy(), want)
