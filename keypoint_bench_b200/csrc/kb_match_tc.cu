@@ -52,8 +52,8 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
-    uint32_t spins = 0;
-    while (!done) {
+    long long t0 = 0;
+    while (true) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -61,7 +61,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "=r"(done)
             : "r"(bar), "r"(parity)
             : "memory");
-        if (!done && ++spins > (1u << 24)) __trap();      // a protocol bug must fail, not hang the GPU
+        if (done) break;
+        // a protocol bug must fail loudly, not hang the GPU: give up after ~2 s of waiting
+        const long long now = clock64();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 4000000000LL) __trap();
     }
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
@@ -375,7 +379,9 @@ struct ResolveParams {
     int* nn0;                // [B*n_max]
     int* nn1;                // [B*m_max]
     double* d2_0;            // [B*n_max] exact squared distance of the direction-0 winner
-    int* n_exact;            // [1] rows that needed the exact rescan (statistics)
+    int* n_exact;            // [1] number of rows queued for the exact rescan
+    int2* list;              // [list_cap] queued rows: (dir | b << 1, query row)
+    int list_cap;
     int B, n_max, m_max, D, n_dirs;
 };
 
@@ -404,23 +410,73 @@ __global__ void __launch_bounds__(256) resolve_kernel(ResolveParams p) {
     // a-priori bound on |t_computed - t_exact|: dropped lo.lo / residual terms (3*2^-18 |x||y|), fp32
     // accumulation in the tensor core (K/16 roundings) and the fp32 -|y|^2/2 term; generous factor on top
     const float e = 6.2e-5f * sqrtf(nq2) * sqrtf(dbmax2) + 3.1e-5f * dbmax2;
-    int j = r.idx;
-    double d2;
+    const int j = r.idx;
     const bool certain = (r.best - r.second) > 2.0f * e && j >= 0 && j < ndb;
     if (certain) {
-        d2 = warp_dist2(Q, DBs + (size_t)j * p.D, p.D, lane);
-    } else {
-        if (lane == 0 && p.n_exact) atomicAdd(p.n_exact, 1);
-        d2 = CUDART_INF;
-        j = 0;
-        for (int c = 0; c < ndb; ++c) {
-            const double v = warp_dist2(Q, DBs + (size_t)c * p.D, p.D, lane);
-            if (v < d2) { d2 = v; j = c; }                         // strict: first of ties (np.argmin)
+        const double d2 = warp_dist2(Q, DBs + (size_t)j * p.D, p.D, lane);
+        if (lane == 0) {
+            if (dir == 0) { p.nn0[(size_t)b * p.n_max + warp] = j; p.d2_0[(size_t)b * p.n_max + warp] = d2; }
+            else p.nn1[(size_t)b * p.m_max + warp] = j;
         }
+    } else if (lane == 0) {
+        const int slot = atomicAdd(p.n_exact, 1);
+        if (slot < p.list_cap) p.list[slot] = make_int2(dir | (b << 1), warp);
     }
-    if (lane == 0) {
-        if (dir == 0) { p.nn0[(size_t)b * p.n_max + warp] = j; p.d2_0[(size_t)b * p.n_max + warp] = d2; }
-        else p.nn1[(size_t)b * p.m_max + warp] = j;
+}
+
+// Exact float64 resolution of the queued rows (best/second closer than the error bound of the split
+// product, e.g. duplicated descriptors): one CTA per row, lanes over components, four candidates in
+// flight per warp.  First of ties wins, as np.argmin.  Same summation order as warp_dist2.
+__global__ void __launch_bounds__(256) rescan_kernel(ResolveParams p) {
+    extern __shared__ float xs[];
+    __shared__ double s_d[8];
+    __shared__ int s_j[8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int total = *p.n_exact;
+    if (total > p.list_cap) total = p.list_cap;
+    for (int e = blockIdx.x; e < total; e += gridDim.x) {
+        const int2 ent = p.list[e];
+        const int dir = ent.x & 1, b = ent.x >> 1, q = ent.y;
+        const int n = p.n0 ? p.n0[b] : p.n_max, m = p.n1 ? p.n1[b] : p.m_max;
+        const int ndb = dir ? n : m;
+        const int q_stride = dir ? p.m_max : p.n_max, db_stride = dir ? p.n_max : p.m_max;
+        const float* Q = (dir ? p.d1 : p.d0) + ((size_t)b * q_stride + q) * p.D;
+        const float* DBs = (dir ? p.d0 : p.d1) + (size_t)b * db_stride * p.D;
+        __syncthreads();
+        for (int k = threadIdx.x; k < p.D; k += 256) xs[k] = Q[k];
+        __syncthreads();
+        double bd = CUDART_INF;
+        int bj = 0x7fffffff;
+        for (int c0 = warp * 4; c0 < ndb; c0 += 32) {
+            double acc[4] = {0.0, 0.0, 0.0, 0.0};
+            const int nc = min(4, ndb - c0);
+            for (int k = lane; k < p.D; k += 32) {
+                const double xv = (double)xs[k];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (u < nc) {
+                        const double d = xv - (double)__ldg(DBs + (size_t)(c0 + u) * p.D + k);
+                        acc[u] = fma(d, d, acc[u]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                double a = acc[u];
+                for (int sft = 16; sft > 0; sft >>= 1) a += __shfl_xor_sync(0xffffffffu, a, sft);
+                if (u < nc && a < bd) { bd = a; bj = c0 + u; }      // ascending c within the warp: strict <
+            }
+        }
+        if (lane == 0) { s_d[warp] = bd; s_j[warp] = bj; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double d2 = s_d[0];
+            int j = s_j[0];
+            for (int w = 1; w < 8; ++w)
+                if (s_d[w] < d2 || (s_d[w] == d2 && s_j[w] < j)) { d2 = s_d[w]; j = s_j[w]; }
+            if (dir == 0) { p.nn0[(size_t)b * p.n_max + q] = j; p.d2_0[(size_t)b * p.n_max + q] = d2; }
+            else p.nn1[(size_t)b * p.m_max + q] = j;
+        }
     }
 }
 
@@ -531,8 +587,55 @@ static TcLayout tc_layout(int B, int n_max, int m_max, int D) {
     add((size_t)B * m_max * 4);                 // nn1
     add((size_t)B * n_max * 8);                 // d2_0
     add(256);                                   // n_exact
+    add((size_t)B * (n_max + m_max) * 8);       // rescan list
     L.bytes = n + 1024;
     return L;
+}
+
+struct TcBuffers {
+    __nv_bfloat16 *S0, *S1;
+    float *c0, *c1, *norm2_0, *norm2_1;
+    unsigned int *maxn0, *maxn1;
+    kbtc::Top2 *res0, *res1;
+    int *nn0, *nn1;
+    double* d2_0;
+    int* n_exact;
+    int2* list;
+    bool ok;
+};
+
+static TcBuffers tc_carve(void* ws, size_t ws_bytes, int B, int n_max, int m_max, const TcLayout& L) {
+    KbArena arena(ws, ws_bytes);
+    TcBuffers t;
+    t.S0 = arena.take<__nv_bfloat16>((size_t)B * n_max * 2 * L.Dp);
+    t.S1 = arena.take<__nv_bfloat16>((size_t)B * m_max * 2 * L.Dp);
+    t.c0 = arena.take<float>((size_t)B * L.cs0);
+    t.c1 = arena.take<float>((size_t)B * L.cs1);
+    t.norm2_0 = arena.take<float>((size_t)B * n_max);
+    t.norm2_1 = arena.take<float>((size_t)B * m_max);
+    t.maxn0 = arena.take<unsigned int>(B);
+    t.maxn1 = arena.take<unsigned int>(B);
+    t.res0 = arena.take<kbtc::Top2>((size_t)B * n_max);
+    t.res1 = arena.take<kbtc::Top2>((size_t)B * m_max);
+    t.nn0 = arena.take<int>((size_t)B * n_max);
+    t.nn1 = arena.take<int>((size_t)B * m_max);
+    t.d2_0 = arena.take<double>((size_t)B * n_max);
+    t.n_exact = arena.take<int>(1);
+    t.list = arena.take<int2>((size_t)B * (n_max + m_max));
+    t.ok = arena.ok();
+    return t;
+}
+
+// Diagnostics for the tests: byte offsets inside a kb_match_mnn(algo=1) workspace of
+// [0] res0 (Top2[B*n_max]: best, second, idx, pad), [1] res1, [2] n_exact (int), [3] norm2_0, [4] norm2_1.
+extern "C" KB_API int kb_match_tc_debug_offsets(int B, int n_max, int m_max, int D, size_t* off) {
+    if (!off || B <= 0 || n_max <= 0 || m_max <= 0 || D <= 0) return KB_ERR_BAD_ARG;
+    const TcLayout L = tc_layout(B, n_max, m_max, D);
+    char* base = (char*)4096;                       // any non-null, 256-aligned base
+    TcBuffers t = tc_carve(base, (size_t)-1, B, n_max, m_max, L);
+    off[0] = (char*)t.res0 - base; off[1] = (char*)t.res1 - base; off[2] = (char*)t.n_exact - base;
+    off[3] = (char*)t.norm2_0 - base; off[4] = (char*)t.norm2_1 - base;
+    return KB_OK;
 }
 
 size_t kb_match_tc_workspace_bytes(int B, int n_max, int m_max, int D) {
@@ -546,22 +649,14 @@ int kb_match_tc_run(const float* d0, const float* d1, const int* n0, const int* 
     if (B > 65535) return KB_ERR_UNSUPPORTED;
     const TcLayout L = tc_layout(B, n_max, m_max, D);
     if (L.KB > 4) return KB_ERR_UNSUPPORTED;                // query tile would not stay resident in shared memory
-    KbArena arena(ws, ws_bytes);
-    __nv_bfloat16* S0 = arena.take<__nv_bfloat16>((size_t)B * n_max * 2 * L.Dp);
-    __nv_bfloat16* S1 = arena.take<__nv_bfloat16>((size_t)B * m_max * 2 * L.Dp);
-    float* c0 = arena.take<float>((size_t)B * L.cs0);
-    float* c1 = arena.take<float>((size_t)B * L.cs1);
-    float* norm2_0 = arena.take<float>((size_t)B * n_max);
-    float* norm2_1 = arena.take<float>((size_t)B * m_max);
-    unsigned int* maxn0 = arena.take<unsigned int>(B);
-    unsigned int* maxn1 = arena.take<unsigned int>(B);
-    Top2* res0 = arena.take<Top2>((size_t)B * n_max);
-    Top2* res1 = arena.take<Top2>((size_t)B * m_max);
-    int* nn0 = arena.take<int>((size_t)B * n_max);
-    int* nn1 = arena.take<int>((size_t)B * m_max);
-    double* d2_0 = arena.take<double>((size_t)B * n_max);
-    int* n_exact = arena.take<int>(1);
-    if (!arena.ok()) return KB_ERR_WORKSPACE;
+    TcBuffers tb = tc_carve(ws, ws_bytes, B, n_max, m_max, L);
+    if (!tb.ok) return KB_ERR_WORKSPACE;
+    __nv_bfloat16 *S0 = tb.S0, *S1 = tb.S1;
+    float *c0 = tb.c0, *c1 = tb.c1, *norm2_0 = tb.norm2_0, *norm2_1 = tb.norm2_1;
+    unsigned int *maxn0 = tb.maxn0, *maxn1 = tb.maxn1;
+    Top2 *res0 = tb.res0, *res1 = tb.res1;
+    int *nn0 = tb.nn0, *nn1 = tb.nn1, *n_exact = tb.n_exact;
+    double* d2_0 = tb.d2_0;
 
     KB_CUDA_TRY(cudaMemsetAsync(maxn0, 0, (size_t)B * 4, st));
     KB_CUDA_TRY(cudaMemsetAsync(maxn1, 0, (size_t)B * 4, st));
@@ -601,9 +696,13 @@ int kb_match_tc_run(const float* d0, const float* d1, const int* n0, const int* 
     rp.d0 = d0; rp.d1 = d1; rp.n0 = n0; rp.n1 = n1; rp.res0 = res0; rp.res1 = res1;
     rp.norm2_0 = norm2_0; rp.norm2_1 = norm2_1; rp.maxn0 = maxn0; rp.maxn1 = maxn1;
     rp.nn0 = nn0; rp.nn1 = nn1; rp.d2_0 = d2_0; rp.n_exact = n_exact;
+    rp.list = tb.list; rp.list_cap = B * (n_max + m_max);
     rp.B = B; rp.n_max = n_max; rp.m_max = m_max; rp.D = D; rp.n_dirs = mp.n_dirs;
     const int qmax = n_max > m_max ? n_max : m_max;
     resolve_kernel<<<dim3((qmax * 32 + 255) / 256, B, mp.n_dirs), 256, 0, st>>>(rp);
+    KB_LAUNCH_CHECK();
+    if ((size_t)D * 4 > 48 * 1024) return KB_ERR_UNSUPPORTED;
+    rescan_kernel<<<sms * 4, 256, (size_t)D * 4, st>>>(rp);
     KB_LAUNCH_CHECK();
 
     PairsParams pp;

@@ -166,7 +166,7 @@ def sample_batched(desc: torch.Tensor, pts: torch.Tensor, count: torch.Tensor | 
 # ------------------------------------------------------------------------------------------------
 
 def match_batched(d0: torch.Tensor, d1: torch.Tensor, n0: torch.Tensor | None = None, n1: torch.Tensor | None = None,
-                  max_distance: float = math.inf, cross_check: bool = True, algo: int = 0):
+                  max_distance: float = math.inf, cross_check: bool = True, algo: int = 0, return_ws: bool = False):
     """Mutual-NN matching (utils/matcher.py:227-234).  d0 [B,n,D], d1 [B,m,D]
     -> pairs[B,n,2] int32 (sorted by first index), dist[B,n] float64, count[B]."""
     _require_cuda(d0, 'd0')
@@ -187,8 +187,25 @@ def match_batched(d0: torch.Tensor, d1: torch.Tensor, n0: torch.Tensor | None = 
         check(lib.kb_match_mnn(a.data_ptr(), bm.data_ptr(), _ptr(c0), _ptr(c1), b, n, m, dd, float(max_distance),
                                int(bool(cross_check)), int(algo), pairs.data_ptr(), dist.data_ptr(), count.data_ptr(),
                                ws.data_ptr(), ws.numel(), _stream()), 'kb_match_mnn')
-    _count(2)
+    _count(2 if algo == 0 else 5)
+    if return_ws:
+        return pairs, dist, count, ws
     return pairs, dist, count
+
+
+def match_tc_debug(ws: torch.Tensor, b: int, n: int, m: int, dd: int) -> dict:
+    """Views into an algo=1 workspace (tests only): per-row top-2 records, exact-rescan count, norms."""
+    import ctypes
+    off = (ctypes.c_size_t * 5)()
+    check(lib.kb_match_tc_debug_offsets(b, n, m, dd, ctypes.cast(off, ctypes.c_void_p)), 'kb_match_tc_debug_offsets')
+    def rec(o, rows):
+        raw = ws[o:o + rows * 16].view(torch.float32).reshape(rows, 4)
+        idx = ws[o:o + rows * 16].view(torch.int32).reshape(rows, 4)[:, 2]
+        return raw[:, 0], raw[:, 1], idx
+    return {'res0': rec(off[0], b * n), 'res1': rec(off[1], b * m),
+            'n_exact': ws[off[2]:off[2] + 4].view(torch.int32),
+            'norm2_0': ws[off[3]:off[3] + 4 * b * n].view(torch.float32),
+            'norm2_1': ws[off[4]:off[4] + 4 * b * m].view(torch.float32)}
 
 
 # ------------------------------------------------------------------------------------------------

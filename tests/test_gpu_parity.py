@@ -166,7 +166,7 @@ def _exact_pairs_or_near_tie(got, d0, d1, maxd, cc):
         assert i in amb_rows or j in amb_cols or abs(D[i, j] - maxd) <= 1e-5 * maxd, (i, j)
 
 
-@pytest.mark.parametrize('algo', [0])
+@pytest.mark.parametrize('algo', [0, 1])
 def test_matcher_matches_reference_fixtures(golden, algo):
     g = golden('ref_match.npz')
     for tag in ('small32', 'sp256', 'nocross', 'tight'):
@@ -182,7 +182,7 @@ def test_matcher_matches_reference_fixtures(golden, algo):
         assert np.allclose(dist[0, :k].cpu().numpy(), D[got[:, 0], got[:, 1]], rtol=1e-12, atol=1e-12)
 
 
-@pytest.mark.parametrize('algo', [0])
+@pytest.mark.parametrize('algo', [0, 1])
 @pytest.mark.parametrize('n,m,dim', [(1000, 1000, 256), (1000, 977, 64), (2048, 2048, 128), (1, 5, 32), (130, 1, 64),
                                      (257, 511, 48)])
 def test_matcher_against_oracle_sizes(algo, n, m, dim):
@@ -197,7 +197,7 @@ def test_matcher_against_oracle_sizes(algo, n, m, dim):
         _exact_pairs_or_near_tie(got, a.numpy(), b.numpy(), maxd, cc)
 
 
-@pytest.mark.parametrize('algo', [0])
+@pytest.mark.parametrize('algo', [0, 1])
 def test_matcher_ragged_batch_and_ties(algo):
     gen = torch.Generator().manual_seed(11)
     a = torch.randn(3, 300, 64, generator=gen)
