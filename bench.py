@@ -254,9 +254,8 @@ def main():
     if world > 1:
         parallel.init('nccl')
     algo = args.algo
-    if algo < 0:
-        algo = int(os.environ.get('KB_MATCH_ALGO', '0'))
-    config['matcher'] = 'tcgen05 split-bf16 Gram + float64 certify' if algo == 1 else 'float64 SIMT'
+    tc = algo == 1 or (algo < 0 and cfg.desc_dim <= 256)
+    config['matcher'] = 'tcgen05 split-bf16 Gram + float64 certify' if tc else 'float64 SIMT'
 
     batch, hms = make_batch(cfg, cfg_index, P, rank * P, device, args.kind)
     task_rep = cfg.desc_dim == 0

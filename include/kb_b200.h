@@ -117,7 +117,8 @@ KB_API int kb_sample_desc(const float* desc, int B, int C, int h, int w, const f
  * pairs with distance >= max_distance are dropped (strict <; pass INFINITY to disable).  Output
  * sorted by i ascending: pairs [B,n_max,2] int32, dist [B,n_max] float64 (may be NULL),
  * count [B].  `algo` 0 = float64 SIMT evaluation of every distance; 1 = tcgen05 tensor-core
- * candidate search (split-bf16 Gram in TMEM) with float64 certification of the winners.
+ * candidate search (split-bf16 Gram in TMEM) with float64 certification of the winners (D <= 256);
+ * -1 = automatic (1 when supported, else 0).  Both produce the same pairs.
  * ------------------------------------------------------------------------------------------- */
 KB_API size_t kb_match_workspace_bytes(int B, int n_max, int m_max, int D, int algo);
 KB_API int kb_match_mnn(const float* d0, const float* d1, const int* n0, const int* n1, int B, int n_max,

@@ -204,7 +204,9 @@ extern "C" size_t kb_match_workspace_bytes(int B, int n_max, int m_max, int D, i
     size_t f64 = kb_align_up((size_t)B * n_max * tj * sizeof(Best), 256) +
                  kb_align_up((size_t)B * m_max * ti * sizeof(Best), 256) +
                  kb_align_up((size_t)B * m_max * sizeof(int), 256) + 1024;
-    if (algo == 1) return kb_match_tc_workspace_bytes(B, n_max, m_max, D);
+    const size_t tc = kb_match_tc_workspace_bytes(B, n_max, m_max, D);
+    if (algo == 1) return tc;
+    if (algo < 0) return tc > f64 ? tc : f64;
     return f64;
 }
 
@@ -213,6 +215,7 @@ extern "C" int kb_match_mnn(const float* d0, const float* d1, const int* n0, con
                             double* dist, int* count, void* ws, size_t ws_bytes, kb_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (!d0 || !d1 || !pairs || !count || B <= 0 || n_max <= 0 || m_max <= 0 || D <= 0) return KB_ERR_BAD_ARG;
+    if (algo < 0) algo = (D <= 256) ? 1 : 0;       // auto: tensor cores whenever the query tile fits on chip
     if (algo == 1)
         return kb_match_tc_run(d0, d1, n0, n1, B, n_max, m_max, D, max_distance, cross_check, pairs, dist, count,
                                ws, ws_bytes, st);

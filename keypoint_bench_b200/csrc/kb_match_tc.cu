@@ -141,13 +141,31 @@ __global__ void __launch_bounds__(256) prep_kernel(PrepParams p) {
     }
     const float* x = p.d + ((size_t)b * p.n_max + row) * p.D;
     float ss = 0.0f;
-    for (int k = lane; k < p.Dp; k += 32) {
-        const float v = k < p.D ? x[k] : 0.0f;
-        const __nv_bfloat16 h = __float2bfloat16_rn(v);
-        const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
-        out[k] = h;
-        out[p.Dp + k] = l;
-        ss = fmaf(v, v, ss);
+    if ((p.D & 3) == 0 && (reinterpret_cast<uintptr_t>(p.d) & 15u) == 0) {
+        // 4 components per lane and step: one 16-byte load, two 8-byte stores
+        for (int k = 4 * lane; k < p.Dp; k += 128) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k < p.D) v = __ldg(reinterpret_cast<const float4*>(x + k));
+            const float f[4] = {v.x, v.y, v.z, v.w};
+            __nv_bfloat16 h[4], l[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                h[e] = __float2bfloat16_rn(f[e]);
+                l[e] = __float2bfloat16_rn(f[e] - __bfloat162float(h[e]));
+                ss = fmaf(f[e], f[e], ss);
+            }
+            *reinterpret_cast<uint2*>(out + k) = *reinterpret_cast<const uint2*>(h);
+            *reinterpret_cast<uint2*>(out + p.Dp + k) = *reinterpret_cast<const uint2*>(l);
+        }
+    } else {
+        for (int k = lane; k < p.Dp; k += 32) {
+            const float v = k < p.D ? x[k] : 0.0f;
+            const __nv_bfloat16 h = __float2bfloat16_rn(v);
+            const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+            out[k] = h;
+            out[p.Dp + k] = l;
+            ss = fmaf(v, v, ss);
+        }
     }
     for (int d = 16; d > 0; d >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, d);
     if (lane == 0) {
@@ -204,6 +222,7 @@ __global__ void __launch_bounds__(NT, 1) nn_top2_kernel(const __grid_constant__ 
     const uint32_t bar_b_full = bars + 16, bar_b_empty = bars + 16 + 8 * NSLOT;
     const uint32_t bar_t_full = bars + 16 + 16 * NSLOT, bar_t_empty = bar_t_full + 16;
     const uint32_t tmem_slot = bar_t_empty + 16;
+    float* cbuf = reinterpret_cast<float*>(smem_dyn + (tmem_slot + 16 - raw));     // [2][BN]
     volatile uint32_t* tmem_slot_ptr =
         reinterpret_cast<volatile uint32_t*>(smem_dyn + (tmem_slot - raw));
 
@@ -316,35 +335,51 @@ __global__ void __launch_bounds__(NT, 1) nn_top2_kernel(const __grid_constant__ 
             float best = -CUDART_INF_F, second = -CUDART_INF_F;
             int bj = 0;
             const int n_ct = (it.n_db + BN - 1) / BN;
+            // -|y|^2/2 of the next column tile travels through a register while the current tile is
+            // reduced, then through a 2 x 128-float shared buffer (one named barrier per tile)
+            float c_next = __ldg(cvec + ew * 32 + lane);
             for (int ct = 0; ct < n_ct; ++ct) {
+                float* cb = cbuf + (ct & 1) * BN;
+                cb[ew * 32 + lane] = c_next;
+                if (ct + 1 < n_ct) c_next = __ldg(cvec + (ct + 1) * BN + ew * 32 + lane);
+                asm volatile("bar.sync 1, 128;" ::: "memory");
                 mbar_wait(bar_t_full + 8 * acc_buf, t_phase[acc_buf]);
                 t_phase[acc_buf] ^= 1;
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc_buf * BN;
-#pragma unroll 1
-                for (int cc = 0; cc < BN / 32; ++cc) {
-                    uint32_t v[32];
-                    tmem_ld32(taddr + cc * 32, v);
-                    const float4* c4 = reinterpret_cast<const float4*>(cvec + ct * BN + cc * 32);
-                    float cv[32];
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const float4 t4 = __ldg(c4 + q);
-                        cv[4 * q] = t4.x; cv[4 * q + 1] = t4.y; cv[4 * q + 2] = t4.z; cv[4 * q + 3] = t4.w;
-                    }
-                    tmem_ld_wait();
+                uint32_t va[32], vb[32];
+                auto fold = [&](const uint32_t (&v)[32], int cc) {
+                    const float4* c4 = reinterpret_cast<const float4*>(cb + cc * 32);
                     const int j0 = ct * BN + cc * 32;
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) {
-                        const float t = __uint_as_float(v[e]) + cv[e];      // x.y - |y|^2/2 (-inf beyond the count)
-                        second = fmaxf(second, fminf(t, best));
-                        bj = (t > best) ? (j0 + e) : bj;                     // strict: first of ties
-                        best = fmaxf(best, t);
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 t4 = c4[q];
+                        const float cv[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float t = __uint_as_float(v[4 * q + e]) + cv[e];   // x.y - |y|^2/2 (-inf beyond the count)
+                            second = fmaxf(second, fminf(t, best));
+                            bj = (t > best) ? (j0 + 4 * q + e) : bj;                 // strict: first of ties
+                            best = fmaxf(best, t);
+                        }
                     }
-                }
+                };
+                tmem_ld32(taddr, va);
+                tmem_ld_wait();
+                tmem_ld32(taddr + 32, vb);
+                fold(va, 0);
+                tmem_ld_wait();
+                tmem_ld32(taddr + 64, va);
+                fold(vb, 1);
+                tmem_ld_wait();
+                tmem_ld32(taddr + 96, vb);
+                fold(va, 2);
+                tmem_ld_wait();
+                // the accumulator is in registers: hand the TMEM buffer back before the last fold
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_t_empty + 8 * acc_buf);
+                fold(vb, 3);
                 acc_buf ^= 1;
             }
             const int qi = it.q_row0 + row_in_tile;
@@ -378,7 +413,6 @@ struct ResolveParams {
     const unsigned int* maxn1;
     int* nn0;                // [B*n_max]
     int* nn1;                // [B*m_max]
-    double* d2_0;            // [B*n_max] exact squared distance of the direction-0 winner
     int* n_exact;            // [1] number of rows queued for the exact rescan
     int2* list;              // [list_cap] queued rows: (dir | b << 1, query row)
     int list_cap;
@@ -395,17 +429,16 @@ __device__ __forceinline__ double warp_dist2(const float* x, const float* y, int
     return acc;
 }
 
+// One thread per query row: certify the tensor-core argmax or queue the row for the exact rescan.
 __global__ void __launch_bounds__(256) resolve_kernel(ResolveParams p) {
-    const int warp = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int q = blockIdx.x * 256 + threadIdx.x;
     const int b = blockIdx.y, dir = blockIdx.z;
     const int n = p.n0 ? p.n0[b] : p.n_max, m = p.n1 ? p.n1[b] : p.m_max;
     const int nq = dir ? m : n, ndb = dir ? n : m;
-    if (warp >= nq || ndb <= 0) return;
-    const int q_stride = dir ? p.m_max : p.n_max, db_stride = dir ? p.n_max : p.m_max;
-    const float* Q = (dir ? p.d1 : p.d0) + ((size_t)b * q_stride + warp) * p.D;
-    const float* DBs = (dir ? p.d0 : p.d1) + (size_t)b * db_stride * p.D;
-    const Top2 r = (dir ? p.res1 : p.res0)[(size_t)b * q_stride + warp];
-    const float nq2 = (dir ? p.norm2_1 : p.norm2_0)[(size_t)b * q_stride + warp];
+    if (q >= nq || ndb <= 0) return;
+    const int q_stride = dir ? p.m_max : p.n_max;
+    const Top2 r = (dir ? p.res1 : p.res0)[(size_t)b * q_stride + q];
+    const float nq2 = (dir ? p.norm2_1 : p.norm2_0)[(size_t)b * q_stride + q];
     const float dbmax2 = __uint_as_float((dir ? p.maxn0 : p.maxn1)[b]);
     // a-priori bound on |t_computed - t_exact|: dropped lo.lo / residual terms (3*2^-18 |x||y|), fp32
     // accumulation in the tensor core (K/16 roundings) and the fp32 -|y|^2/2 term; generous factor on top
@@ -413,27 +446,69 @@ __global__ void __launch_bounds__(256) resolve_kernel(ResolveParams p) {
     const int j = r.idx;
     const bool certain = (r.best - r.second) > 2.0f * e && j >= 0 && j < ndb;
     if (certain) {
-        const double d2 = warp_dist2(Q, DBs + (size_t)j * p.D, p.D, lane);
-        if (lane == 0) {
-            if (dir == 0) { p.nn0[(size_t)b * p.n_max + warp] = j; p.d2_0[(size_t)b * p.n_max + warp] = d2; }
-            else p.nn1[(size_t)b * p.m_max + warp] = j;
-        }
-    } else if (lane == 0) {
+        (dir ? p.nn1 : p.nn0)[(size_t)b * q_stride + q] = j;
+    } else {
         const int slot = atomicAdd(p.n_exact, 1);
-        if (slot < p.list_cap) p.list[slot] = make_int2(dir | (b << 1), warp);
+        if (slot < p.list_cap) p.list[slot] = make_int2(dir | (b << 1), q);
     }
 }
 
 // Exact float64 resolution of the queued rows (best/second closer than the error bound of the split
-// product, e.g. duplicated descriptors): one CTA per row, lanes over components, four candidates in
-// flight per warp.  First of ties wins, as np.argmin.  Same summation order as warp_dist2.
+// product, e.g. duplicated descriptors): one CTA per row, lanes over components, eight candidates in
+// flight per warp (16 independent 16-byte loads per lane at D=256).  First of ties wins, as np.argmin.
+template <bool VEC>
+__device__ __forceinline__ void rescan_row(const float* xs, const float* DBs, int D, int ndb, int warp, int lane,
+                                           double& bd, int& bj) {
+    constexpr int G = 8;
+    for (int c0 = warp * G; c0 < ndb; c0 += 8 * G) {
+        double acc[G];
+#pragma unroll
+        for (int u = 0; u < G; ++u) acc[u] = 0.0;
+        if (VEC) {
+            for (int k = 4 * lane; k < D; k += 128) {
+                const float4 xv = *reinterpret_cast<const float4*>(xs + k);
+                float4 yv[G];
+#pragma unroll
+                for (int u = 0; u < G; ++u) {
+                    const int c = min(c0 + u, ndb - 1);
+                    yv[u] = __ldg(reinterpret_cast<const float4*>(DBs + (size_t)c * D + k));
+                }
+#pragma unroll
+                for (int u = 0; u < G; ++u) {
+                    double d = (double)xv.x - (double)yv[u].x; acc[u] = fma(d, d, acc[u]);
+                    d = (double)xv.y - (double)yv[u].y; acc[u] = fma(d, d, acc[u]);
+                    d = (double)xv.z - (double)yv[u].z; acc[u] = fma(d, d, acc[u]);
+                    d = (double)xv.w - (double)yv[u].w; acc[u] = fma(d, d, acc[u]);
+                }
+            }
+        } else {
+            for (int k = lane; k < D; k += 32) {
+                const double xv = (double)xs[k];
+#pragma unroll
+                for (int u = 0; u < G; ++u) {
+                    const int c = min(c0 + u, ndb - 1);
+                    const double d = xv - (double)__ldg(DBs + (size_t)c * D + k);
+                    acc[u] = fma(d, d, acc[u]);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < G; ++u) {
+            double a = acc[u];
+            for (int sft = 16; sft > 0; sft >>= 1) a += __shfl_xor_sync(0xffffffffu, a, sft);
+            if (c0 + u < ndb && a < bd) { bd = a; bj = c0 + u; }      // ascending c within the warp: strict <
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) rescan_kernel(ResolveParams p) {
-    extern __shared__ float xs[];
+    extern __shared__ __align__(16) float xs[];
     __shared__ double s_d[8];
     __shared__ int s_j[8];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int total = *p.n_exact;
     if (total > p.list_cap) total = p.list_cap;
+    const bool vec = (p.D & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.d0) | reinterpret_cast<uintptr_t>(p.d1)) & 15u) == 0;
     for (int e = blockIdx.x; e < total; e += gridDim.x) {
         const int2 ent = p.list[e];
         const int dir = ent.x & 1, b = ent.x >> 1, q = ent.y;
@@ -447,26 +522,8 @@ __global__ void __launch_bounds__(256) rescan_kernel(ResolveParams p) {
         __syncthreads();
         double bd = CUDART_INF;
         int bj = 0x7fffffff;
-        for (int c0 = warp * 4; c0 < ndb; c0 += 32) {
-            double acc[4] = {0.0, 0.0, 0.0, 0.0};
-            const int nc = min(4, ndb - c0);
-            for (int k = lane; k < p.D; k += 32) {
-                const double xv = (double)xs[k];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (u < nc) {
-                        const double d = xv - (double)__ldg(DBs + (size_t)(c0 + u) * p.D + k);
-                        acc[u] = fma(d, d, acc[u]);
-                    }
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                double a = acc[u];
-                for (int sft = 16; sft > 0; sft >>= 1) a += __shfl_xor_sync(0xffffffffu, a, sft);
-                if (u < nc && a < bd) { bd = a; bj = c0 + u; }      // ascending c within the warp: strict <
-            }
-        }
+        if (vec) rescan_row<true>(xs, DBs, p.D, ndb, warp, lane, bd, bj);
+        else rescan_row<false>(xs, DBs, p.D, ndb, warp, lane, bd, bj);
         if (lane == 0) { s_d[warp] = bd; s_j[warp] = bj; }
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -474,23 +531,49 @@ __global__ void __launch_bounds__(256) rescan_kernel(ResolveParams p) {
             int j = s_j[0];
             for (int w = 1; w < 8; ++w)
                 if (s_d[w] < d2 || (s_d[w] == d2 && s_j[w] < j)) { d2 = s_d[w]; j = s_j[w]; }
-            if (dir == 0) { p.nn0[(size_t)b * p.n_max + q] = j; p.d2_0[(size_t)b * p.n_max + q] = d2; }
-            else p.nn1[(size_t)b * p.m_max + q] = j;
+            (dir ? p.nn1 : p.nn0)[(size_t)b * q_stride + q] = j;
         }
     }
+}
+
+// One warp per row of d0: mutual check, float64 distance of the surviving pair, strict < max_distance.
+struct GateParams {
+    const float* d0;
+    const float* d1;
+    const int* n0;
+    const int* n1;
+    const int* nn0;
+    const int* nn1;
+    int* keep_j;             // [B*n_max] matched column or -1
+    double* dist_i;          // [B*n_max]
+    int n_max, m_max, D, cross_check;
+    double max_distance;
+};
+
+__global__ void __launch_bounds__(256) gate_kernel(GateParams p) {
+    const int i = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.y;
+    const int n = p.n0 ? p.n0[b] : p.n_max, m = p.n1 ? p.n1[b] : p.m_max;
+    if (i >= n || m <= 0) return;
+    const int j = p.nn0[(size_t)b * p.n_max + i];
+    int keep = -1;
+    double d = 0.0;
+    if (!p.cross_check || p.nn1[(size_t)b * p.m_max + j] == i) {
+        d = sqrt(warp_dist2(p.d0 + ((size_t)b * p.n_max + i) * p.D, p.d1 + ((size_t)b * p.m_max + j) * p.D, p.D, lane));
+        if (d < p.max_distance) keep = j;
+    }
+    if (lane == 0) { p.keep_j[(size_t)b * p.n_max + i] = keep; p.dist_i[(size_t)b * p.n_max + i] = d; }
 }
 
 struct PairsParams {
     const int* n0;
     const int* n1;
-    const int* nn0;
-    const int* nn1;
-    const double* d2_0;
+    const int* keep_j;
+    const double* dist_i;
     int* pairs;
     double* dist;
     int* count;
-    int n_max, m_max, cross_check;
-    double max_distance;
+    int n_max, m_max;
 };
 
 __global__ void __launch_bounds__(1024) pairs_kernel(PairsParams p) {
@@ -504,20 +587,14 @@ __global__ void __launch_bounds__(1024) pairs_kernel(PairsParams p) {
     int n_out = 0;
     for (int base = 0; base < n; base += 1024) {
         const int i = base + threadIdx.x;
-        bool keep = false;
-        int j = 0;
-        double d = 0.0;
-        if (i < n) {
-            j = p.nn0[(size_t)b * p.n_max + i];
-            d = sqrt(p.d2_0[(size_t)b * p.n_max + i]);
-            keep = (!p.cross_check || p.nn1[(size_t)b * p.m_max + j] == i) && (d < p.max_distance);
-        }
+        const int j = i < n ? p.keep_j[(size_t)b * p.n_max + i] : -1;
+        const bool keep = j >= 0;
         int tot;
         const int off = n_out + kb::block_exclusive_scan(keep ? 1 : 0, s_scan, &tot);
         if (keep) {
             p.pairs[((size_t)b * p.n_max + off) * 2 + 0] = i;
             p.pairs[((size_t)b * p.n_max + off) * 2 + 1] = j;
-            if (p.dist) p.dist[(size_t)b * p.n_max + off] = d;
+            if (p.dist) p.dist[(size_t)b * p.n_max + off] = p.dist_i[(size_t)b * p.n_max + i];
         }
         n_out += tot;
     }
@@ -588,6 +665,7 @@ static TcLayout tc_layout(int B, int n_max, int m_max, int D) {
     add((size_t)B * n_max * 8);                 // d2_0
     add(256);                                   // n_exact
     add((size_t)B * (n_max + m_max) * 8);       // rescan list
+    add((size_t)B * n_max * 4);                 // keep_j
     L.bytes = n + 1024;
     return L;
 }
@@ -601,6 +679,7 @@ struct TcBuffers {
     double* d2_0;
     int* n_exact;
     int2* list;
+    int* keep_j;
     bool ok;
 };
 
@@ -622,6 +701,7 @@ static TcBuffers tc_carve(void* ws, size_t ws_bytes, int B, int n_max, int m_max
     t.d2_0 = arena.take<double>((size_t)B * n_max);
     t.n_exact = arena.take<int>(1);
     t.list = arena.take<int2>((size_t)B * (n_max + m_max));
+    t.keep_j = arena.take<int>((size_t)B * n_max);
     t.ok = arena.ok();
     return t;
 }
@@ -682,7 +762,7 @@ int kb_match_tc_run(const float* d0, const float* d1, const int* n0, const int* 
     mp.n0 = n0; mp.n1 = n1; mp.c0 = c0; mp.c1 = c1; mp.res0 = res0; mp.res1 = res1;
     mp.B = B; mp.n_max = n_max; mp.m_max = m_max; mp.cs0 = L.cs0; mp.cs1 = L.cs1; mp.KB = L.KB;
     mp.tiles0 = L.tiles0; mp.tiles1 = L.tiles1; mp.n_dirs = cross_check ? 2 : 1;
-    const size_t smem = (size_t)(2 * L.KB + NSLOT) * TILE_BYTES + 1024 + 256;
+    const size_t smem = (size_t)(2 * L.KB + NSLOT) * TILE_BYTES + 1024 + 256 + 2 * BN * 4;
     KB_CUDA_TRY(cudaFuncSetAttribute(nn_top2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, sms = 0;
     KB_CUDA_TRY(cudaGetDevice(&dev));
@@ -695,19 +775,25 @@ int kb_match_tc_run(const float* d0, const float* d1, const int* n0, const int* 
     ResolveParams rp;
     rp.d0 = d0; rp.d1 = d1; rp.n0 = n0; rp.n1 = n1; rp.res0 = res0; rp.res1 = res1;
     rp.norm2_0 = norm2_0; rp.norm2_1 = norm2_1; rp.maxn0 = maxn0; rp.maxn1 = maxn1;
-    rp.nn0 = nn0; rp.nn1 = nn1; rp.d2_0 = d2_0; rp.n_exact = n_exact;
+    rp.nn0 = nn0; rp.nn1 = nn1; rp.n_exact = n_exact;
     rp.list = tb.list; rp.list_cap = B * (n_max + m_max);
     rp.B = B; rp.n_max = n_max; rp.m_max = m_max; rp.D = D; rp.n_dirs = mp.n_dirs;
     const int qmax = n_max > m_max ? n_max : m_max;
-    resolve_kernel<<<dim3((qmax * 32 + 255) / 256, B, mp.n_dirs), 256, 0, st>>>(rp);
+    resolve_kernel<<<dim3((qmax + 255) / 256, B, mp.n_dirs), 256, 0, st>>>(rp);
     KB_LAUNCH_CHECK();
     if ((size_t)D * 4 > 48 * 1024) return KB_ERR_UNSUPPORTED;
     rescan_kernel<<<sms * 4, 256, (size_t)D * 4, st>>>(rp);
     KB_LAUNCH_CHECK();
 
+    GateParams gp;
+    gp.d0 = d0; gp.d1 = d1; gp.n0 = n0; gp.n1 = n1; gp.nn0 = nn0; gp.nn1 = nn1; gp.keep_j = tb.keep_j; gp.dist_i = d2_0;
+    gp.n_max = n_max; gp.m_max = m_max; gp.D = D; gp.cross_check = cross_check; gp.max_distance = max_distance;
+    gate_kernel<<<dim3((n_max * 32 + 255) / 256, B), 256, 0, st>>>(gp);
+    KB_LAUNCH_CHECK();
+
     PairsParams pp;
-    pp.n0 = n0; pp.n1 = n1; pp.nn0 = nn0; pp.nn1 = nn1; pp.d2_0 = d2_0; pp.pairs = pairs; pp.dist = dist;
-    pp.count = count; pp.n_max = n_max; pp.m_max = m_max; pp.cross_check = cross_check; pp.max_distance = max_distance;
+    pp.n0 = n0; pp.n1 = n1; pp.keep_j = tb.keep_j; pp.dist_i = d2_0; pp.pairs = pairs; pp.dist = dist;
+    pp.count = count; pp.n_max = n_max; pp.m_max = m_max;
     pairs_kernel<<<B, 1024, 0, st>>>(pp);
     KB_LAUNCH_CHECK();
     return KB_OK;

@@ -166,7 +166,7 @@ def sample_batched(desc: torch.Tensor, pts: torch.Tensor, count: torch.Tensor | 
 # ------------------------------------------------------------------------------------------------
 
 def match_batched(d0: torch.Tensor, d1: torch.Tensor, n0: torch.Tensor | None = None, n1: torch.Tensor | None = None,
-                  max_distance: float = math.inf, cross_check: bool = True, algo: int = 0, return_ws: bool = False):
+                  max_distance: float = math.inf, cross_check: bool = True, algo: int = -1, return_ws: bool = False):
     """Mutual-NN matching (utils/matcher.py:227-234).  d0 [B,n,D], d1 [B,m,D]
     -> pairs[B,n,2] int32 (sorted by first index), dist[B,n] float64, count[B]."""
     _require_cuda(d0, 'd0')
@@ -187,7 +187,7 @@ def match_batched(d0: torch.Tensor, d1: torch.Tensor, n0: torch.Tensor | None = 
         check(lib.kb_match_mnn(a.data_ptr(), bm.data_ptr(), _ptr(c0), _ptr(c1), b, n, m, dd, float(max_distance),
                                int(bool(cross_check)), int(algo), pairs.data_ptr(), dist.data_ptr(), count.data_ptr(),
                                ws.data_ptr(), ws.numel(), _stream()), 'kb_match_mnn')
-    _count(2 if algo == 0 else 5)
+    _count(2 if (algo == 0 or dd > 256) else 7)
     if return_ws:
         return pairs, dist, count, ws
     return pairs, dist, count

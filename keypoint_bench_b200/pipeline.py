@@ -34,7 +34,7 @@ class PairBatch:
         return self.score.shape[0] // 2
 
 
-def extract_match(batch: PairBatch, cfg: PathConfig, algo: int = 0, covisible_only: bool = True, timer=None) -> dict:
+def extract_match(batch: PairBatch, cfg: PathConfig, algo: int = -1, covisible_only: bool = True, timer=None) -> dict:
     """detect -> (covisible) -> sample -> match for every pair.  Returns padded device tensors:
     kpts [2P,top_k,3] + n_kpts [2P]; kcov [2P,top_k,2] + n_cov [2P] (when covisible_only);
     matches [P,top_k,2] int32 (indices into the rows fed to the matcher) + n_matches [P]."""

@@ -33,7 +33,7 @@ def brute_force_matcher(pts0: torch.Tensor, pts1: torch.Tensor, desc_map_0: torc
     desc1 = sample_descriptors_at(desc_map_1, pts1)
     max_distance = params['max_distance']
     max_distance = math.inf if max_distance is None else float(max_distance)
-    algo = int(params.get('algo', 1 if params.get('tensor_core', False) else 0))
+    algo = int(params.get('algo', -1))       # -1: tcgen05 path when D <= 256, float64 SIMT otherwise
     pairs, _, count = ops.match_batched(desc0[None], desc1[None], None, None, max_distance, bool(params['cross_check']),
                                         algo=algo)
     k = int(count[0].item())

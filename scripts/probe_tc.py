@@ -48,10 +48,26 @@ def case(B, n, m, D, maxd=5.0, cc=True, seed=0, norm=True, verbose=True):
     return ok and ratio < 1.0
 
 
+def kernel_table(fn, iters=5):
+    """Per-kernel device time (CUPTI via torch.profiler; not a bench number, just shares)."""
+    from torch.profiler import profile, ProfilerActivity
+    fn()
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(iters):
+            fn()
+        torch.cuda.synchronize()
+    rows = [(e.key, e.device_time_total / iters, e.count / iters) for e in prof.key_averages() if e.device_time_total > 0]
+    for k, t, c in sorted(rows, key=lambda r: -r[1]):
+        print(f'    {k[:70]:70s} {t:10.1f} us/iter  x{c:.0f}', flush=True)
+
+
 def timing(B, n, m, D):
     g = torch.Generator().manual_seed(1)
     a = torch.nn.functional.normalize(torch.randn(B, n, D, generator=g), dim=2).cuda()
     b = torch.nn.functional.normalize(torch.randn(B, m, D, generator=g), dim=2).cuda()
+    b[:, :n // 2] = a[:, :n // 2] + 0.05 * torch.randn(B, n // 2, D, generator=g).cuda()
+    kernel_table(lambda: ops.match_batched(a, b, None, None, 5.0, True, algo=1))
     for algo in (0, 1):
         for _ in range(3):
             ops.match_batched(a, b, None, None, 5.0, True, algo=algo)

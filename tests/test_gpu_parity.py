@@ -338,3 +338,41 @@ def test_detect_sparse_randomised_against_greedy_oracle(seed):
     assert n == want.shape[0], (params, kind, h, w, int(path[0]))
     assert np.array_equal(raster[0, :n].cpu().numpy().astype(np.int64), want_r), (params, kind, int(path[0]))
     assert np.array_equal(xyp[0, :n].cpu().numpy(), want)
+
+
+# ------------------------------------------------------------------------------------------------ tensor-core matcher internals
+
+def test_matcher_auto_falls_back_beyond_256_dims():
+    gen = torch.Generator().manual_seed(5)
+    a = torch.randn(1, 150, 300, generator=gen)
+    b = torch.randn(1, 170, 300, generator=gen)
+    pairs, dist, count = ops().match_batched(a.to(DEV), b.to(DEV), None, None, math.inf, True)      # algo = -1
+    want = ref_ops.match_descriptors(a[0].numpy(), b[0].numpy(), cross_check=True)
+    assert np.array_equal(pairs[0, :int(count[0])].cpu().numpy().astype(np.int64), want)
+
+
+@pytest.mark.parametrize('n,m,dim,normed', [(1000, 977, 256, True), (700, 900, 64, False), (300, 300, 128, True)])
+def test_tensor_core_scores_stay_inside_the_certification_bound(n, m, dim, normed):
+    """The split-bf16 Gram scores t = x.y - |y|^2/2 must lie within the a-priori bound the resolver
+    certifies with (kb_match_tc.cu), measured against float64."""
+    gen = torch.Generator().manual_seed(n + dim)
+    a = torch.randn(2, n, dim, generator=gen) * (1.0 if normed else 3.0)
+    b = torch.randn(2, m, dim, generator=gen) * (1.0 if normed else 3.0)
+    if normed:
+        a, b = torch.nn.functional.normalize(a, dim=2), torch.nn.functional.normalize(b, dim=2)
+    a, b = a.to(DEV), b.to(DEV)
+    pairs, dist, count, ws = ops().match_batched(a, b, None, None, math.inf, True, algo=1, return_ws=True)
+    dbg = ops().match_tc_debug(ws, 2, n, m, dim)
+    best, second, idx = dbg['res0']
+    a64, b64 = a.double(), b.double()
+    idx_l = idx.long().reshape(2, n)
+    assert int(idx_l.min()) >= 0 and int(idx_l.max()) < m
+    yb = torch.gather(b64, 1, idx_l[..., None].expand(2, n, dim))
+    t_exact = (a64 * yb).sum(-1) - 0.5 * (yb * yb).sum(-1)
+    err = (best.reshape(2, n).double() - t_exact).abs()
+    nbmax = b64.norm(dim=2).max(dim=1).values[:, None]
+    bound = 6.2e-5 * a64.norm(dim=2) * nbmax + 3.1e-5 * nbmax * nbmax
+    assert float((err / bound).max()) < 0.5          # observed ~0.03: the bound keeps > 10x margin
+    # and the reported best really is the maximum of the exact scores up to that bound
+    t_all = a64 @ b64.transpose(1, 2) - 0.5 * (b64 * b64).sum(-1)[:, None, :]
+    assert bool(((t_all.max(dim=2).values - t_exact) <= 2 * bound).all())
