@@ -93,6 +93,113 @@ __global__ void __launch_bounds__(NT) sample_kernel(SampleParams p) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Plane-staged variant for low-resolution maps (SuperPoint / XFeat: 60x80 planes, ~1000+ keypoints):
+// nearly every pixel of the map is touched by some keypoint, so instead of gathering C strided
+// 4-byte taps per keypoint (4x sector amplification, L2-bound), a CTA pulls FOUR whole channel planes
+// into shared memory with one bulk async copy (contiguous in NCHW, each map byte leaves HBM exactly
+// once), then every thread interpolates its keypoints out of shared memory and writes the four
+// channels as one 16-byte piece of the [n,C] row.  Two CTAs per SM overlap one CTA's copy with the
+// other's arithmetic.  Same arithmetic (and rounding order) as sample_kernel.
+constexpr int PL_C = 4;          // planes per CTA
+constexpr int PL_NT = 256;
+
+__device__ __forceinline__ uint32_t smem_addr_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(PL_NT, 2) sample_planes_kernel(SampleParams p) {
+    extern __shared__ __align__(128) unsigned char pl_smem[];
+    __shared__ __align__(8) unsigned long long pl_bar;
+    float* planes = reinterpret_cast<float*>(pl_smem);
+    const int b = blockIdx.y, c0 = blockIdx.x * PL_C;
+    const int nc = min(PL_C, p.C - c0);
+    const int hw = p.h * p.w;
+    const int n = p.count ? p.count[b] : p.n_max;
+    if (n <= 0) return;
+    const float* src = p.desc + ((size_t)b * p.C + c0) * hw;
+    const uint32_t bytes = (uint32_t)nc * hw * 4u;
+    const bool bulk = ((reinterpret_cast<uintptr_t>(src) | bytes) & 15u) == 0;
+    const uint32_t bar = smem_addr_u32(&pl_bar);
+    if (bulk) {
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+            // <= 128 KB per copy; split so that each piece stays well inside the instruction's size field
+            uint32_t done = 0;
+            while (done < bytes) {
+                const uint32_t piece = min(bytes - done, 32768u);
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(smem_addr_u32(pl_smem + done)), "l"(reinterpret_cast<const char*>(src) + done),
+                               "r"(piece), "r"(bar) : "memory");
+                done += piece;
+            }
+        }
+    } else {
+        for (int i = threadIdx.x; i < nc * hw; i += PL_NT) planes[i] = __ldg(src + i);
+    }
+    // keypoint geometry of this thread's first keypoint while the copy is in flight
+    __syncthreads();
+    if (bulk) {
+        uint32_t ok = 0;
+        while (!ok) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(ok) : "r"(bar), "r"(0u) : "memory");
+        }
+    }
+    for (int k = threadIdx.x; k < n; k += PL_NT) {
+        const float* pt = p.pts + ((size_t)b * p.n_max + k) * p.stride;
+        const float kx = pt[0], ky = pt[1];
+        float gx, gy;
+        if (p.coord_mode == 0) {                        // matcher.py:221-222
+            gx = (kx - 0.5f) * 2.0f;
+            gy = (ky - 0.5f) * 2.0f;
+        } else {                                        // lightglue.py:27-33
+            const float s = (float)p.s;
+            const float ax = kx - s / 2.0f + 0.5f, ay = ky - s / 2.0f + 0.5f;
+            gx = ax / ((float)p.w * s - s / 2.0f - 0.5f) * 2.0f - 1.0f;
+            gy = ay / ((float)p.h * s - s / 2.0f - 0.5f) * 2.0f - 1.0f;
+        }
+        const float ix = ((gx + 1.0f) / 2.0f) * (float)(p.w - 1);
+        const float iy = ((gy + 1.0f) / 2.0f) * (float)(p.h - 1);
+        const float fx0 = floorf(ix), fy0 = floorf(iy);
+        const float fx1 = fx0 + 1.0f, fy1 = fy0 + 1.0f;
+        const float w_nw = (fx1 - ix) * (fy1 - iy);
+        const float w_ne = (ix - fx0) * (fy1 - iy);
+        const float w_sw = (fx1 - ix) * (iy - fy0);
+        const float w_se = (ix - fx0) * (iy - fy0);
+        const bool finite = (ix > -2.0f) && (ix < (float)p.w + 1.0f) && (iy > -2.0f) && (iy < (float)p.h + 1.0f);
+        const int x0 = finite ? (int)fx0 : -8, y0 = finite ? (int)fy0 : -8;
+        const int x1 = x0 + 1, y1 = y0 + 1;
+        const bool in_x0 = x0 >= 0 && x0 < p.w, in_x1 = x1 >= 0 && x1 < p.w;
+        const bool in_y0 = y0 >= 0 && y0 < p.h, in_y1 = y1 >= 0 && y1 < p.h;
+        const bool t_nw = in_x0 && in_y0, t_ne = in_x1 && in_y0, t_sw = in_x0 && in_y1, t_se = in_x1 && in_y1;
+        const int o_nw = y0 * p.w + x0, o_ne = o_nw + 1, o_sw = o_nw + p.w, o_se = o_sw + 1;
+        float val[PL_C];
+#pragma unroll
+        for (int c = 0; c < PL_C; ++c) {
+            val[c] = 0.0f;
+            if (c < nc) {
+                const float* m = planes + c * hw;
+                const float nw = t_nw ? m[o_nw] : 0.0f;
+                const float ne = t_ne ? m[o_ne] : 0.0f;
+                const float sw = t_sw ? m[o_sw] : 0.0f;
+                const float se = t_se ? m[o_se] : 0.0f;
+                val[c] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(nw, w_nw), __fmul_rn(ne, w_ne)), __fmul_rn(sw, w_sw)),
+                                   __fmul_rn(se, w_se));
+            }
+        }
+        float* o = p.out + ((size_t)b * p.n_max + k) * p.C + c0;
+        if (nc == PL_C && ((reinterpret_cast<uintptr_t>(o) & 15u) == 0)) {
+            *reinterpret_cast<float4*>(o) = make_float4(val[0], val[1], val[2], val[3]);
+        } else {
+            for (int c = 0; c < nc; ++c) o[c] = val[c];
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" int kb_sample_desc(const float* desc, int B, int C, int h, int w, const float* pts, int pts_stride,
@@ -106,6 +213,16 @@ extern "C" int kb_sample_desc(const float* desc, int B, int C, int h, int w, con
     p.desc = desc; p.pts = pts; p.count = count; p.out = out;
     p.B = B; p.C = C; p.h = h; p.w = w; p.n_max = n_max; p.stride = pts_stride;
     p.normalize = normalize; p.coord_mode = coord_mode; p.s = s;
+    // low-resolution, densely sampled maps: stage whole planes (see sample_planes_kernel)
+    const size_t plane_bytes = (size_t)h * w * 4;
+    if (!normalize && plane_bytes * PL_C <= 100 * 1024 && (size_t)n_max * 16 > (size_t)h * w) {
+        const size_t smem = plane_bytes * PL_C;
+        KB_CUDA_TRY(cudaFuncSetAttribute(sample_planes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid((C + PL_C - 1) / PL_C, B);
+        sample_planes_kernel<<<grid, PL_NT, smem, (cudaStream_t)stream>>>(p);
+        KB_LAUNCH_CHECK();
+        return KB_OK;
+    }
     dim3 grid((n_max * 32 + NT - 1) / NT, B);
     sample_kernel<<<grid, NT, 0, (cudaStream_t)stream>>>(p);
     KB_LAUNCH_CHECK();

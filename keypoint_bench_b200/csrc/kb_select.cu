@@ -11,7 +11,7 @@
 int kb_nms_rounds_inplace(float* v, const float* src, int B, int H, int W, int nms_dist, int max_iter,
                           float min_value, int per_map, const int* active, const int* any_active, int* rounds,
                           void* ws, size_t ws_bytes, cudaStream_t st);
-size_t kb_sparse_workspace_bytes(int B, int H, int W, int top_k);
+size_t kb_sparse_workspace_bytes(int B, int H, int W, int nms_dist, int top_k);
 int kb_sparse_detect(const float* score, int B, int H, int W, int nms_dist, int border, float threshold,
                      float min_score, int top_k, float* xyp, int* raster, int* count, int* path,
                      int** need_fallback_out, int** any_fallback_out, void* ws, size_t ws_bytes, cudaStream_t st);
@@ -242,7 +242,7 @@ static size_t detect_cand_cap(int H, int W, int nms_dist, float threshold) {
 }
 
 static bool detect_uses_sparse(int H, int W, int nms_dist, float threshold, int top_k) {
-    return nms_dist > 0 && threshold >= 0.0f && kb_sparse_workspace_bytes(1, H, W, top_k) > 0;
+    return nms_dist > 0 && threshold >= 0.0f && kb_sparse_workspace_bytes(1, H, W, nms_dist, top_k) > 0;
 }
 
 extern "C" size_t kb_detect_workspace_bytes(int B, int H, int W, int nms_dist, int top_k, float threshold) {
@@ -252,7 +252,7 @@ extern "C" size_t kb_detect_workspace_bytes(int B, int H, int W, int nms_dist, i
     n += kb_align_up(kb_fast_nms_workspace_bytes(B, H, W), 256);                 // NMS scratch
     n += kb_align_up((size_t)B * detect_cand_cap(H, W, nms_dist, threshold) * sizeof(uint64_t), 256);
     if (detect_uses_sparse(H, W, nms_dist, threshold, top_k))
-        n += kb_align_up(kb_sparse_workspace_bytes(B, H, W, top_k), 256);
+        n += kb_align_up(kb_sparse_workspace_bytes(B, H, W, nms_dist, top_k), 256);
     return n + 1024;
 }
 
@@ -273,7 +273,7 @@ extern "C" int kb_detect(const float* score, int B, int H, int W, int nms_dist, 
     p.cand_cap = (int)detect_cand_cap(H, W, nms_dist, threshold);
     p.cand = arena.take<uint64_t>((size_t)B * p.cand_cap);
     const bool sparse = detect_uses_sparse(H, W, nms_dist, threshold, top_k);
-    const size_t sp_bytes = sparse ? kb_sparse_workspace_bytes(B, H, W, top_k) : 0;
+    const size_t sp_bytes = sparse ? kb_sparse_workspace_bytes(B, H, W, nms_dist, top_k) : 0;
     char* sp_ws = sparse ? arena.take<char>(sp_bytes) : nullptr;
     if (!arena.ok()) return KB_ERR_WORKSPACE;
 

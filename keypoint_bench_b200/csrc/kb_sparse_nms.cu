@@ -1,37 +1,50 @@
 // Sparse exact detection path: NMS + border + threshold + top-k for non-negative score maps.
 //
 // The fixed point of the reference's fast_nms rounds (utils/extracter.py:49-98) on a non-negative map
-// is greedy NMS over the total order (score desc, raster asc) with Chebyshev radius r, and whether a
-// pixel is kept depends only on pixels of HIGHER priority.  detection() (extracter.py:193-221) keeps
-// the top_k interior survivors, so only the highest-scoring pixels can matter:
+// is greedy NMS over the total order (score desc, raster asc) with Chebyshev radius r: a pixel is kept
+// iff no KEPT pixel of higher priority lies within r.  Two consequences drive this path:
+//   * the pixels that win their whole (2r+1)^2 window ("round-1 maxima", exactly what the reference
+//     finds in its first round, extracter.py:54-70) are certainly kept, and every other pixel within r
+//     of one of them is certainly dead and never suppresses anything;
+//   * whether a pixel is kept depends only on pixels of HIGHER priority, so detection()'s top_k
+//     (extracter.py:217-218) only needs the pixels above the score of the (top_k+1)-th kept one.
 //
-//   tau_kernel      per map: a 4096-pixel sample picks tau so that ~C_target pixels exceed it;
-//   extract_kernel  ONE streaming pass over the maps (the HBM-bound kernel: float4 loads, 1 read of
-//                   every pixel): pixels > tau are appended to the map's candidate list as 64-bit
-//                   priority keys; also flags maps containing negative scores (those need the
-//                   round-faithful kernel because the reference's stop rule is then not monotone);
-//   greedy_kernel   one CTA per map: bitonic-sort the candidates by priority in shared memory, then
-//                   greedy NMS in that order against a 1-bit-per-pixel "kept" bitmap in shared memory,
-//                   1024 candidates per step (in-step conflicts resolved by a short fixed-point loop),
-//                   stopping as soon as top_k+1 interior survivors exist.
+//   tau_kernel     per map: 4096 sampled pixels (128 runs of 32 floats) give the score tau above which
+//                  ~1/12 of the pixels lie; lower pixels are not listed at all.
+//   round1_kernel  THE streaming kernel (one read of every pixel, 32x128 tiles + 2r halo staged in shared
+//                  memory): separable (2r+1)-window maximum in registers (row strips, then column strips
+//                  with warp ballots), exact first-of-ties rule, 1-bit maxima mask dilated by r on 32-bit
+//                  words; emits two candidate lists per map as 64-bit priority keys: round-1 maxima > tau
+//                  and pixels > tau not covered by any round-1 maximum.  Everything else is decided.
+//   sparse_kernel  one CTA per map: takes the ~1.25*top_k best round-1 maxima and every uncovered
+//                  candidate at or above the weakest of them, bins them on a coarse cell grid in shared
+//                  memory and resolves the remaining keep/suppress decisions by priority (a candidate is
+//                  kept once every higher-priority neighbour within r is dead, dead once one is kept),
+//                  then sorts the kept interior pixels and writes the top_k rows.
 //
-// A map is certified when it produced more than top_k interior survivors (K > top_k: output sorted by
-// priority) or when its candidate list was complete (tau == threshold: output in raster order,
-// extracter.py:217).  Anything else is flagged for the round-faithful kernel (kb_nms.cu).
+// A map is certified when it produced more than top_k interior survivors (K > top_k: rows sorted by
+// priority) or when its candidate lists were complete (K <= top_k: raster order, extracter.py:217).
+// Anything else (negative scores, list overflow, nms_dist > 8) is flagged on the device for the
+// round-faithful kernel (kb_nms.cu), so results are exact in all cases.
 #include "kb_common.cuh"
 
 namespace kbsparse {
 
 constexpr int SAMPLES = 4096;
 constexpr int TAU_NT = 256;
-constexpr int EX_NT = 256;
-constexpr int GR_NT = 1024;
+constexpr int DTH = 32, DTW = 128, DNT = 256;     // round-1 tile
+constexpr int SP_NT = 1024;                       // sparse kernel threads
+constexpr int MAX_CELLS = 8192;
+constexpr int LIST_CAP = 16384;                   // entries per list and map
+constexpr int SMEM_CAP = 12288;                   // candidates resolved in shared memory per map
 
 struct SparseParams {
     const float* score;       // [B,H,W]
     float* tau;               // [B]
-    int* cand_count;          // [B]
-    uint64_t* cand;           // [B,cap]
+    uint64_t* listM;          // [B,LIST_CAP] round-1 maxima above tau
+    uint64_t* listO;          // [B,LIST_CAP] uncovered pixels above tau
+    int* cntM;                // [B]
+    int* cntO;                // [B]
     int* flags;               // [B] bit0: has negative score
     int* need_fallback;       // [B] (out) 1 = run the round-faithful path for this map
     int* any_fallback;        // [1]
@@ -39,124 +52,278 @@ struct SparseParams {
     int* raster;              // [B,top_k]
     int* count;               // [B]
     int* path;                // [B] or null
-    int B, H, W, r, border, top_k, cap, c_target;
+    int B, H, W, r, border, top_k, c_pix;
+    int cell_shift, gw, gh;   // coarse grid of the sparse stage
     float threshold, min_score;
 };
 
 // ------------------------------------------------------------------------------------------------
+// tau: the rank-th largest of 4096 sampled pixels (bitwise counting select, no atomics)
 __global__ void __launch_bounds__(TAU_NT) tau_kernel(SparseParams p) {
-    __shared__ uint32_t s_keys[SAMPLES];
-    __shared__ int s_hist[256];
-    __shared__ uint32_t s_prefix, s_mask;
-    __shared__ int s_need;
+    __shared__ int s_part[TAU_NT / 32];
     const int b = blockIdx.x;
     const long long npx = (long long)p.H * p.W;
     const float theta = fmaxf(p.threshold, 0.0f);
-    if (threadIdx.x == 0) { p.cand_count[b] = 0; p.flags[b] = 0; p.need_fallback[b] = 0; }
+    if (threadIdx.x == 0) { p.cntM[b] = 0; p.cntO[b] = 0; p.flags[b] = 0; p.need_fallback[b] = 0; }
     if (b == 0 && threadIdx.x == 0) *p.any_fallback = 0;
-    // rank of the sample that estimates the C_target-th largest pixel
-    const long long rank = ((long long)p.c_target * SAMPLES + npx - 1) / npx;
-    if (npx <= SAMPLES || rank >= SAMPLES / 2) {        // small map / dense request: take everything
+    const long long rank = ((long long)p.c_pix * SAMPLES + npx - 1) / npx;
+    if (npx <= 4 * SAMPLES || rank >= SAMPLES / 2) {        // small map / dense request: list everything
         if (threadIdx.x == 0) p.tau[b] = theta;
         return;
     }
     const float* img = p.score + (size_t)b * npx;
-    const long long stride = npx / SAMPLES;
-    for (int k = threadIdx.x; k < SAMPLES; k += TAU_NT) {
-        uint32_t h = (uint32_t)k * 2654435761u;
+    constexpr int PER = SAMPLES / TAU_NT;                   // 16 keys per thread
+    constexpr int RUN = 32;                                 // floats per contiguous run
+    const long long n_runs = SAMPLES / RUN, stride = npx / n_runs;
+    uint32_t keys[PER];
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const int k = i * TAU_NT + threadIdx.x;             // sample index: run = k / 32, element = k % 32
+        const int run = k / RUN, el = k % RUN;
+        uint32_t h = (uint32_t)run * 2654435761u;
         h ^= h >> 15;
-        const long long idx = (long long)k * stride + (long long)(h % (uint32_t)stride);
-        s_keys[k] = kb::float_order_key(img[idx]);
+        long long start = (long long)run * stride + (long long)(h % (uint32_t)(stride - RUN + 1));
+        keys[i] = kb::float_order_key(__ldg(img + start + el));
     }
-    if (threadIdx.x == 0) { s_prefix = 0u; s_mask = 0u; s_need = (int)rank; }
-    __syncthreads();
-    for (int shift = 24; shift >= 0; shift -= 8) {
-        s_hist[threadIdx.x] = 0;
+    uint32_t v = 0u;
+    for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t t = v | (1u << bit);
+        int c = 0;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) c += keys[i] >= t ? 1 : 0;
+        c = __reduce_add_sync(0xffffffffu, c);
+        if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = c;
         __syncthreads();
-        const uint32_t pre = s_prefix, msk = s_mask;
-        for (int k = threadIdx.x; k < SAMPLES; k += TAU_NT) {
-            const uint32_t key = s_keys[k];
-            if ((key & msk) == pre) atomicAdd(&s_hist[(key >> shift) & 255u], 1);
-        }
+        int tot = 0;
+#pragma unroll
+        for (int w = 0; w < TAU_NT / 32; ++w) tot += s_part[w];
         __syncthreads();
-        if (threadIdx.x == 0) {
-            int need = s_need, cum = 0, d = 255;
-            for (; d > 0; --d) {
-                if (cum + s_hist[d] >= need) break;
-                cum += s_hist[d];
-            }
-            s_need = need - cum;
-            s_prefix = pre | ((uint32_t)d << shift);
-            s_mask = msk | (255u << shift);
-        }
-        __syncthreads();
+        if (tot >= (int)rank) v = t;
     }
     if (threadIdx.x == 0) {
-        const float t = kb::float_from_order_key(s_prefix);
-        p.tau[b] = (t > theta) ? t : theta;             // NaN-safe: falls back to theta
+        const float t = kb::float_from_order_key(v);
+        p.tau[b] = (t > theta) ? t : theta;                 // NaN-safe: falls back to theta
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// Streaming candidate extraction.  grid = (chunks per map, B); every thread owns 4 consecutive floats
-// per iteration (float4 when the map's byte offset allows it).
-constexpr int EX_ITEMS = 4;
-constexpr int EX_CHUNK = EX_NT * EX_ITEMS * 8;      // floats per CTA
+// window maximum of W consecutive entries starting at v[i], from precomputed power-of-two maxima
+template <int W>
+__device__ __forceinline__ float win_from(const float* p1, const float* p2, const float* p4, const float* p8,
+                                          const float* p16, int i) {
+    float res = -1.0f;                 // scores are >= 0 on this path (zero padding included)
+    int pos = i;
+    if (W & 16) { res = fmaxf(res, p16[pos]); pos += 16; }
+    if (W & 8) { res = fmaxf(res, p8[pos]); pos += 8; }
+    if (W & 4) { res = fmaxf(res, p4[pos]); pos += 4; }
+    if (W & 2) { res = fmaxf(res, p2[pos]); pos += 2; }
+    if (W & 1) { res = fmaxf(res, p1[pos]); }
+    return res;
+}
 
-__global__ void __launch_bounds__(EX_NT) extract_kernel(SparseParams p) {
-    const int b = blockIdx.y;
-    const long long npx = (long long)p.H * p.W;
-    const float* img = p.score + (size_t)b * npx;
+// out[i] = max(v[i .. i+W-1]) for i in [0, N_OUT); v has N_OUT + W - 1 entries (all in registers)
+template <int W, int N_OUT>
+__device__ __forceinline__ void window_max(const float (&v)[N_OUT + W - 1], float (&out)[N_OUT]) {
+    constexpr int N = N_OUT + W - 1;
+    float p2[N], p4[N], p8[N], p16[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) { p2[i] = v[i]; p4[i] = v[i]; p8[i] = v[i]; p16[i] = v[i]; }
+    if (W >= 2) {
+#pragma unroll
+        for (int i = 0; i + 1 < N; ++i) p2[i] = fmaxf(v[i], v[i + 1]);
+    }
+    if (W >= 4) {
+#pragma unroll
+        for (int i = 0; i + 3 < N; ++i) p4[i] = fmaxf(p2[i], p2[i + 2]);
+    }
+    if (W >= 8) {
+#pragma unroll
+        for (int i = 0; i + 7 < N; ++i) p8[i] = fmaxf(p4[i], p4[i + 4]);
+    }
+    if (W >= 16) {
+#pragma unroll
+        for (int i = 0; i + 15 < N; ++i) p16[i] = fmaxf(p8[i], p8[i + 8]);
+    }
+#pragma unroll
+    for (int i = 0; i < N_OUT; ++i) out[i] = win_from<W>(v, p2, p4, p8, p16, i);
+}
+
+template <int R>
+struct Tile {
+    static constexpr int SH = DTH + 4 * R, SW = DTW + 4 * R;      // staged scores (halo 2R)
+    static constexpr int SP = SW | 1;                             // odd pitch
+    static constexpr int MH = DTH + 2 * R, MW = DTW + 2 * R;      // region whose round-1 maxima matter
+    static constexpr int HP = MW | 1;                             // pitch of the row-maximum array
+    static constexpr int MWW = (MW + 31) / 32;                    // mask words per row
+    // strip lengths sized so that the row pass is <= 3 rounds of the 256 threads and the column pass
+    // <= 2 rounds of the 8 warps
+    static constexpr int ROW_STRIPS = (3 * DNT) / SH;
+    static constexpr int XS = (MW + ROW_STRIPS - 1) / ROW_STRIPS; // outputs per row strip
+    static constexpr int COL_STRIPS = (2 * DNT / 32) / MWW;
+    static constexpr int YS = (MH + COL_STRIPS - 1) / COL_STRIPS; // outputs per column strip
+    static constexpr size_t smem_bytes() {
+        return (size_t)(SH * SP + SH * HP) * 4 + (size_t)(2 * MH + DTH) * MWW * 4 + 64;
+    }
+};
+
+template <int R>
+__global__ void __launch_bounds__(DNT) round1_kernel(SparseParams p) {
+    using T = Tile<R>;
+    constexpr int W = 2 * R + 1;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* S = reinterpret_cast<float*>(smem_raw);                // [SH][SP]
+    float* HF = S + T::SH * T::SP;                                // [SH][HP] row-window maxima
+    uint32_t* MB = reinterpret_cast<uint32_t*>(HF + T::SH * T::HP);   // [MH][MWW] round-1 maxima bits
+    uint32_t* DB = MB + T::MH * T::MWW;                           // [MH][MWW] horizontally dilated
+    uint32_t* CB = DB + T::MH * T::MWW;                           // [DTH][MWW] coverage
+    __shared__ int s_scan[33];
+    __shared__ int s_base[2];
+
+    const int b = blockIdx.z;
+    const int y0 = blockIdx.y * DTH, x0 = blockIdx.x * DTW;
+    const int H = p.H, Wd = p.W;
+    const float* img = p.score + (size_t)b * H * Wd;
     const float tau = p.tau[b];
-    uint64_t* out = p.cand + (size_t)b * p.cap;
-    const bool vec_ok = ((reinterpret_cast<uintptr_t>(img) & 15u) == 0);
-    const long long base0 = (long long)blockIdx.x * EX_CHUNK;
-    bool neg = false;
-    const int lane = threadIdx.x & 31;
-#pragma unroll 2
-    for (int it = 0; it < 8; ++it) {
-        const long long i0 = base0 + ((long long)it * EX_NT + threadIdx.x) * EX_ITEMS;
-        float v[4] = {0.f, 0.f, 0.f, 0.f};
-        int nvalid = 0;
-        if (i0 + 3 < npx && vec_ok) {
-            const float4 q = __ldcs(reinterpret_cast<const float4*>(img + i0));
-            v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
-            nvalid = 4;
-        } else if (i0 < npx) {
-            nvalid = (int)((npx - i0) < 4 ? (npx - i0) : 4);
-            for (int e = 0; e < nvalid; ++e) v[e] = __ldcs(img + i0 + e);
-        }
-        int c = 0;
-        unsigned hit = 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    // ---- stage the tile with a 2R halo (zero padding, extracter.py:58) -------------------------
+    for (int i = threadIdx.x; i < T::SH * T::SW; i += DNT) {
+        const int sy = i / T::SW, sx = i - sy * T::SW;
+        const int gy = y0 + sy - 2 * R, gx = x0 + sx - 2 * R;
+        float val = 0.0f;
+        if (gy >= 0 && gy < H && gx >= 0 && gx < Wd) val = __ldg(img + (size_t)gy * Wd + gx);
+        S[sy * T::SP + sx] = val;
+    }
+    __syncthreads();
+
+    // ---- row pass: HF[sy][mx] = max S[sy][mx .. mx+2R]  (mx in region coordinates) --------------
+    {
+        constexpr int STRIPS = (T::MW + T::XS - 1) / T::XS;
+        for (int task = threadIdx.x; task < T::SH * STRIPS; task += DNT) {
+            const int sy = task % T::SH, strip = task / T::SH;     // adjacent threads -> adjacent rows (odd pitch)
+            const int mx0 = strip * T::XS;
+            float v[T::XS + W - 1];
+            const float* row = S + sy * T::SP + mx0;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const bool ok = e < nvalid;
-            neg |= ok && (v[e] < 0.0f);
-            if (ok && v[e] > tau) { hit |= 1u << e; ++c; }
-        }
-        // warp-aggregated append (order inside the list is irrelevant: it is sorted later)
-        int inc = c;
+            for (int i = 0; i < T::XS + W - 1; ++i) v[i] = (mx0 + i < T::SW) ? row[i] : 0.0f;
+            float out[T::XS];
+            window_max<W, T::XS>(v, out);
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, inc, d);
-            if (lane >= d) inc += t;
+            for (int i = 0; i < T::XS; ++i)
+                if (mx0 + i < T::MW) HF[sy * T::HP + mx0 + i] = out[i];
         }
-        const int wtot = __shfl_sync(0xffffffffu, inc, 31);
-        if (wtot) {
-            int wbase = 0;
-            if (lane == 31) wbase = atomicAdd(&p.cand_count[b], wtot);
-            wbase = __shfl_sync(0xffffffffu, wbase, 31);
-            int off = wbase + inc - c;
+    }
+    __syncthreads();
+
+    // ---- column pass + first-of-ties rule + ballot into the maxima mask -------------------------
+    {
+        constexpr int CG = T::MWW;                                 // 32-column groups
+        constexpr int STRIPS = (T::MH + T::YS - 1) / T::YS;
+        for (int task = warp; task < CG * STRIPS; task += DNT / 32) {
+            const int cgp = task % CG, strip = task / CG;
+            const int mx = cgp * 32 + lane, my0 = strip * T::YS;
+            const bool col_ok = mx < T::MW;
+            float v[T::YS + W - 1];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                if (hit & (1u << e)) {
-                    if (off < p.cap) out[off] = kb::priority_key(v[e], (uint32_t)(i0 + e));
-                    ++off;
+            for (int i = 0; i < T::YS + W - 1; ++i)
+                v[i] = (col_ok && my0 + i < T::SH) ? HF[(my0 + i) * T::HP + mx] : 0.0f;
+            float wm[T::YS];
+            window_max<W, T::YS>(v, wm);
+            // maximum over the R rows above (full-width windows): entries EARLIER in raster order
+            float vu[T::YS + R - 1], up[T::YS];
+#pragma unroll
+            for (int i = 0; i < T::YS + R - 1; ++i) vu[i] = v[i];
+            window_max<R, T::YS>(vu, up);
+#pragma unroll
+            for (int i = 0; i < T::YS; ++i) {
+                const int my = my0 + i;
+                bool is_max = false;
+                if (col_ok && my < T::MH) {
+                    const int sy = my + R, sx = mx + R;
+                    const float c = S[sy * T::SP + sx];
+                    if (c > 0.0f && c == wm[i] && c > up[i]) {
+                        // c equals the window maximum and beats every row above: it is THE maximum unless
+                        // an equal entry sits to its left (torch.argmax returns the first, extracter.py:69-70)
+                        const float* rr = S + sy * T::SP + sx;
+                        float left = -1.0f;
+#pragma unroll
+                        for (int dx = 1; dx <= R; ++dx) left = fmaxf(left, rr[-dx]);
+                        is_max = c > left;
+                    }
                 }
+                const unsigned wbits = __ballot_sync(0xffffffffu, is_max);
+                if (lane == 0 && my < T::MH) MB[my * T::MWW + cgp] = wbits;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- dilation of the maxima mask by R: rows, then columns -----------------------------------
+    for (int i = threadIdx.x; i < T::MH * T::MWW; i += DNT) {
+        const int my = i / T::MWW, w = i - my * T::MWW;
+        const uint32_t cur = MB[i];
+        const uint32_t prev = w > 0 ? MB[i - 1] : 0u;
+        const uint32_t next = w + 1 < T::MWW ? MB[i + 1] : 0u;
+        uint32_t acc = cur;
+#pragma unroll
+        for (int d = 1; d <= R; ++d)
+            acc |= (cur << d) | (prev >> (32 - d)) | (cur >> d) | (next << (32 - d));
+        DB[i] = acc;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < DTH * T::MWW; i += DNT) {
+        const int y = i / T::MWW, w = i - y * T::MWW;
+        uint32_t acc = 0u;
+#pragma unroll
+        for (int d = 0; d <= 2 * R; ++d) acc |= DB[(y + d) * T::MWW + w];
+        CB[i] = acc;
+    }
+    __syncthreads();
+
+    // ---- emission: round-1 maxima and uncovered pixels above tau --------------------------------
+    constexpr int PER = DTH * DTW / DNT;                           // 16 pixels per thread
+    uint32_t hitM = 0u, hitO = 0u;
+    bool neg = false;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const int pix = i * DNT + threadIdx.x;
+        const int y = pix / DTW, x = pix % DTW;
+        const int gy = y0 + y, gx = x0 + x;
+        if (gy < H && gx < Wd) {
+            const float s = S[(y + 2 * R) * T::SP + x + 2 * R];
+            neg |= s < 0.0f;
+            if (s > tau) {
+                const int mx = x + R;
+                const bool m1 = (MB[(y + R) * T::MWW + (mx >> 5)] >> (mx & 31)) & 1u;
+                const bool cov = (CB[y * T::MWW + (mx >> 5)] >> (mx & 31)) & 1u;
+                if (m1) hitM |= 1u << i;
+                else if (!cov) hitO |= 1u << i;
             }
         }
     }
     if (__any_sync(0xffffffffu, neg) && lane == 0) atomicOr(&p.flags[b], 1);
+    const int nM = __popc(hitM), nO = __popc(hitO);
+    int tot;
+    const int packed = kb::block_exclusive_scan(nM | (nO << 16), s_scan, &tot);
+    if (threadIdx.x == 0) {
+        s_base[0] = (tot & 0xffff) ? atomicAdd(&p.cntM[b], tot & 0xffff) : 0;
+        s_base[1] = (tot >> 16) ? atomicAdd(&p.cntO[b], tot >> 16) : 0;
+    }
+    __syncthreads();
+    int offM = s_base[0] + (packed & 0xffff), offO = s_base[1] + (packed >> 16);
+    uint64_t* outM = p.listM + (size_t)b * LIST_CAP;
+    uint64_t* outO = p.listO + (size_t)b * LIST_CAP;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        if ((hitM | hitO) & (1u << i)) {
+            const int pix = i * DNT + threadIdx.x;
+            const int y = pix / DTW, x = pix % DTW;
+            const float s = S[(y + 2 * R) * T::SP + x + 2 * R];
+            const uint64_t key = kb::priority_key(s, (uint32_t)((y0 + y) * Wd + x0 + x));
+            if (hitM & (1u << i)) { if (offM < LIST_CAP) outM[offM] = key; ++offM; }
+            else { if (offO < LIST_CAP) outO[offO] = key; ++offO; }
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -172,7 +339,7 @@ __device__ __forceinline__ void emit(const SparseParams& p, int b, int slot, flo
 __device__ void bitonic_desc(uint64_t* a, int n) {
     for (int k = 2; k <= n; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < n; i += GR_NT) {
+            for (int i = threadIdx.x; i < n; i += SP_NT) {
                 const int l = i ^ j;
                 if (l > i) {
                     const uint64_t x = a[i], y = a[l];
@@ -185,169 +352,254 @@ __device__ void bitonic_desc(uint64_t* a, int n) {
     }
 }
 
-constexpr uint32_t ST_DEAD = 0u, ST_UNDEC = 1u, ST_KEPT = 2u;
+__device__ __forceinline__ int block_sum(int v, int* s_part) {
+    v = __reduce_add_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = v;
+    __syncthreads();
+    int tot = 0;
+#pragma unroll
+    for (int w = 0; w < SP_NT / 32; ++w) tot += s_part[w];
+    __syncthreads();
+    return tot;
+}
 
-__global__ void __launch_bounds__(GR_NT, 1) greedy_kernel(SparseParams p, int maxc /*pow2*/) {
+constexpr uint8_t ST_DEAD = 0, ST_UNDEC = 1, ST_KEPT = 2;
+
+__global__ void __launch_bounds__(SP_NT, 1) sparse_kernel(SparseParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);                   // [SMEM_CAP]
+    uint32_t* pos = reinterpret_cast<uint32_t*>(keys + SMEM_CAP);             // [SMEM_CAP] y << 16 | x
+    uint32_t* cstart = pos + SMEM_CAP;                                        // [MAX_CELLS + 1]
+    uint16_t* items = reinterpret_cast<uint16_t*>(cstart + MAX_CELLS + 1);    // [SMEM_CAP] cell-sorted candidate ids
+    volatile uint8_t* state = reinterpret_cast<volatile uint8_t*>(items + SMEM_CAP);   // [SMEM_CAP]
+    __shared__ int s_scan[33];
+    __shared__ int s_part[SP_NT / 32];
+
     const int b = blockIdx.x;
     const int H = p.H, W = p.W, r = p.r;
-    const int Ww = (W + 31) >> 5;
-    uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);
-    uint32_t* bitmap = reinterpret_cast<uint32_t*>(keys + maxc);
-    uint32_t* chunk = bitmap + (size_t)H * Ww;             // GR_NT packed (state<<30 | y<<15 | x)
-    __shared__ int s_scan[33];
-
-    const int total = p.cand_count[b];
-    const bool neg = (p.flags[b] & 1) != 0;
-    if (neg || total > maxc || total > p.cap) {
+    auto fallback = [&]() {
         if (threadIdx.x == 0) { p.need_fallback[b] = 1; atomicExch(p.any_fallback, 1); }
-        return;
-    }
-    const int c = total;
-    const uint64_t* src = p.cand + (size_t)b * p.cap;
-    int n2 = 1;
-    while (n2 < c) n2 <<= 1;
-    for (int i = threadIdx.x; i < n2; i += GR_NT) keys[i] = (i < c) ? src[i] : 0ull;
-    for (int i = threadIdx.x; i < H * Ww; i += GR_NT) bitmap[i] = 0u;
-    __syncthreads();
-    bitonic_desc(keys, n2);
-
-    int n_emit = 0;     // interior survivors so far, compacted in priority order into keys[0..n_emit)
-    for (int base = 0; base < c && n_emit <= p.top_k; base += GR_NT) {
-        const int i = base + threadIdx.x;
-        const bool valid = i < c;
-        uint64_t key = 0ull;
-        int x = 0, y = 0;
-        bool alive = false;
-        if (valid) {
-            key = keys[i];
-            const uint32_t ras = kb::key_raster(key);
-            y = ras / W;
-            x = ras - y * W;
-            // any survivor of an earlier step within Chebyshev distance r?
-            const int xl = max(x - r, 0), xh = min(x + r, W - 1);
-            const int wl = xl >> 5, wh = xh >> 5;
-            const uint32_t ml = 0xffffffffu << (xl & 31);
-            const uint32_t mh = 0xffffffffu >> (31 - (xh & 31));
-            uint32_t any = 0u;
-            const int yl = max(y - r, 0), yh = min(y + r, H - 1);
-            for (int yy = yl; yy <= yh; ++yy) {
-                const uint32_t* row = bitmap + yy * Ww;
-                if (wl == wh) {
-                    any |= row[wl] & ml & mh;
-                } else {
-                    any |= (row[wl] & ml) | (row[wh] & mh);
-                    for (int w = wl + 1; w < wh; ++w) any |= row[w];
-                }
-            }
-            alive = (any == 0u);
-        }
-        chunk[threadIdx.x] = ((alive ? ST_UNDEC : ST_DEAD) << 30) | ((uint32_t)y << 15) | (uint32_t)x;
-        __syncthreads();
-        // conflicts with higher-priority candidates of the same step (rare: record up to 4, rescan if more)
-        int conf[4] = {-1, -1, -1, -1};
-        int nconf = 0;
-        if (alive) {
-            for (int j = 0; j < (int)threadIdx.x; ++j) {
-                const uint32_t o = chunk[j];
-                if ((o >> 30) == ST_DEAD) continue;
-                const int ox = (int)(o & 0x7fffu), oy = (int)((o >> 15) & 0x7fffu);
-                if (abs(ox - x) <= r && abs(oy - y) <= r) {
-                    if (nconf < 4) conf[nconf] = j;
-                    ++nconf;
-                }
-            }
-        }
-        uint32_t st = alive ? ST_UNDEC : ST_DEAD;
-        // fixed-point loop: a candidate is kept once every conflicting earlier candidate is dead
-        while (true) {
-            uint32_t nst = st;
-            if (st == ST_UNDEC) {
-                bool blocked = false, wait = false;
-                if (nconf <= 4) {
-                    for (int q = 0; q < nconf; ++q) {
-                        const uint32_t s = chunk[conf[q]] >> 30;
-                        blocked |= (s == ST_KEPT);
-                        wait |= (s == ST_UNDEC);
-                    }
-                } else {
-                    for (int j = 0; j < (int)threadIdx.x; ++j) {
-                        const uint32_t o = chunk[j];
-                        const uint32_t s = o >> 30;
-                        if (s == ST_DEAD) continue;
-                        const int ox = (int)(o & 0x7fffu), oy = (int)((o >> 15) & 0x7fffu);
-                        if (abs(ox - x) <= r && abs(oy - y) <= r) {
-                            blocked |= (s == ST_KEPT);
-                            wait |= (s == ST_UNDEC);
-                        }
-                    }
-                }
-                nst = blocked ? ST_DEAD : (wait ? ST_UNDEC : ST_KEPT);
-            }
-            __syncthreads();
-            if (nst != st) chunk[threadIdx.x] = (nst << 30) | ((uint32_t)y << 15) | (uint32_t)x;
-            st = nst;
-            if (!__syncthreads_or(st == ST_UNDEC)) break;
-        }
-        const bool kept = (st == ST_KEPT);
-        if (kept) atomicOr(&bitmap[y * Ww + (x >> 5)], 1u << (x & 31));
-        const bool interior = kept && x >= p.border && x < W - p.border && y >= p.border && y < H - p.border;
-        int tot;
-        const int off = n_emit + kb::block_exclusive_scan(interior ? 1 : 0, s_scan, &tot);
-        if (interior) keys[off] = key;          // off <= i: never clobbers an unread candidate
-        n_emit += tot;
-        __syncthreads();
-    }
-
+    };
+    const int nM = p.cntM[b], nO = p.cntO[b];
+    if ((p.flags[b] & 1) || nM > LIST_CAP || nO > LIST_CAP) { fallback(); return; }
+    const uint64_t* LM = p.listM + (size_t)b * LIST_CAP;
+    const uint64_t* LO = p.listO + (size_t)b * LIST_CAP;
     const float theta = fmaxf(p.threshold, 0.0f);
-    const bool complete = (p.tau[b] == theta) && (p.threshold >= 0.0f);
-    if (n_emit > p.top_k) {
-        // K > top_k: rows sorted by score descending (extracter.py:217-218), canonical tie order
-        int cnt = 0;
-        for (int i = threadIdx.x; i < p.top_k; i += GR_NT) {
-            const uint64_t key = keys[i];
-            const float sc = kb::key_score(key);
-            // rows with score <= min_score form a suffix of the sorted list (extracter.py:219-220)
-            if (!(p.min_score > 0.0f) || sc > p.min_score) { emit(p, b, i, sc, kb::key_raster(key)); ++cnt; }
-        }
-        int tot;
-        kb::block_exclusive_scan(cnt, s_scan, &tot);
-        if (threadIdx.x == 0) { p.count[b] = tot; if (p.path) p.path[b] = 1; }
-    } else if (complete) {
-        // K <= top_k: raster order (extracter.py:217), then the min_score filter (extracter.py:219-220)
-        int n2b = 1;
-        while (n2b < n_emit) n2b <<= 1;
-        for (int i = threadIdx.x; i < n2b; i += GR_NT) {
-            uint64_t k2 = 0ull;
-            if (i < n_emit) {
-                const uint64_t key = keys[i];
-                k2 = ((uint64_t)(0xffffffffu - kb::key_raster(key)) << 32) | (key >> 32);
+    const bool lists_complete = (p.tau[b] == theta);
+
+    // The listing is exact for every pixel with score >= T for ANY cut T; try the cheapest cut first
+    // (the ~1.25*top_k best round-1 maxima), widen if it does not certify.
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        long long ksel = attempt == 0 ? (long long)p.top_k + p.top_k / 4 + 32
+                       : attempt == 1 ? 3LL * p.top_k + 64 : (long long)LIST_CAP + 1;
+        // ---- cut: score key of the ksel-th largest round-1 maximum (0 = take everything) -------
+        uint32_t tkey = 0u;
+        if ((long long)nM > ksel) {
+            constexpr int PER = LIST_CAP / SP_NT;                 // 16
+            uint32_t k32[PER];
+#pragma unroll
+            for (int i = 0; i < PER; ++i) {
+                const int idx = i * SP_NT + threadIdx.x;
+                k32[i] = idx < nM ? (uint32_t)(LM[idx] >> 32) : 0u;
             }
-            keys[i] = k2;
+            for (int bit = 31; bit >= 0; --bit) {
+                const uint32_t t = tkey | (1u << bit);
+                int c = 0;
+#pragma unroll
+                for (int i = 0; i < PER; ++i) c += k32[i] >= t ? 1 : 0;
+                if ((long long)block_sum(c, s_part) >= ksel) tkey = t;
+            }
+        }
+        const bool cut_complete = lists_complete && tkey == 0u;
+        // ---- load the candidates at or above the cut: maxima first, then the uncovered ones -----
+        int c = 0, cM = 0;
+        bool overflow = false;
+        for (int pass = 0; pass < 2; ++pass) {
+            const uint64_t* L = pass ? LO : LM;
+            const int n = pass ? nO : nM;
+            for (int base = 0; base < n; base += SP_NT) {
+                const int idx = base + threadIdx.x;
+                uint64_t key = 0ull;
+                bool take = false;
+                if (idx < n) { key = L[idx]; take = (uint32_t)(key >> 32) >= tkey; }
+                int tot;
+                const int off = c + kb::block_exclusive_scan(take ? 1 : 0, s_scan, &tot);
+                if (take && off < SMEM_CAP) {
+                    keys[off] = key;
+                    const uint32_t ras = kb::key_raster(key);
+                    const uint32_t y = ras / (uint32_t)W;
+                    pos[off] = (y << 16) | (ras - y * (uint32_t)W);
+                    state[off] = pass ? ST_UNDEC : ST_KEPT;
+                }
+                c += tot;
+                if (c > SMEM_CAP) { overflow = true; break; }
+            }
+            if (overflow) break;
+            if (pass == 0) cM = c;
         }
         __syncthreads();
-        bitonic_desc(keys, n2b);
-        int n_out = 0;
-        for (int base = 0; base < n_emit; base += GR_NT) {
-            const int i = base + threadIdx.x;
-            bool keep = false;
-            float sc = 0.f;
-            uint32_t ras = 0;
-            if (i < n_emit) {
-                const uint64_t k2 = keys[i];
-                ras = 0xffffffffu - (uint32_t)(k2 >> 32);
-                sc = kb::float_from_order_key((uint32_t)(k2 & 0xffffffffu));
-                keep = !(p.min_score > 0.0f) || sc > p.min_score;
+        if (overflow) { fallback(); return; }
+
+        // ---- coarse cell grid (counting sort of the candidates by cell) ---------------------------
+        const int n_cells = p.gw * p.gh;
+        for (int i = threadIdx.x; i <= n_cells; i += SP_NT) cstart[i] = 0u;
+        __syncthreads();
+        for (int i = threadIdx.x; i < c; i += SP_NT) {
+            const uint32_t q = pos[i];
+            const int cell = (int)((q >> 16) >> p.cell_shift) * p.gw + (int)((q & 0xffffu) >> p.cell_shift);
+            atomicAdd(&cstart[cell + 1], 1u);
+        }
+        __syncthreads();
+        {   // inclusive scan over cstart[1..n_cells] -> cstart[k] = first slot of cell k
+            constexpr int PERC = MAX_CELLS / SP_NT;               // 8
+            uint32_t loc[PERC];
+            int sum = 0;
+#pragma unroll
+            for (int i = 0; i < PERC; ++i) {
+                const int cell = threadIdx.x * PERC + i;
+                loc[i] = cell < n_cells ? cstart[cell + 1] : 0u;
+                sum += (int)loc[i];
             }
             int tot;
-            const int off = n_out + kb::block_exclusive_scan(keep ? 1 : 0, s_scan, &tot);
-            if (keep) emit(p, b, off, sc, ras);
-            n_out += tot;
+            int run = kb::block_exclusive_scan(sum, s_scan, &tot);
+#pragma unroll
+            for (int i = 0; i < PERC; ++i) {
+                const int cell = threadIdx.x * PERC + i;
+                if (cell < n_cells) cstart[cell + 1] = (uint32_t)run;     // start of this cell, shifted by one
+                run += (int)loc[i];
+            }
         }
-        if (threadIdx.x == 0) { p.count[b] = n_out; if (p.path) p.path[b] = 1; }
-    } else {
-        if (threadIdx.x == 0) { p.need_fallback[b] = 1; atomicExch(p.any_fallback, 1); }
+        __syncthreads();
+        // cstart[cell+1] holds the start of `cell`; bumping it while scattering leaves the start of cell+1
+        for (int i = threadIdx.x; i < c; i += SP_NT) {
+            const uint32_t q = pos[i];
+            const int cell = (int)((q >> 16) >> p.cell_shift) * p.gw + (int)((q & 0xffffu) >> p.cell_shift);
+            const uint32_t slot = atomicAdd(&cstart[cell + 1], 1u);
+            items[slot] = (uint16_t)i;
+        }
+        __syncthreads();
+        // now cell k occupies items[cstart[k] .. cstart[k+1])  (cstart[0] == 0)
+
+        // ---- keep / suppress decisions by priority -------------------------------------------------
+        while (true) {
+            int undecided = 0;
+            for (int i = cM + threadIdx.x; i < c; i += SP_NT) {
+                if (state[i] != ST_UNDEC) continue;
+                const uint32_t q = pos[i];
+                const int x = (int)(q & 0xffffu), y = (int)(q >> 16);
+                const uint64_t key = keys[i];
+                const int cx = x >> p.cell_shift, cy = y >> p.cell_shift;
+                const int cx0 = max(cx - 1, 0), cx1 = min(cx + 1, p.gw - 1);
+                bool blocked = false, wait = false;
+                for (int yy = max(cy - 1, 0); yy <= min(cy + 1, p.gh - 1) && !blocked; ++yy) {
+                    const uint32_t lo = cstart[yy * p.gw + cx0], hi = cstart[yy * p.gw + cx1 + 1];
+                    for (uint32_t t = lo; t < hi; ++t) {
+                        const int j = items[t];
+                        const uint32_t qj = pos[j];
+                        const int dx = (int)(qj & 0xffffu) - x, dy = (int)(qj >> 16) - y;
+                        if (dx > r || dx < -r || dy > r || dy < -r) continue;
+                        if (keys[j] <= key) continue;             // lower priority (or itself)
+                        const uint8_t sj = state[j];
+                        if (sj == ST_KEPT) { blocked = true; break; }
+                        wait |= (sj == ST_UNDEC);
+                    }
+                }
+                if (blocked) state[i] = ST_DEAD;
+                else if (!wait) state[i] = ST_KEPT;
+                else undecided = 1;
+            }
+            if (!__syncthreads_or(undecided)) break;
+        }
+
+        // ---- kept interior candidates, compacted to the front of keys[] ---------------------------
+        int n_ki = 0;
+        for (int base = 0; base < c; base += SP_NT) {
+            const int i = base + threadIdx.x;
+            bool interior = false;
+            uint64_t key = 0ull;
+            if (i < c && state[i] == ST_KEPT) {
+                const uint32_t q = pos[i];
+                const int x = (int)(q & 0xffffu), y = (int)(q >> 16);
+                interior = x >= p.border && x < W - p.border && y >= p.border && y < H - p.border;
+                key = keys[i];
+            }
+            int tot;
+            const int off = n_ki + kb::block_exclusive_scan(interior ? 1 : 0, s_scan, &tot);
+            if (interior) keys[off] = key;          // off <= i: never clobbers an unread candidate
+            n_ki += tot;
+        }
+        __syncthreads();
+
+        if (n_ki > p.top_k) {
+            // K > top_k: rows sorted by score descending (extracter.py:217-218), canonical tie order
+            int n2 = 1;
+            while (n2 < n_ki) n2 <<= 1;
+            for (int i = n_ki + threadIdx.x; i < n2; i += SP_NT) keys[i] = 0ull;
+            __syncthreads();
+            bitonic_desc(keys, n2);
+            int cnt = 0;
+            for (int i = threadIdx.x; i < p.top_k; i += SP_NT) {
+                const uint64_t key = keys[i];
+                const float sc = kb::key_score(key);
+                // rows with score <= min_score form a suffix of the sorted list (extracter.py:219-220)
+                if (!(p.min_score > 0.0f) || sc > p.min_score) { emit(p, b, i, sc, kb::key_raster(key)); ++cnt; }
+            }
+            const int tot = block_sum(cnt, s_part);
+            if (threadIdx.x == 0) { p.count[b] = tot; if (p.path) p.path[b] = 1; }
+            return;
+        }
+        if (cut_complete) {
+            // K <= top_k: raster order (extracter.py:217), then the min_score filter (extracter.py:219-220)
+            int n2b = 1;
+            while (n2b < n_ki) n2b <<= 1;
+            for (int i = threadIdx.x; i < n2b; i += SP_NT) {
+                uint64_t k2 = 0ull;
+                if (i < n_ki) {
+                    const uint64_t key = keys[i];
+                    k2 = ((uint64_t)(0xffffffffu - kb::key_raster(key)) << 32) | (key >> 32);
+                }
+                keys[i] = k2;
+            }
+            __syncthreads();
+            bitonic_desc(keys, n2b);
+            int n_out = 0;
+            for (int base = 0; base < n_ki; base += SP_NT) {
+                const int i = base + threadIdx.x;
+                bool keep = false;
+                float sc = 0.f;
+                uint32_t ras = 0;
+                if (i < n_ki) {
+                    const uint64_t k2 = keys[i];
+                    ras = 0xffffffffu - (uint32_t)(k2 >> 32);
+                    sc = kb::float_from_order_key((uint32_t)(k2 & 0xffffffffu));
+                    keep = !(p.min_score > 0.0f) || sc > p.min_score;
+                }
+                int tot;
+                const int off = n_out + kb::block_exclusive_scan(keep ? 1 : 0, s_scan, &tot);
+                if (keep) emit(p, b, off, sc, ras);
+                n_out += tot;
+            }
+            if (threadIdx.x == 0) { p.count[b] = n_out; if (p.path) p.path[b] = 1; }
+            return;
+        }
+        if (tkey == 0u) break;          // everything listed was used and it is still not enough
+        __syncthreads();
     }
+    fallback();
+}
+
+template <int R>
+static int launch_round1(const SparseParams& p, cudaStream_t st) {
+    const size_t smem = Tile<R>::smem_bytes();
+    KB_CUDA_TRY(cudaFuncSetAttribute(round1_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((p.W + DTW - 1) / DTW, (p.H + DTH - 1) / DTH, p.B);
+    round1_kernel<R><<<grid, DNT, smem, st>>>(p);
+    KB_LAUNCH_CHECK();
+    return KB_OK;
+}
+
+constexpr size_t sparse_smem_bytes() {
+    return (size_t)SMEM_CAP * 8 + (size_t)SMEM_CAP * 4 + (size_t)(MAX_CELLS + 1) * 4 + (size_t)SMEM_CAP * 2 + SMEM_CAP + 64;
 }
 
 }  // namespace kbsparse
@@ -356,34 +608,35 @@ __global__ void __launch_bounds__(GR_NT, 1) greedy_kernel(SparseParams p, int ma
 // host side (called from kb_detect in kb_select.cu)
 // ------------------------------------------------------------------------------------------------
 struct KbSparsePlan {
-    int maxc;          // candidate capacity per map (power of two), 0 = sparse path not applicable
-    int c_target;
-    size_t smem;
+    bool ok;
+    int cell_shift, gw, gh, c_pix;
 };
 
-KbSparsePlan kb_sparse_plan(int H, int W, int top_k) {
-    KbSparsePlan pl{0, 0, 0};
-    if (H >= 32768 || W >= 32768) return pl;
-    const size_t bitmap = (size_t)H * ((W + 31) / 32) * 4;
-    const size_t fixed = bitmap + kbsparse::GR_NT * 4 + 1024;
-    const size_t budget = 220 * 1024;
-    if (fixed + 2048 * 8 > budget) return pl;
-    int maxc = 2048;
-    while ((size_t)maxc * 2 * 8 + fixed <= budget && maxc < 16384 && maxc < 8 * top_k) maxc <<= 1;
-    if (maxc < top_k + 2) return pl;
-    pl.maxc = maxc;
-    long long ct = 4LL * top_k;
-    if (ct > (long long)maxc * 6 / 10) ct = (long long)maxc * 6 / 10;
-    if (ct < top_k + 2) ct = top_k + 2;
-    pl.c_target = (int)ct;
-    pl.smem = (size_t)maxc * 8 + fixed;
+static KbSparsePlan kb_sparse_plan(int H, int W, int nms_dist, int top_k) {
+    KbSparsePlan pl{false, 0, 0, 0, 0};
+    if (nms_dist < 1 || nms_dist > 8) return pl;
+    if (H >= 32768 || W >= 32768 || H < 1 || W < 1) return pl;
+    if (top_k < 1 || top_k + 1 > kbsparse::SMEM_CAP / 2) return pl;
+    int sh = 2;                                         // cell edge >= max(r, 4), a power of two
+    while ((1 << sh) < nms_dist) ++sh;
+    while ((long long)((W >> sh) + 1) * ((H >> sh) + 1) > kbsparse::MAX_CELLS) ++sh;
+    pl.cell_shift = sh;
+    pl.gw = (W >> sh) + 1;
+    pl.gh = (H >> sh) + 1;
+    long long cp = (long long)H * W / 12;               // pixels listed per map: ~1/12 of the map ...
+    const long long lo = 6LL * top_k, hi = 40000;       // ... at least 6*top_k, at most 40000
+    if (cp < lo) cp = lo;
+    if (cp > hi) cp = hi;
+    pl.c_pix = (int)cp;
+    pl.ok = true;
     return pl;
 }
 
-size_t kb_sparse_workspace_bytes(int B, int H, int W, int top_k) {
-    KbSparsePlan pl = kb_sparse_plan(H, W, top_k);
-    if (!pl.maxc) return 0;
-    return kb_align_up((size_t)B * pl.maxc * sizeof(uint64_t), 256) + 5 * kb_align_up((size_t)B * 4, 256) + 1024;
+bool kb_sparse_supported(int H, int W, int nms_dist, int top_k) { return kb_sparse_plan(H, W, nms_dist, top_k).ok; }
+
+size_t kb_sparse_workspace_bytes(int B, int H, int W, int nms_dist, int top_k) {
+    if (!kb_sparse_plan(H, W, nms_dist, top_k).ok) return 0;
+    return 2 * kb_align_up((size_t)B * kbsparse::LIST_CAP * sizeof(uint64_t), 256) + 7 * kb_align_up((size_t)B * 4, 256) + 1024;
 }
 
 // Runs the sparse path for all B maps.  need_fallback[B] / any_fallback[1] (device) report what is left.
@@ -391,31 +644,44 @@ int kb_sparse_detect(const float* score, int B, int H, int W, int nms_dist, int 
                      float min_score, int top_k, float* xyp, int* raster, int* count, int* path,
                      int** need_fallback_out, int** any_fallback_out, void* ws, size_t ws_bytes, cudaStream_t st) {
     using namespace kbsparse;
-    KbSparsePlan pl = kb_sparse_plan(H, W, top_k);
-    if (!pl.maxc) return KB_ERR_UNSUPPORTED;
+    const KbSparsePlan pl = kb_sparse_plan(H, W, nms_dist, top_k);
+    if (!pl.ok) return KB_ERR_UNSUPPORTED;
+    if (B > 65535) return KB_ERR_UNSUPPORTED;
     KbArena arena(ws, ws_bytes);
     SparseParams p;
-    p.cand = arena.take<uint64_t>((size_t)B * pl.maxc);
+    p.listM = arena.take<uint64_t>((size_t)B * LIST_CAP);
+    p.listO = arena.take<uint64_t>((size_t)B * LIST_CAP);
     p.tau = arena.take<float>(B);
-    p.cand_count = arena.take<int>(B);
+    p.cntM = arena.take<int>(B);
+    p.cntO = arena.take<int>(B);
     p.flags = arena.take<int>(B);
     p.need_fallback = arena.take<int>(B);
     p.any_fallback = arena.take<int>(1);
     if (!arena.ok()) return KB_ERR_WORKSPACE;
     p.score = score; p.xyp = xyp; p.raster = raster; p.count = count; p.path = path;
-    p.B = B; p.H = H; p.W = W; p.r = nms_dist; p.border = border; p.top_k = top_k; p.cap = pl.maxc;
-    p.c_target = pl.c_target; p.threshold = threshold; p.min_score = min_score;
+    p.B = B; p.H = H; p.W = W; p.r = nms_dist; p.border = border; p.top_k = top_k; p.c_pix = pl.c_pix;
+    p.cell_shift = pl.cell_shift; p.gw = pl.gw; p.gh = pl.gh;
+    p.threshold = threshold; p.min_score = min_score;
     *need_fallback_out = p.need_fallback;
     *any_fallback_out = p.any_fallback;
-    if (B > 65535) return KB_ERR_UNSUPPORTED;
     tau_kernel<<<B, TAU_NT, 0, st>>>(p);
     KB_LAUNCH_CHECK();
-    const long long npx = (long long)H * W;
-    dim3 grid((unsigned)((npx + EX_CHUNK - 1) / EX_CHUNK), B);
-    extract_kernel<<<grid, EX_NT, 0, st>>>(p);
-    KB_LAUNCH_CHECK();
-    KB_CUDA_TRY(cudaFuncSetAttribute(greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-    greedy_kernel<<<B, GR_NT, pl.smem, st>>>(p, pl.maxc);
+    int rc = KB_ERR_UNSUPPORTED;
+    switch (nms_dist) {
+        case 1: rc = launch_round1<1>(p, st); break;
+        case 2: rc = launch_round1<2>(p, st); break;
+        case 3: rc = launch_round1<3>(p, st); break;
+        case 4: rc = launch_round1<4>(p, st); break;
+        case 5: rc = launch_round1<5>(p, st); break;
+        case 6: rc = launch_round1<6>(p, st); break;
+        case 7: rc = launch_round1<7>(p, st); break;
+        case 8: rc = launch_round1<8>(p, st); break;
+        default: break;
+    }
+    if (rc != KB_OK) return rc;
+    const size_t smem = sparse_smem_bytes();
+    KB_CUDA_TRY(cudaFuncSetAttribute(sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sparse_kernel<<<B, SP_NT, smem, st>>>(p);
     KB_LAUNCH_CHECK();
     return KB_OK;
 }

@@ -376,3 +376,22 @@ def test_tensor_core_scores_stay_inside_the_certification_bound(n, m, dim, norme
     # and the reported best really is the maximum of the exact scores up to that bound
     t_all = a64 @ b64.transpose(1, 2) - 0.5 * (b64 * b64).sum(-1)[:, None, :]
     assert bool(((t_all.max(dim=2).values - t_exact) <= 2 * bound).all())
+
+
+def test_sampling_plane_staged_path_cfg2_shape():
+    """[.,256,60,80] maps with ~1000 keypoints take the plane-staged kernel; compare with the oracle and
+    with torch's own CUDA grid_sample (tolerance 1e-5, north_star)."""
+    gen = torch.Generator().manual_seed(21)
+    d = torch.randn(3, 256, 60, 80, generator=gen)
+    p = torch.rand(3, 1000, 3, generator=gen)
+    p[0, :5, :2] = torch.tensor([[0.0, 0.0], [1.0, 1.0], [1.0, 0.0], [-0.01, 0.5], [0.5, 1.02]])
+    cnt = torch.tensor([1000, 873, 1], dtype=torch.int32)
+    out = ops().sample_batched(d.to(DEV), p.to(DEV), cnt.to(DEV))
+    for b in range(3):
+        n = int(cnt[b])
+        grid = ((p[b, :n, :2] - 0.5) * 2)[None, None].to(DEV)
+        want = torch.nn.functional.grid_sample(d[b:b + 1].to(DEV), grid, align_corners=True)[0, :, 0].T
+        assert torch.allclose(out[b, :n], want, rtol=1e-5, atol=1e-5)
+        ref = ref_ops.sample_brute_force(d[b].numpy(), p[b, :n].numpy())
+        assert np.allclose(out[b, :n].cpu().numpy(), ref, rtol=1e-5, atol=1e-5)
+    assert float(out[1, 873:].abs().max()) == 0.0          # rows beyond the count stay untouched (zero)
