@@ -162,7 +162,7 @@ struct Tile {
     static constexpr int COL_STRIPS = (2 * DNT / 32) / MWW;
     static constexpr int YS = (MH + COL_STRIPS - 1) / COL_STRIPS; // outputs per column strip
     static constexpr size_t smem_bytes() {
-        return (size_t)(SH * SP + SH * HP) * 4 + (size_t)(2 * MH + DTH) * MWW * 4 + 64;
+        return (size_t)(SH * SP + SH * HP) * 4 + (size_t)(3 * MH + DTH) * MWW * 4 + 64;
     }
 };
 
@@ -176,6 +176,7 @@ __global__ void __launch_bounds__(DNT) round1_kernel(SparseParams p) {
     uint32_t* MB = reinterpret_cast<uint32_t*>(HF + T::SH * T::HP);   // [MH][MWW] round-1 maxima bits
     uint32_t* DB = MB + T::MH * T::MWW;                           // [MH][MWW] horizontally dilated
     uint32_t* CB = DB + T::MH * T::MWW;                           // [DTH][MWW] coverage
+    uint32_t* TB = CB + DTH * T::MWW;                             // [MH][MWW] score > tau
     __shared__ int s_scan[33];
     __shared__ int s_base[2];
 
@@ -186,13 +187,24 @@ __global__ void __launch_bounds__(DNT) round1_kernel(SparseParams p) {
     const float tau = p.tau[b];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-    // ---- stage the tile with a 2R halo (zero padding, extracter.py:58) -------------------------
-    for (int i = threadIdx.x; i < T::SH * T::SW; i += DNT) {
-        const int sy = i / T::SW, sx = i - sy * T::SW;
-        const int gy = y0 + sy - 2 * R, gx = x0 + sx - 2 * R;
-        float val = 0.0f;
-        if (gy >= 0 && gy < H && gx >= 0 && gx < Wd) val = __ldg(img + (size_t)gy * Wd + gx);
-        S[sy * T::SP + sx] = val;
+    // ---- stage the tile with a 2R halo (zero padding, extracter.py:58): one warp per row -------
+    {
+        constexpr int CH = (T::SW + 31) / 32;
+        const int gx_base = x0 - 2 * R + lane;
+        for (int sy = warp; sy < T::SH; sy += DNT / 32) {
+            const int gy = y0 + sy - 2 * R;
+            const bool row_ok = gy >= 0 && gy < H;
+            const float* grow = img + (size_t)(row_ok ? gy : 0) * Wd;
+            float val[CH];
+#pragma unroll
+            for (int k = 0; k < CH; ++k) {
+                const int gx = gx_base + 32 * k;
+                val[k] = (row_ok && gx >= 0 && gx < Wd) ? __ldg(grow + gx) : 0.0f;
+            }
+#pragma unroll
+            for (int k = 0; k < CH; ++k)
+                if (lane + 32 * k < T::SW) S[sy * T::SP + lane + 32 * k] = val[k];
+        }
     }
     __syncthreads();
 
@@ -216,6 +228,7 @@ __global__ void __launch_bounds__(DNT) round1_kernel(SparseParams p) {
     __syncthreads();
 
     // ---- column pass + first-of-ties rule + ballot into the maxima mask -------------------------
+    bool neg = false;
     {
         constexpr int CG = T::MWW;                                 // 32-column groups
         constexpr int STRIPS = (T::MH + T::YS - 1) / T::YS;
@@ -237,10 +250,12 @@ __global__ void __launch_bounds__(DNT) round1_kernel(SparseParams p) {
 #pragma unroll
             for (int i = 0; i < T::YS; ++i) {
                 const int my = my0 + i;
-                bool is_max = false;
+                bool is_max = false, hit = false;
                 if (col_ok && my < T::MH) {
                     const int sy = my + R, sx = mx + R;
                     const float c = S[sy * T::SP + sx];
+                    hit = c > tau;
+                    neg |= c < 0.0f;
                     if (c > 0.0f && c == wm[i] && c > up[i]) {
                         // c equals the window maximum and beats every row above: it is THE maximum unless
                         // an equal entry sits to its left (torch.argmax returns the first, extracter.py:69-70)
@@ -252,7 +267,8 @@ __global__ void __launch_bounds__(DNT) round1_kernel(SparseParams p) {
                     }
                 }
                 const unsigned wbits = __ballot_sync(0xffffffffu, is_max);
-                if (lane == 0 && my < T::MH) MB[my * T::MWW + cgp] = wbits;
+                const unsigned hbits = __ballot_sync(0xffffffffu, hit);
+                if (lane == 0 && my < T::MH) { MB[my * T::MWW + cgp] = wbits; TB[my * T::MWW + cgp] = hbits; }
             }
         }
     }
@@ -280,31 +296,24 @@ __global__ void __launch_bounds__(DNT) round1_kernel(SparseParams p) {
     }
     __syncthreads();
 
-    // ---- emission: round-1 maxima and uncovered pixels above tau --------------------------------
-    constexpr int PER = DTH * DTW / DNT;                           // 16 pixels per thread
-    uint32_t hitM = 0u, hitO = 0u;
-    bool neg = false;
-#pragma unroll
-    for (int i = 0; i < PER; ++i) {
-        const int pix = i * DNT + threadIdx.x;
-        const int y = pix / DTW, x = pix % DTW;
-        const int gy = y0 + y, gx = x0 + x;
-        if (gy < H && gx < Wd) {
-            const float s = S[(y + 2 * R) * T::SP + x + 2 * R];
-            neg |= s < 0.0f;
-            if (s > tau) {
-                const int mx = x + R;
-                const bool m1 = (MB[(y + R) * T::MWW + (mx >> 5)] >> (mx & 31)) & 1u;
-                const bool cov = (CB[y * T::MWW + (mx >> 5)] >> (mx & 31)) & 1u;
-                if (m1) hitM |= 1u << i;
-                else if (!cov) hitO |= 1u << i;
-            }
-        }
-    }
+    // ---- emission: round-1 maxima and uncovered pixels above tau, one 32-pixel mask word per thread
     if (__any_sync(0xffffffffu, neg) && lane == 0) atomicOr(&p.flags[b], 1);
-    const int nM = __popc(hitM), nO = __popc(hitO);
+    uint32_t emM = 0u, emO = 0u;
+    int ey = 0, ew = 0;
+    if (threadIdx.x < DTH * T::MWW) {
+        ey = threadIdx.x / T::MWW;
+        ew = threadIdx.x - ey * T::MWW;
+        // bits of this word that are output columns of THIS tile (region columns R .. R+DTW-1)
+        const int lo = max(R - 32 * ew, 0), hi = min(R + DTW - 32 * ew, 32);
+        uint32_t valid = 0u;
+        if (hi > lo) valid = (hi - lo == 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1u) << lo);
+        const uint32_t hitw = TB[(ey + R) * T::MWW + ew] & valid;      // pixels outside the image hold 0 <= tau
+        const uint32_t m1w = MB[(ey + R) * T::MWW + ew];
+        emM = hitw & m1w;
+        emO = hitw & ~m1w & ~CB[ey * T::MWW + ew];
+    }
     int tot;
-    const int packed = kb::block_exclusive_scan(nM | (nO << 16), s_scan, &tot);
+    const int packed = kb::block_exclusive_scan(__popc(emM) | (__popc(emO) << 16), s_scan, &tot);
     if (threadIdx.x == 0) {
         s_base[0] = (tot & 0xffff) ? atomicAdd(&p.cntM[b], tot & 0xffff) : 0;
         s_base[1] = (tot >> 16) ? atomicAdd(&p.cntO[b], tot >> 16) : 0;
@@ -313,16 +322,15 @@ __global__ void __launch_bounds__(DNT) round1_kernel(SparseParams p) {
     int offM = s_base[0] + (packed & 0xffff), offO = s_base[1] + (packed >> 16);
     uint64_t* outM = p.listM + (size_t)b * LIST_CAP;
     uint64_t* outO = p.listO + (size_t)b * LIST_CAP;
-#pragma unroll
-    for (int i = 0; i < PER; ++i) {
-        if ((hitM | hitO) & (1u << i)) {
-            const int pix = i * DNT + threadIdx.x;
-            const int y = pix / DTW, x = pix % DTW;
-            const float s = S[(y + 2 * R) * T::SP + x + 2 * R];
-            const uint64_t key = kb::priority_key(s, (uint32_t)((y0 + y) * Wd + x0 + x));
-            if (hitM & (1u << i)) { if (offM < LIST_CAP) outM[offM] = key; ++offM; }
-            else { if (offO < LIST_CAP) outO[offO] = key; ++offO; }
-        }
+    uint32_t both = emM | emO;
+    while (both) {
+        const int bit = __ffs(both) - 1;
+        both &= both - 1;
+        const int mx = 32 * ew + bit;                               // region column; tile column = mx - R
+        const float sc = S[(ey + 2 * R) * T::SP + mx + R];
+        const uint64_t key = kb::priority_key(sc, (uint32_t)((y0 + ey) * Wd + x0 + mx - R));
+        if (emM & (1u << bit)) { if (offM < LIST_CAP) outM[offM] = key; ++offM; }
+        else { if (offO < LIST_CAP) outO[offO] = key; ++offO; }
     }
 }
 
@@ -395,19 +403,22 @@ __global__ void __launch_bounds__(SP_NT, 1) sparse_kernel(SparseParams p) {
         // ---- cut: score key of the ksel-th largest round-1 maximum (0 = take everything) -------
         uint32_t tkey = 0u;
         if ((long long)nM > ksel) {
+            // (any cut is exact, so the 12 low bits of the score key are not resolved)
             constexpr int PER = LIST_CAP / SP_NT;                 // 16
+            const int per = (nM + SP_NT - 1) / SP_NT;
             uint32_t k32[PER];
 #pragma unroll
             for (int i = 0; i < PER; ++i) {
                 const int idx = i * SP_NT + threadIdx.x;
-                k32[i] = idx < nM ? (uint32_t)(LM[idx] >> 32) : 0u;
+                k32[i] = (i < per && idx < nM) ? (uint32_t)(LM[idx] >> 32) : 0u;
             }
-            for (int bit = 31; bit >= 0; --bit) {
+            for (int bit = 31; bit >= 12; --bit) {
                 const uint32_t t = tkey | (1u << bit);
                 int c = 0;
 #pragma unroll
-                for (int i = 0; i < PER; ++i) c += k32[i] >= t ? 1 : 0;
-                if ((long long)block_sum(c, s_part) >= ksel) tkey = t;
+                for (int i = 0; i < PER; ++i)
+                    if (i < per) c += __syncthreads_count(k32[i] >= t);
+                if ((long long)c >= ksel) tkey = t;
             }
         }
         const bool cut_complete = lists_complete && tkey == 0u;
