@@ -125,8 +125,9 @@ KB_API int kb_match_mnn(const float* d0, const float* d1, const int* n0, const i
                  int m_max, int D, double max_distance, int cross_check, int algo, int* pairs,
                  double* dist, int* count, void* ws, size_t ws_bytes, kb_stream_t stream);
 /* Diagnostics (tests only): byte offsets inside an algo=1 workspace after kb_match_mnn returned:
- * off[0] per-row (best, second, argbest, pad) of direction 0 (16 B records), off[1] same for
- * direction 1, off[2] int32 count of rows that needed the exact float64 rescan,
+ * off[0] records of direction 0: per row FOUR records (one per column slice of the epilogue) of 32 B
+ * (float best, second, third, pad; int argbest, argsecond, pad, pad), off[1] same for direction 1, off[2] int32[2] = rows that needed the exact float64 rescan,
+ * rows settled by the two-candidate exact check,
  * off[3]/off[4] float32 squared row norms of d0/d1. */
 KB_API int kb_match_tc_debug_offsets(int B, int n_max, int m_max, int D, size_t* off);
 

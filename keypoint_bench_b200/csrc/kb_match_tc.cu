@@ -19,21 +19,26 @@
 //                   otherwise the row is rescanned exactly in float64 (first of ties, as np.argmin).
 //   pairs_kernel    mutual check, strict < max_distance gate, ordered compaction (per pair).
 #include <cuda.h>
+#include <cstdlib>
 #include <cuda_bf16.h>
 #include <math_constants.h>
 #include "kb_common.cuh"
 
 namespace kbtc {
 
-constexpr int BM = 128, BN = 128, BK = 64;
+constexpr int BM = 128, BN = 256, BK = 64;       // BN = 256: one tcgen05.mma covers 128x256x16 (the issue rate of
+                                                 // a single thread, ~70 cycles, cannot feed N = 128 instructions)
 constexpr int TILE_BYTES = BM * BK * 2;          // 16 KB, one 128B-swizzled K-major tile
-constexpr int NSLOT = 6;
-constexpr int NT = 256;                          // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warps 4-7 epilogue
-constexpr int TMEM_COLS = 256;                   // two 128-column fp32 accumulators
+constexpr int MAX_SLOTS = 6;                     // ring depth is chosen on the host from the free shared memory
+constexpr int EPI_SLICES = 4;                    // column slices of a tile, one epilogue warp per (lane quadrant, slice)
+constexpr int EPI_WARPS = 4 * EPI_SLICES;        // 16 epilogue warps: four per SM sub-partition hide each other's latencies
+constexpr int NT = 128 + 32 * EPI_WARPS;         // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps 4-19 epilogue
+constexpr int TMEM_COLS = 512;                   // two 256-column fp32 accumulators (all of TMEM)
+constexpr int SLOT_BYTES = 2 * TILE_BYTES;       // one database block: 256 rows x 64 k (two TMA boxes)
 
-struct Top2 {
-    float best, second;
-    int idx, pad;
+struct Top2 {                 // per query row: three best scores, indices of the best two (32 bytes)
+    float best, second, third, pad0;
+    int idx, idx2, pad1, pad2;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -99,6 +104,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart (SBO=64), LBO=1,
@@ -123,41 +137,68 @@ struct PrepParams {
     int B, n_max, D, Dp, cs;
 };
 
+constexpr int PREP_ROWS = 4;          // rows per warp: independent 16-byte loads in flight
+
+// returns |row|^2 (all lanes)
+__device__ __forceinline__ float prep_finish_row(const PrepParams& p, int b, int row, float ss, int lane) {
+    for (int d = 16; d > 0; d >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, d);
+    if (lane == 0) {
+        p.c[(size_t)b * p.cs + row] = -0.5f * ss;
+        p.norm2[(size_t)b * p.n_max + row] = ss;
+    }
+    return ss;
+}
+
 __global__ void __launch_bounds__(256) prep_kernel(PrepParams p) {
     const int warp = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.y;
-    if (warp >= p.cs) return;
+    const int row0 = warp * PREP_ROWS;
+    __shared__ float s_max[8];
+    float wmax = 0.0f;                      // max |row|^2 over this warp's rows (one atomic per CTA, not per row)
     const int n = p.cnt ? p.cnt[b] : p.n_max;
-    const int row = warp;
-    if (row >= p.n_max) {                       // padding of the c array up to a whole column tile
-        if (lane == 0) p.c[(size_t)b * p.cs + row] = -CUDART_INF_F;
-        return;
-    }
-    __nv_bfloat16* out = p.S + ((size_t)b * p.n_max + row) * (2 * p.Dp);
-    if (row >= n) {
-        for (int k = lane; k < 2 * p.Dp; k += 32) out[k] = __float2bfloat16(0.0f);
-        if (lane == 0) { p.c[(size_t)b * p.cs + row] = -CUDART_INF_F; p.norm2[(size_t)b * p.n_max + row] = 0.0f; }
-        return;
-    }
-    const float* x = p.d + ((size_t)b * p.n_max + row) * p.D;
-    float ss = 0.0f;
-    if ((p.D & 3) == 0 && (reinterpret_cast<uintptr_t>(p.d) & 15u) == 0) {
-        // 4 components per lane and step: one 16-byte load, two 8-byte stores
+    const bool vec = (p.D & 3) == 0 && (reinterpret_cast<uintptr_t>(p.d) & 15u) == 0;
+    if (row0 >= p.cs) {
+        // nothing
+    } else if (vec && row0 + PREP_ROWS <= n) {
+        // fast path: four valid rows, 4 components per lane and step
+        const float* x = p.d + ((size_t)b * p.n_max + row0) * p.D;
+        __nv_bfloat16* out = p.S + ((size_t)b * p.n_max + row0) * (2 * p.Dp);
+        float ss[PREP_ROWS] = {0.f, 0.f, 0.f, 0.f};
         for (int k = 4 * lane; k < p.Dp; k += 128) {
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (k < p.D) v = __ldg(reinterpret_cast<const float4*>(x + k));
-            const float f[4] = {v.x, v.y, v.z, v.w};
-            __nv_bfloat16 h[4], l[4];
+            float4 v[PREP_ROWS];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                h[e] = __float2bfloat16_rn(f[e]);
-                l[e] = __float2bfloat16_rn(f[e] - __bfloat162float(h[e]));
-                ss = fmaf(f[e], f[e], ss);
+            for (int r = 0; r < PREP_ROWS; ++r)
+                v[r] = k < p.D ? __ldg(reinterpret_cast<const float4*>(x + (size_t)r * p.D + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int r = 0; r < PREP_ROWS; ++r) {
+                const float f[4] = {v[r].x, v[r].y, v[r].z, v[r].w};
+                __nv_bfloat16 h[4], l[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    h[e] = __float2bfloat16_rn(f[e]);
+                    l[e] = __float2bfloat16_rn(f[e] - __bfloat162float(h[e]));
+                    ss[r] = fmaf(f[e], f[e], ss[r]);
+                }
+                __nv_bfloat16* o = out + (size_t)r * (2 * p.Dp);
+                *reinterpret_cast<uint2*>(o + k) = *reinterpret_cast<const uint2*>(h);
+                *reinterpret_cast<uint2*>(o + p.Dp + k) = *reinterpret_cast<const uint2*>(l);
             }
-            *reinterpret_cast<uint2*>(out + k) = *reinterpret_cast<const uint2*>(h);
-            *reinterpret_cast<uint2*>(out + p.Dp + k) = *reinterpret_cast<const uint2*>(l);
         }
-    } else {
+#pragma unroll
+        for (int r = 0; r < PREP_ROWS; ++r) wmax = fmaxf(wmax, prep_finish_row(p, b, row0 + r, ss[r], lane));
+    } else for (int row = row0; row < row0 + PREP_ROWS && row < p.cs; ++row) {
+        if (row >= p.n_max) {                       // padding of the c array up to a whole column tile
+            if (lane == 0) p.c[(size_t)b * p.cs + row] = -CUDART_INF_F;
+            continue;
+        }
+        __nv_bfloat16* out = p.S + ((size_t)b * p.n_max + row) * (2 * p.Dp);
+        if (row >= n) {
+            for (int k = lane; k < 2 * p.Dp; k += 32) out[k] = __float2bfloat16(0.0f);
+            if (lane == 0) { p.c[(size_t)b * p.cs + row] = -CUDART_INF_F; p.norm2[(size_t)b * p.n_max + row] = 0.0f; }
+            continue;
+        }
+        const float* x = p.d + ((size_t)b * p.n_max + row) * p.D;
+        float ss = 0.0f;
         for (int k = lane; k < p.Dp; k += 32) {
             const float v = k < p.D ? x[k] : 0.0f;
             const __nv_bfloat16 h = __float2bfloat16_rn(v);
@@ -166,12 +207,14 @@ __global__ void __launch_bounds__(256) prep_kernel(PrepParams p) {
             out[p.Dp + k] = l;
             ss = fmaf(v, v, ss);
         }
+        wmax = fmaxf(wmax, prep_finish_row(p, b, row, ss, lane));
     }
-    for (int d = 16; d > 0; d >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, d);
-    if (lane == 0) {
-        p.c[(size_t)b * p.cs + row] = -0.5f * ss;
-        p.norm2[(size_t)b * p.n_max + row] = ss;
-        atomicMax(&p.maxn[b], __float_as_uint(ss));
+    if (lane == 0) s_max[threadIdx.x >> 5] = wmax;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float mx = s_max[0];
+        for (int w = 1; w < 8; ++w) mx = fmaxf(mx, s_max[w]);
+        if (mx > 0.0f) atomicMax(&p.maxn[b], __float_as_uint(mx));
     }
 }
 
@@ -185,7 +228,9 @@ struct MainParams {
     const float* c1;         // [B,cs1]
     Top2* res0;              // [B*n_max]
     Top2* res1;              // [B*m_max]
-    int B, n_max, m_max, cs0, cs1, KB, tiles0, tiles1, n_dirs;
+    int B, n_max, m_max, cs0, cs1, KB, tiles0, tiles1, n_dirs, n_slots;
+    int align_slack;         // bytes the kernel may spend on aligning its tiles to 1024
+    int dbg;                 // timing experiments only (KB_TC_DEBUG): 1 = epilogue skips the fold, 2 = no MMAs issued
 };
 
 struct Item {
@@ -210,17 +255,19 @@ __device__ __forceinline__ bool decode_item(const MainParams& p, int item, Item&
 
 __global__ void __launch_bounds__(NT, 1) nn_top2_kernel(const __grid_constant__ CUtensorMap map0,
                                                         const __grid_constant__ CUtensorMap map1, MainParams p) {
-    extern __shared__ unsigned char smem_dyn[];
+    extern __shared__ __align__(1024) unsigned char smem_dyn[];
     const uint32_t raw = smem_u32(smem_dyn);
     const uint32_t base = (raw + 1023u) & ~1023u;                   // 1024B alignment for SWIZZLE_128B
     const int KB = p.KB;
     const uint32_t a_tiles = base;                                  // 2*KB tiles: hi blocks then lo blocks
     const uint32_t b_slots = base + (uint32_t)(2 * KB) * TILE_BYTES;
-    const uint32_t bars = b_slots + NSLOT * TILE_BYTES;
+    const int NSLOT = p.n_slots;
+    const uint32_t bars = b_slots + NSLOT * SLOT_BYTES;
+    if (base - raw > (uint32_t)p.align_slack) __trap();             // the host sized the allocation for this slack
     // barrier map (8 bytes each)
     const uint32_t bar_a_full = bars, bar_a_free = bars + 8;
-    const uint32_t bar_b_full = bars + 16, bar_b_empty = bars + 16 + 8 * NSLOT;
-    const uint32_t bar_t_full = bars + 16 + 16 * NSLOT, bar_t_empty = bar_t_full + 16;
+    const uint32_t bar_b_full = bars + 16, bar_b_empty = bars + 16 + 8 * MAX_SLOTS;
+    const uint32_t bar_t_full = bars + 16 + 16 * MAX_SLOTS, bar_t_empty = bar_t_full + 16;
     const uint32_t tmem_slot = bar_t_empty + 16;
     float* cbuf = reinterpret_cast<float*>(smem_dyn + (tmem_slot + 16 - raw));     // [2][BN]
     volatile uint32_t* tmem_slot_ptr =
@@ -231,7 +278,7 @@ __global__ void __launch_bounds__(NT, 1) nn_top2_kernel(const __grid_constant__ 
         mbar_init(bar_a_full, 1);
         mbar_init(bar_a_free, 1);
         for (int s = 0; s < NSLOT; ++s) { mbar_init(bar_b_full + 8 * s, 1); mbar_init(bar_b_empty + 8 * s, 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(bar_t_full + 8 * s, 1); mbar_init(bar_t_empty + 8 * s, 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(bar_t_full + 8 * s, 1); mbar_init(bar_t_empty + 8 * s, EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -246,146 +293,203 @@ __global__ void __launch_bounds__(NT, 1) nn_top2_kernel(const __grid_constant__ 
 
     const int n_items = p.n_dirs == 2 ? p.B * (p.tiles0 + p.tiles1) : p.B * p.tiles0;
 
+    // The producer and the MMA issuer run their loops with the WHOLE warp (uniform control flow keeps
+    // addresses, descriptors and phases in uniform registers); only the issuing instructions themselves
+    // are predicated on one lane.  A divergent single-lane loop costs ~150 cycles per tcgen05.mma in
+    // address arithmetic alone, more than twice the 64 cycles the instruction occupies the tensor core.
     if (warp == 0) {
         // ================================ TMA producer ==========================================
-        if (lane == 0) {
-            uint32_t a_phase = 0, slot = 0, b_phase = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-                Item it;
-                if (!decode_item(p, item, it)) continue;
-                const CUtensorMap* qmap = it.dir ? &map1 : &map0;
-                const CUtensorMap* dmap = it.dir ? &map0 : &map1;
-                mbar_wait(bar_a_free, a_phase ^ 1);                 // previous item's MMAs are done with A
+        const bool issuer = lane == 0;
+        uint32_t a_phase = 0, slot = 0, b_phase = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            Item it;
+            if (!decode_item(p, item, it)) continue;
+            const CUtensorMap* qmap = it.dir ? &map1 : &map0;
+            const CUtensorMap* dmap = it.dir ? &map0 : &map1;
+            mbar_wait(bar_a_free, a_phase ^ 1);                     // previous item's MMAs are done with A
+            if (issuer) {
                 mbar_expect_tx(bar_a_full, (uint32_t)(2 * KB) * TILE_BYTES);
                 for (int t = 0; t < 2 * KB; ++t)
                     tma_load_2d(a_tiles + t * TILE_BYTES, qmap, t * BK, it.q_base + it.q_row0, bar_a_full);
-                a_phase ^= 1;
-                const int n_ct = (it.n_db + BN - 1) / BN;
-                for (int ct = 0; ct < n_ct; ++ct) {
-                    for (int kb = 0; kb < KB; ++kb) {
-                        for (int part = 0; part < 2; ++part) {      // hi block then lo block
-                            mbar_wait(bar_b_empty + 8 * slot, b_phase ^ 1);
-                            mbar_expect_tx(bar_b_full + 8 * slot, TILE_BYTES);
-                            tma_load_2d(b_slots + slot * TILE_BYTES, dmap, (part * KB + kb) * BK,
-                                        it.db_base + ct * BN, bar_b_full + 8 * slot);
-                            if (++slot == NSLOT) { slot = 0; b_phase ^= 1; }
+            }
+            a_phase ^= 1;
+            const int n_ct = (it.n_db + BN - 1) / BN;
+            for (int ct = 0; ct < n_ct; ++ct) {
+                const int row = it.db_base + ct * BN;
+                for (int kb = 0; kb < KB; ++kb) {
+#pragma unroll
+                    for (int part = 0; part < 2; ++part) {          // hi block then lo block
+                        mbar_wait(bar_b_empty + 8 * slot, b_phase ^ 1);
+                        if (issuer) {
+                            mbar_expect_tx(bar_b_full + 8 * slot, SLOT_BYTES);
+                            tma_load_2d(b_slots + slot * SLOT_BYTES, dmap, (part * KB + kb) * BK, row,
+                                        bar_b_full + 8 * slot);
+                            tma_load_2d(b_slots + slot * SLOT_BYTES + TILE_BYTES, dmap, (part * KB + kb) * BK, row + BM,
+                                        bar_b_full + 8 * slot);
                         }
+                        if (++slot == (uint32_t)NSLOT) { slot = 0; b_phase ^= 1; }
                     }
                 }
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ============================================
-        if (lane == 0) {
-            uint32_t a_phase = 0, slot = 0, b_phase = 0, acc_buf = 0, t_phase[2] = {0, 0};
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-                Item it;
-                if (!decode_item(p, item, it)) continue;
-                mbar_wait(bar_a_full, a_phase);
-                a_phase ^= 1;
+        const bool issuer = lane == 0;
+        uint32_t a_phase = 0, slot = 0, b_phase = 0, acc_buf = 0, t_phase = 0;      // t_phase: one bit per buffer
+        const uint64_t desc0 = umma_desc(0);                        // everything but the start address
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            Item it;
+            if (!decode_item(p, item, it)) continue;
+            mbar_wait(bar_a_full, a_phase);
+            a_phase ^= 1;
+            tc_fence_after();
+            const int n_ct = (it.n_db + BN - 1) / BN;
+            for (int ct = 0; ct < n_ct; ++ct) {
+                mbar_wait(bar_t_empty + 8 * acc_buf, ((t_phase >> acc_buf) & 1u) ^ 1u);   // epilogue drained this buffer
                 tc_fence_after();
-                const int n_ct = (it.n_db + BN - 1) / BN;
-                for (int ct = 0; ct < n_ct; ++ct) {
-                    mbar_wait(bar_t_empty + 8 * acc_buf, t_phase[acc_buf] ^ 1);   // epilogue drained this buffer
+                const uint32_t d_tmem = tmem_base + acc_buf * BN;
+                for (int kb = 0; kb < KB; ++kb) {
+                    const uint64_t a_hi = desc0 | (uint64_t)((a_tiles + kb * TILE_BYTES) >> 4);
+                    const uint64_t a_lo = desc0 | (uint64_t)((a_tiles + (KB + kb) * TILE_BYTES) >> 4);
+                    // ---- database hi block: hi.hi and lo.hi
+                    mbar_wait(bar_b_full + 8 * slot, b_phase);
                     tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + acc_buf * BN;
-                    uint32_t accum = 0;
-                    for (int kb = 0; kb < KB; ++kb) {
-                        const uint32_t a_hi = a_tiles + kb * TILE_BYTES, a_lo = a_tiles + (KB + kb) * TILE_BYTES;
-                        // ---- database hi block: hi.hi and lo.hi
-                        mbar_wait(bar_b_full + 8 * slot, b_phase);
-                        tc_fence_after();
-                        uint32_t bt = b_slots + slot * TILE_BYTES;
-#pragma unroll
-                        for (int k = 0; k < BK / 16; ++k) {
-                            tc_mma(d_tmem, umma_desc(a_hi + k * 32), umma_desc(bt + k * 32), IDESC, accum);
-                            accum = 1;
-                        }
-#pragma unroll
-                        for (int k = 0; k < BK / 16; ++k)
-                            tc_mma(d_tmem, umma_desc(a_lo + k * 32), umma_desc(bt + k * 32), IDESC, 1);
-                        tc_commit(bar_b_empty + 8 * slot);
-                        if (++slot == NSLOT) { slot = 0; b_phase ^= 1; }
-                        // ---- database lo block: hi.lo
-                        mbar_wait(bar_b_full + 8 * slot, b_phase);
-                        tc_fence_after();
-                        bt = b_slots + slot * TILE_BYTES;
-#pragma unroll
-                        for (int k = 0; k < BK / 16; ++k)
-                            tc_mma(d_tmem, umma_desc(a_hi + k * 32), umma_desc(bt + k * 32), IDESC, 1);
-                        tc_commit(bar_b_empty + 8 * slot);
-                        if (++slot == NSLOT) { slot = 0; b_phase ^= 1; }
+                    uint64_t bt = desc0 | (uint64_t)((b_slots + slot * SLOT_BYTES) >> 4);
+                    if (issuer && !(p.dbg & 2)) {
+                        tc_mma(d_tmem, a_hi, bt, IDESC, kb > 0 ? 1u : 0u);        // 32 bytes (16 bf16) per K step: +2
+                        tc_mma(d_tmem, a_hi + 2, bt + 2, IDESC, 1u);
+                        tc_mma(d_tmem, a_hi + 4, bt + 4, IDESC, 1u);
+                        tc_mma(d_tmem, a_hi + 6, bt + 6, IDESC, 1u);
+                        tc_mma(d_tmem, a_lo, bt, IDESC, 1u);
+                        tc_mma(d_tmem, a_lo + 2, bt + 2, IDESC, 1u);
+                        tc_mma(d_tmem, a_lo + 4, bt + 4, IDESC, 1u);
+                        tc_mma(d_tmem, a_lo + 6, bt + 6, IDESC, 1u);
                     }
-                    tc_commit(bar_t_full + 8 * acc_buf);            // accumulator ready for the epilogue
-                    t_phase[acc_buf] ^= 1;
-                    acc_buf ^= 1;
+                    if (issuer) tc_commit(bar_b_empty + 8 * slot);
+                    __syncwarp();
+                    if (++slot == (uint32_t)NSLOT) { slot = 0; b_phase ^= 1; }
+                    // ---- database lo block: hi.lo
+                    mbar_wait(bar_b_full + 8 * slot, b_phase);
+                    tc_fence_after();
+                    bt = desc0 | (uint64_t)((b_slots + slot * SLOT_BYTES) >> 4);
+                    if (issuer && !(p.dbg & 2)) {
+                        tc_mma(d_tmem, a_hi, bt, IDESC, 1u);
+                        tc_mma(d_tmem, a_hi + 2, bt + 2, IDESC, 1u);
+                        tc_mma(d_tmem, a_hi + 4, bt + 4, IDESC, 1u);
+                        tc_mma(d_tmem, a_hi + 6, bt + 6, IDESC, 1u);
+                    }
+                    if (issuer) tc_commit(bar_b_empty + 8 * slot);
+                    __syncwarp();
+                    if (++slot == (uint32_t)NSLOT) { slot = 0; b_phase ^= 1; }
                 }
-                tc_commit(bar_a_free);                              // A tiles may be overwritten
+                if (issuer) tc_commit(bar_t_full + 8 * acc_buf);    // accumulator ready for the epilogue
+                __syncwarp();
+                t_phase ^= 1u << acc_buf;
+                acc_buf ^= 1;
             }
+            if (issuer) tc_commit(bar_a_free);                      // A tiles may be overwritten
+            __syncwarp();
         }
     } else if (warp >= 4) {
         // ================================ epilogue ==============================================
-        const int ew = warp - 4;                                    // TMEM lanes 32*ew .. 32*ew+31
-        const int row_in_tile = ew * 32 + lane;
-        uint32_t acc_buf = 0, t_phase[2] = {0, 0};
+        const int ew = warp - 4;
+        const int quad = ew & 3;                                    // == warp % 4: TMEM lanes 32*quad .. 32*quad+31
+        const int slice = ew >> 2;                                  // columns 64*slice .. 64*slice+63 of every tile
+        const int row_in_tile = quad * 32 + lane;
+        const int cidx = ew * 32 + lane;                            // c entry this thread stages (first 8 warps)
+        constexpr int SW = BN / EPI_SLICES;                         // 64 columns per warp and tile
+        uint32_t acc_buf = 0, t_phase = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             Item it;
             if (!decode_item(p, item, it)) continue;
             const float* cvec = (it.dir ? p.c0 : p.c1) + (size_t)it.b * (it.dir ? p.cs0 : p.cs1);
-            float best = -CUDART_INF_F, second = -CUDART_INF_F;
-            int bj = 0;
+            // running top-3 scores and top-2 indices of this row over this warp's column slice; the slices
+            // are merged by the resolver.  (Which of two exactly tied scores ranks first is irrelevant
+            // here: near-ties are settled exactly in the resolver.)
+            float b1 = -CUDART_INF_F, b2 = -CUDART_INF_F, b3 = -CUDART_INF_F;
+            int i1 = 0, i2 = 0;
             const int n_ct = (it.n_db + BN - 1) / BN;
-            // -|y|^2/2 of the next column tile travels through a register while the current tile is
-            // reduced, then through a 2 x 128-float shared buffer (one named barrier per tile)
-            float c_next = __ldg(cvec + ew * 32 + lane);
-            for (int ct = 0; ct < n_ct; ++ct) {
-                float* cb = cbuf + (ct & 1) * BN;
-                cb[ew * 32 + lane] = c_next;
-                if (ct + 1 < n_ct) c_next = __ldg(cvec + (ct + 1) * BN + ew * 32 + lane);
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                mbar_wait(bar_t_full + 8 * acc_buf, t_phase[acc_buf]);
-                t_phase[acc_buf] ^= 1;
-                tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc_buf * BN;
-                uint32_t va[32], vb[32];
-                auto fold = [&](const uint32_t (&v)[32], int cc) {
-                    const float4* c4 = reinterpret_cast<const float4*>(cb + cc * 32);
-                    const int j0 = ct * BN + cc * 32;
+            // TMEM -> register bandwidth (~56 B/clk/SM measured) is what bounds this epilogue, so every warp
+            // keeps a tcgen05.ld in flight while it folds the previous 16 columns (two 16-register buffers;
+            // the first chunk of the next tile is requested before the last chunk of this one is folded).
+            // -|y|^2/2 of a tile is staged through a 256-float shared buffer between two named barriers.
+            auto fold = [&](const uint32_t (&v)[16], int ct, int col0) {
+                const float4* c4 = reinterpret_cast<const float4*>(cbuf + col0);
+                const int j0 = ct * BN + col0;
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const float4 t4 = c4[q];
-                        const float cv[4] = {t4.x, t4.y, t4.z, t4.w};
+                for (int q = 0; q < 4; ++q) {
+                    const float4 t4 = c4[q];
+                    float t[4];
+                    t[0] = __uint_as_float(v[4 * q + 0]) + t4.x;              // x.y - |y|^2/2 (-inf beyond the count)
+                    t[1] = __uint_as_float(v[4 * q + 1]) + t4.y;
+                    t[2] = __uint_as_float(v[4 * q + 2]) + t4.z;
+                    t[3] = __uint_as_float(v[4 * q + 3]) + t4.w;
+                    const float m4 = fmaxf(fmaxf(t[0], t[1]), fmaxf(t[2], t[3]));
+                    // groups of four columns that cannot enter any lane's top-3 are skipped with one warp vote
+                    if (__any_sync(0xffffffffu, m4 > b3)) {
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            const float t = __uint_as_float(v[4 * q + e]) + cv[e];   // x.y - |y|^2/2 (-inf beyond the count)
-                            second = fmaxf(second, fminf(t, best));
-                            bj = (t > best) ? (j0 + 4 * q + e) : bj;                 // strict: first of ties
-                            best = fmaxf(best, t);
+                            const float te = t[e];
+                            const int j = j0 + 4 * q + e;
+                            const bool g1 = te > b1, g2 = te > b2;
+                            b3 = fmaxf(b3, fminf(te, b2));
+                            b2 = fmaxf(b2, fminf(te, b1));
+                            b1 = fmaxf(b1, te);
+                            i2 = g1 ? i1 : (g2 ? j : i2);
+                            i1 = g1 ? j : i1;
                         }
                     }
-                };
-                tmem_ld32(taddr, va);
+                }
+            };
+            auto stage_c = [&](int ct) {                                // all 16 warps call this
+                const float cv = cidx < BN ? __ldg(cvec + ct * BN + cidx) : 0.0f;
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");   // everyone is done with the old values
+                if (cidx < BN) cbuf[cidx] = cv;
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+            };
+            const int col_base = slice * SW;
+            uint32_t ra[16], rb[16];
+            // prologue: first tile
+            mbar_wait(bar_t_full + 8 * acc_buf, (t_phase >> acc_buf) & 1u);
+            t_phase ^= 1u << acc_buf;
+            tc_fence_after();
+            uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc_buf * BN + col_base;
+            tmem_ld16(taddr, ra);
+            stage_c(0);
+            tmem_ld_wait();
+            for (int ct = 0; ct < n_ct; ++ct) {
+                tmem_ld16(taddr + 16, rb);
+                fold(ra, ct, col_base);
                 tmem_ld_wait();
-                tmem_ld32(taddr + 32, vb);
-                fold(va, 0);
+                tmem_ld16(taddr + 32, ra);
+                fold(rb, ct, col_base + 16);
                 tmem_ld_wait();
-                tmem_ld32(taddr + 64, va);
-                fold(vb, 1);
+                tmem_ld16(taddr + 48, rb);
+                fold(ra, ct, col_base + 32);
                 tmem_ld_wait();
-                tmem_ld32(taddr + 96, vb);
-                fold(va, 2);
-                tmem_ld_wait();
-                // the accumulator is in registers: hand the TMEM buffer back before the last fold
+                // the slice has left TMEM: hand the accumulator back to the MMA issuer
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_t_empty + 8 * acc_buf);
-                fold(vb, 3);
                 acc_buf ^= 1;
+                fold(rb, ct, col_base + 48);
+                if (ct + 1 < n_ct) {
+                    mbar_wait(bar_t_full + 8 * acc_buf, (t_phase >> acc_buf) & 1u);
+                    t_phase ^= 1u << acc_buf;
+                    tc_fence_after();
+                    taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc_buf * BN + col_base;
+                    tmem_ld16(taddr, ra);
+                    stage_c(ct + 1);
+                    tmem_ld_wait();
+                }
             }
             const int qi = it.q_row0 + row_in_tile;
             if (qi < it.n_q) {
-                Top2 o; o.best = best; o.second = second; o.idx = bj; o.pad = 0;
-                (it.dir ? p.res1 : p.res0)[(size_t)it.q_base + qi] = o;
+                Top2 o;
+                o.best = b1; o.second = b2; o.third = b3; o.pad0 = 0.0f;
+                o.idx = i1; o.idx2 = i2; o.pad1 = 0; o.pad2 = 0;
+                (it.dir ? p.res1 : p.res0)[((size_t)it.q_base + qi) * EPI_SLICES + slice] = o;
             }
         }
     }
@@ -414,6 +518,7 @@ struct ResolveParams {
     int* nn0;                // [B*n_max]
     int* nn1;                // [B*m_max]
     int* n_exact;            // [1] number of rows queued for the exact rescan
+    int* n_pair;             // [1] rows settled by the two-candidate exact check (statistics)
     int2* list;              // [list_cap] queued rows: (dir | b << 1, query row)
     int list_cap;
     int B, n_max, m_max, D, n_dirs;
@@ -429,38 +534,83 @@ __device__ __forceinline__ double warp_dist2(const float* x, const float* y, int
     return acc;
 }
 
-// One thread per query row: certify the tensor-core argmax or queue the row for the exact rescan.
+// One thread per query row.  With e the a-priori error bound of the split product:
+//   best - second > 2e : the tensor-core argmax is certified;
+//   best - third  > 2e : the exact winner is one of the two best -- their float64 distances are
+//                        evaluated on the spot by the whole warp (smaller wins, ties to the smaller index);
+//   otherwise          : the row is queued for the exact rescan (three or more near-ties: duplicates).
 __global__ void __launch_bounds__(256) resolve_kernel(ResolveParams p) {
-    const int q = blockIdx.x * 256 + threadIdx.x;
+    const int q = blockIdx.x * 256 + threadIdx.x, lane = threadIdx.x & 31;
     const int b = blockIdx.y, dir = blockIdx.z;
     const int n = p.n0 ? p.n0[b] : p.n_max, m = p.n1 ? p.n1[b] : p.m_max;
     const int nq = dir ? m : n, ndb = dir ? n : m;
-    if (q >= nq || ndb <= 0) return;
-    const int q_stride = dir ? p.m_max : p.n_max;
-    const Top2 r = (dir ? p.res1 : p.res0)[(size_t)b * q_stride + q];
-    const float nq2 = (dir ? p.norm2_1 : p.norm2_0)[(size_t)b * q_stride + q];
-    const float dbmax2 = __uint_as_float((dir ? p.maxn0 : p.maxn1)[b]);
-    // a-priori bound on |t_computed - t_exact|: dropped lo.lo / residual terms (3*2^-18 |x||y|), fp32
-    // accumulation in the tensor core (K/16 roundings) and the fp32 -|y|^2/2 term; generous factor on top
-    const float e = 6.2e-5f * sqrtf(nq2) * sqrtf(dbmax2) + 3.1e-5f * dbmax2;
-    const int j = r.idx;
-    const bool certain = (r.best - r.second) > 2.0f * e && j >= 0 && j < ndb;
-    if (certain) {
-        (dir ? p.nn1 : p.nn0)[(size_t)b * q_stride + q] = j;
-    } else {
+    if (ndb <= 0) return;
+    const int q_stride = dir ? p.m_max : p.n_max, db_stride = dir ? p.n_max : p.m_max;
+    int mode = 0;                        // 0 nothing to do, 1 certified, 2 two candidates, 3 rescan
+    int j1 = 0, j2 = 0;
+    if (q < nq) {
+        Top2 r = (dir ? p.res1 : p.res0)[((size_t)b * q_stride + q) * EPI_SLICES];
+#pragma unroll
+        for (int sl = 1; sl < EPI_SLICES; ++sl) {                     // merge the column slices of the epilogue
+            const Top2 o = (dir ? p.res1 : p.res0)[((size_t)b * q_stride + q) * EPI_SLICES + sl];
+            const float cand[3] = {o.best, o.second, o.third};
+            const int cix[3] = {o.idx, o.idx2, 0};
+#pragma unroll
+            for (int e = 0; e < 3; ++e) {
+                const float te = cand[e];
+                const bool g1 = te > r.best, g2 = te > r.second;
+                r.third = fmaxf(r.third, fminf(te, r.second));
+                r.second = fmaxf(r.second, fminf(te, r.best));
+                r.best = fmaxf(r.best, te);
+                r.idx2 = g1 ? r.idx : (g2 ? cix[e] : r.idx2);
+                r.idx = g1 ? cix[e] : r.idx;
+            }
+        }
+        const float nq2 = (dir ? p.norm2_1 : p.norm2_0)[(size_t)b * q_stride + q];
+        const float dbmax2 = __uint_as_float((dir ? p.maxn0 : p.maxn1)[b]);
+        // bound on |t_computed - t_exact|: dropped lo.lo / residual terms (3*2^-18 |x||y|), fp32
+        // accumulation in the tensor core (K/16 roundings) and the fp32 -|y|^2/2 term; generous factor on top
+        const float e = 6.2e-5f * sqrtf(nq2) * sqrtf(dbmax2) + 3.1e-5f * dbmax2;
+        j1 = r.idx; j2 = r.idx2;
+        const bool ok1 = j1 >= 0 && j1 < ndb, ok2 = j2 >= 0 && j2 < ndb && j2 != j1;
+        if (ok1 && (r.best - r.second) > 2.0f * e) mode = 1;
+        else if (ok1 && ok2 && (r.best - r.third) > 2.0f * e) mode = 2;
+        else mode = 3;
+    }
+    int* nn = dir ? p.nn1 : p.nn0;
+    if (mode == 1) nn[(size_t)b * q_stride + q] = j1;
+    if (mode == 3) {
         const int slot = atomicAdd(p.n_exact, 1);
         if (slot < p.list_cap) p.list[slot] = make_int2(dir | (b << 1), q);
+    }
+    unsigned pend = __ballot_sync(0xffffffffu, mode == 2);
+    const float* Qb = (dir ? p.d1 : p.d0) + (size_t)b * q_stride * p.D;
+    const float* DBs = (dir ? p.d0 : p.d1) + (size_t)b * db_stride * p.D;
+    while (pend) {
+        const int src = __ffs(pend) - 1;
+        pend &= pend - 1;
+        const int qq = __shfl_sync(0xffffffffu, q, src);
+        const int a1 = __shfl_sync(0xffffffffu, j1, src), a2 = __shfl_sync(0xffffffffu, j2, src);
+        const double d1 = warp_dist2(Qb + (size_t)qq * p.D, DBs + (size_t)a1 * p.D, p.D, lane);
+        const double d2 = warp_dist2(Qb + (size_t)qq * p.D, DBs + (size_t)a2 * p.D, p.D, lane);
+        if (lane == 0) {
+            const bool first = d1 < d2 || (d1 == d2 && a1 < a2);
+            nn[(size_t)b * q_stride + qq] = first ? a1 : a2;
+            if (p.n_pair) atomicAdd(p.n_pair, 1);
+        }
     }
 }
 
 // Exact float64 resolution of the queued rows (best/second closer than the error bound of the split
 // product, e.g. duplicated descriptors): one CTA per row, lanes over components, eight candidates in
 // flight per warp (16 independent 16-byte loads per lane at D=256).  First of ties wins, as np.argmin.
+constexpr int RESCAN_WARPS = 32;      // a queued row is rare but must not become a long tail: whole-SM CTA per row
+
 template <bool VEC>
 __device__ __forceinline__ void rescan_row(const float* xs, const float* DBs, int D, int ndb, int warp, int lane,
                                            double& bd, int& bj) {
     constexpr int G = 8;
-    for (int c0 = warp * G; c0 < ndb; c0 += 8 * G) {
+    for (int c0 = warp * G; c0 < ndb; c0 += RESCAN_WARPS * G) {
         double acc[G];
 #pragma unroll
         for (int u = 0; u < G; ++u) acc[u] = 0.0;
@@ -501,10 +651,10 @@ __device__ __forceinline__ void rescan_row(const float* xs, const float* DBs, in
     }
 }
 
-__global__ void __launch_bounds__(256) rescan_kernel(ResolveParams p) {
+__global__ void __launch_bounds__(RESCAN_WARPS * 32) rescan_kernel(ResolveParams p) {
     extern __shared__ __align__(16) float xs[];
-    __shared__ double s_d[8];
-    __shared__ int s_j[8];
+    __shared__ double s_d[RESCAN_WARPS];
+    __shared__ int s_j[RESCAN_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int total = *p.n_exact;
     if (total > p.list_cap) total = p.list_cap;
@@ -518,7 +668,7 @@ __global__ void __launch_bounds__(256) rescan_kernel(ResolveParams p) {
         const float* Q = (dir ? p.d1 : p.d0) + ((size_t)b * q_stride + q) * p.D;
         const float* DBs = (dir ? p.d0 : p.d1) + (size_t)b * db_stride * p.D;
         __syncthreads();
-        for (int k = threadIdx.x; k < p.D; k += 256) xs[k] = Q[k];
+        for (int k = threadIdx.x; k < p.D; k += RESCAN_WARPS * 32) xs[k] = Q[k];
         __syncthreads();
         double bd = CUDART_INF;
         int bj = 0x7fffffff;
@@ -529,7 +679,7 @@ __global__ void __launch_bounds__(256) rescan_kernel(ResolveParams p) {
         if (threadIdx.x == 0) {
             double d2 = s_d[0];
             int j = s_j[0];
-            for (int w = 1; w < 8; ++w)
+            for (int w = 1; w < RESCAN_WARPS; ++w)
                 if (s_d[w] < d2 || (s_d[w] == d2 && s_j[w] < j)) { d2 = s_d[w]; j = s_j[w]; }
             (dir ? p.nn1 : p.nn0)[(size_t)b * q_stride + q] = j;
         }
@@ -551,18 +701,64 @@ struct GateParams {
 };
 
 __global__ void __launch_bounds__(256) gate_kernel(GateParams p) {
-    const int i = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    constexpr int G = 4;                  // rows per warp, their loads issued together
+    const int i0 = ((blockIdx.x * 256 + threadIdx.x) >> 5) * G, lane = threadIdx.x & 31;
     const int b = blockIdx.y;
     const int n = p.n0 ? p.n0[b] : p.n_max, m = p.n1 ? p.n1[b] : p.m_max;
-    if (i >= n || m <= 0) return;
-    const int j = p.nn0[(size_t)b * p.n_max + i];
-    int keep = -1;
-    double d = 0.0;
-    if (!p.cross_check || p.nn1[(size_t)b * p.m_max + j] == i) {
-        d = sqrt(warp_dist2(p.d0 + ((size_t)b * p.n_max + i) * p.D, p.d1 + ((size_t)b * p.m_max + j) * p.D, p.D, lane));
-        if (d < p.max_distance) keep = j;
+    if (i0 >= n || m <= 0) return;
+    int jj[G];
+    bool live[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        const int i = i0 + g;
+        jj[g] = i < n ? p.nn0[(size_t)b * p.n_max + i] : 0;
+        live[g] = i < n && (!p.cross_check || p.nn1[(size_t)b * p.m_max + jj[g]] == i);
     }
-    if (lane == 0) { p.keep_j[(size_t)b * p.n_max + i] = keep; p.dist_i[(size_t)b * p.n_max + i] = d; }
+    double acc[G] = {0.0, 0.0, 0.0, 0.0};
+    const bool vec = (p.D & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.d0) | reinterpret_cast<uintptr_t>(p.d1)) & 15u) == 0;
+    if (vec) {
+        for (int k = 4 * lane; k < p.D; k += 128) {
+            float4 xv[G], yv[G];
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                xv[g] = yv[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (live[g]) {
+                    xv[g] = __ldg(reinterpret_cast<const float4*>(p.d0 + ((size_t)b * p.n_max + i0 + g) * p.D + k));
+                    yv[g] = __ldg(reinterpret_cast<const float4*>(p.d1 + ((size_t)b * p.m_max + jj[g]) * p.D + k));
+                }
+            }
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                double d = (double)xv[g].x - (double)yv[g].x; acc[g] = fma(d, d, acc[g]);
+                d = (double)xv[g].y - (double)yv[g].y; acc[g] = fma(d, d, acc[g]);
+                d = (double)xv[g].z - (double)yv[g].z; acc[g] = fma(d, d, acc[g]);
+                d = (double)xv[g].w - (double)yv[g].w; acc[g] = fma(d, d, acc[g]);
+            }
+        }
+    } else for (int k = lane; k < p.D; k += 32) {
+        float xv[G], yv[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            xv[g] = live[g] ? __ldg(p.d0 + ((size_t)b * p.n_max + i0 + g) * p.D + k) : 0.0f;
+            yv[g] = live[g] ? __ldg(p.d1 + ((size_t)b * p.m_max + jj[g]) * p.D + k) : 0.0f;
+        }
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const double d = (double)xv[g] - (double)yv[g];
+            acc[g] = fma(d, d, acc[g]);
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        double a = acc[g];
+        for (int s = 16; s > 0; s >>= 1) a += __shfl_xor_sync(0xffffffffu, a, s);
+        const int i = i0 + g;
+        if (lane == 0 && i < n) {
+            const double d = sqrt(a);
+            p.keep_j[(size_t)b * p.n_max + i] = (live[g] && d < p.max_distance) ? jj[g] : -1;
+            p.dist_i[(size_t)b * p.n_max + i] = d;
+        }
+    }
 }
 
 struct PairsParams {
@@ -646,8 +842,8 @@ static TcLayout tc_layout(int B, int n_max, int m_max, int D) {
     L.KB = L.Dp / 64;
     L.tiles0 = (n_max + kbtc::BM - 1) / kbtc::BM;
     L.tiles1 = (m_max + kbtc::BM - 1) / kbtc::BM;
-    L.cs0 = L.tiles0 * kbtc::BM;
-    L.cs1 = L.tiles1 * kbtc::BM;
+    L.cs0 = (n_max + kbtc::BN - 1) / kbtc::BN * kbtc::BN;     // -|y|^2/2 padded to whole column tiles
+    L.cs1 = (m_max + kbtc::BN - 1) / kbtc::BN * kbtc::BN;
     size_t n = 0;
     auto add = [&](size_t bytes) { n += kb_align_up(bytes, 256); };
     add((size_t)B * n_max * 2 * L.Dp * 2);      // S0
@@ -658,8 +854,8 @@ static TcLayout tc_layout(int B, int n_max, int m_max, int D) {
     add((size_t)B * m_max * 4);                 // norm2_1
     add((size_t)B * 4);                         // maxn0
     add((size_t)B * 4);                         // maxn1
-    add((size_t)B * n_max * sizeof(kbtc::Top2));
-    add((size_t)B * m_max * sizeof(kbtc::Top2));
+    add((size_t)B * n_max * sizeof(kbtc::Top2) * kbtc::EPI_SLICES);
+    add((size_t)B * m_max * sizeof(kbtc::Top2) * kbtc::EPI_SLICES);
     add((size_t)B * n_max * 4);                 // nn0
     add((size_t)B * m_max * 4);                 // nn1
     add((size_t)B * n_max * 8);                 // d2_0
@@ -694,12 +890,12 @@ static TcBuffers tc_carve(void* ws, size_t ws_bytes, int B, int n_max, int m_max
     t.norm2_1 = arena.take<float>((size_t)B * m_max);
     t.maxn0 = arena.take<unsigned int>(B);
     t.maxn1 = arena.take<unsigned int>(B);
-    t.res0 = arena.take<kbtc::Top2>((size_t)B * n_max);
-    t.res1 = arena.take<kbtc::Top2>((size_t)B * m_max);
+    t.res0 = arena.take<kbtc::Top2>((size_t)B * n_max * kbtc::EPI_SLICES);
+    t.res1 = arena.take<kbtc::Top2>((size_t)B * m_max * kbtc::EPI_SLICES);
     t.nn0 = arena.take<int>((size_t)B * n_max);
     t.nn1 = arena.take<int>((size_t)B * m_max);
     t.d2_0 = arena.take<double>((size_t)B * n_max);
-    t.n_exact = arena.take<int>(1);
+    t.n_exact = arena.take<int>(2);
     t.list = arena.take<int2>((size_t)B * (n_max + m_max));
     t.keep_j = arena.take<int>((size_t)B * n_max);
     t.ok = arena.ok();
@@ -740,16 +936,16 @@ int kb_match_tc_run(const float* d0, const float* d1, const int* n0, const int* 
 
     KB_CUDA_TRY(cudaMemsetAsync(maxn0, 0, (size_t)B * 4, st));
     KB_CUDA_TRY(cudaMemsetAsync(maxn1, 0, (size_t)B * 4, st));
-    KB_CUDA_TRY(cudaMemsetAsync(n_exact, 0, 4, st));
+    KB_CUDA_TRY(cudaMemsetAsync(n_exact, 0, 8, st));
     {
         PrepParams q;
         q.d = d0; q.cnt = n0; q.S = S0; q.c = c0; q.norm2 = norm2_0; q.maxn = maxn0;
         q.B = B; q.n_max = n_max; q.D = D; q.Dp = L.Dp; q.cs = L.cs0;
-        prep_kernel<<<dim3((L.cs0 * 32 + 255) / 256, B), 256, 0, st>>>(q);
+        prep_kernel<<<dim3(((L.cs0 + PREP_ROWS - 1) / PREP_ROWS * 32 + 255) / 256, B), 256, 0, st>>>(q);
         KB_LAUNCH_CHECK();
         q.d = d1; q.cnt = n1; q.S = S1; q.c = c1; q.norm2 = norm2_1; q.maxn = maxn1;
         q.n_max = m_max; q.cs = L.cs1;
-        prep_kernel<<<dim3((L.cs1 * 32 + 255) / 256, B), 256, 0, st>>>(q);
+        prep_kernel<<<dim3(((L.cs1 + PREP_ROWS - 1) / PREP_ROWS * 32 + 255) / 256, B), 256, 0, st>>>(q);
         KB_LAUNCH_CHECK();
     }
     CUtensorMap map0, map1;
@@ -762,7 +958,20 @@ int kb_match_tc_run(const float* d0, const float* d1, const int* n0, const int* 
     mp.n0 = n0; mp.n1 = n1; mp.c0 = c0; mp.c1 = c1; mp.res0 = res0; mp.res1 = res1;
     mp.B = B; mp.n_max = n_max; mp.m_max = m_max; mp.cs0 = L.cs0; mp.cs1 = L.cs1; mp.KB = L.KB;
     mp.tiles0 = L.tiles0; mp.tiles1 = L.tiles1; mp.n_dirs = cross_check ? 2 : 1;
-    const size_t smem = (size_t)(2 * L.KB + NSLOT) * TILE_BYTES + 1024 + 256 + 2 * BN * 4;
+    // after the tiles: barriers (256 bytes) and the 256-float c buffer; the tiles must start on a
+    // 1024-byte boundary (128B swizzle) -- dynamic shared memory normally does, `slack` covers the rest
+    const size_t fixed = 256 + BN * 4;
+    const size_t budget = 227 * 1024;
+    int n_slots = (int)((budget - fixed - (size_t)2 * L.KB * TILE_BYTES) / SLOT_BYTES);
+    if (n_slots > MAX_SLOTS) n_slots = MAX_SLOTS;
+    if (n_slots < 2) return KB_ERR_UNSUPPORTED;
+    const size_t used = (size_t)2 * L.KB * TILE_BYTES + (size_t)n_slots * SLOT_BYTES + fixed;
+    size_t slack = budget - used;
+    if (slack > 1024) slack = 1024;
+    mp.n_slots = n_slots;
+    mp.align_slack = (int)slack;
+    const size_t smem = used + slack;
+    { const char* e = getenv("KB_TC_DEBUG"); mp.dbg = e ? atoi(e) : 0; }
     KB_CUDA_TRY(cudaFuncSetAttribute(nn_top2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, sms = 0;
     KB_CUDA_TRY(cudaGetDevice(&dev));
@@ -775,20 +984,20 @@ int kb_match_tc_run(const float* d0, const float* d1, const int* n0, const int* 
     ResolveParams rp;
     rp.d0 = d0; rp.d1 = d1; rp.n0 = n0; rp.n1 = n1; rp.res0 = res0; rp.res1 = res1;
     rp.norm2_0 = norm2_0; rp.norm2_1 = norm2_1; rp.maxn0 = maxn0; rp.maxn1 = maxn1;
-    rp.nn0 = nn0; rp.nn1 = nn1; rp.n_exact = n_exact;
+    rp.nn0 = nn0; rp.nn1 = nn1; rp.n_exact = n_exact; rp.n_pair = n_exact + 1;
     rp.list = tb.list; rp.list_cap = B * (n_max + m_max);
     rp.B = B; rp.n_max = n_max; rp.m_max = m_max; rp.D = D; rp.n_dirs = mp.n_dirs;
     const int qmax = n_max > m_max ? n_max : m_max;
     resolve_kernel<<<dim3((qmax + 255) / 256, B, mp.n_dirs), 256, 0, st>>>(rp);
     KB_LAUNCH_CHECK();
     if ((size_t)D * 4 > 48 * 1024) return KB_ERR_UNSUPPORTED;
-    rescan_kernel<<<sms * 4, 256, (size_t)D * 4, st>>>(rp);
+    rescan_kernel<<<sms, RESCAN_WARPS * 32, (size_t)D * 4, st>>>(rp);
     KB_LAUNCH_CHECK();
 
     GateParams gp;
     gp.d0 = d0; gp.d1 = d1; gp.n0 = n0; gp.n1 = n1; gp.nn0 = nn0; gp.nn1 = nn1; gp.keep_j = tb.keep_j; gp.dist_i = d2_0;
     gp.n_max = n_max; gp.m_max = m_max; gp.D = D; gp.cross_check = cross_check; gp.max_distance = max_distance;
-    gate_kernel<<<dim3((n_max * 32 + 255) / 256, B), 256, 0, st>>>(gp);
+    gate_kernel<<<dim3(((n_max + 3) / 4 * 32 + 255) / 256, B), 256, 0, st>>>(gp);
     KB_LAUNCH_CHECK();
 
     PairsParams pp;

@@ -198,12 +198,17 @@ def match_tc_debug(ws: torch.Tensor, b: int, n: int, m: int, dd: int) -> dict:
     import ctypes
     off = (ctypes.c_size_t * 5)()
     check(lib.kb_match_tc_debug_offsets(b, n, m, dd, ctypes.cast(off, ctypes.c_void_p)), 'kb_match_tc_debug_offsets')
-    def rec(o, rows):
-        raw = ws[o:o + rows * 16].view(torch.float32).reshape(rows, 4)
-        idx = ws[o:o + rows * 16].view(torch.int32).reshape(rows, 4)[:, 2]
-        return raw[:, 0], raw[:, 1], idx
+    def rec(o, rows, slices=4):
+        # per row: `slices` records of 32 bytes (float best, second, third, pad; int argbest, argsecond, pad, pad),
+        # one per column slice of the epilogue; the resolver merges them -- here: best over the slices
+        raw = ws[o:o + rows * slices * 32].view(torch.float32).reshape(rows, slices, 8)
+        idx = ws[o:o + rows * slices * 32].view(torch.int32).reshape(rows, slices, 8)[:, :, 4]
+        best, arg = raw[:, :, 0].max(dim=1)
+        second = torch.where(torch.arange(slices, device=ws.device)[None, :] == arg[:, None],
+                             raw[:, :, 1], raw[:, :, 0]).max(dim=1).values
+        return best, second, idx.gather(1, arg[:, None])[:, 0]
     return {'res0': rec(off[0], b * n), 'res1': rec(off[1], b * m),
-            'n_exact': ws[off[2]:off[2] + 4].view(torch.int32),
+            'n_exact': ws[off[2]:off[2] + 4].view(torch.int32), 'n_pair': ws[off[2] + 4:off[2] + 8].view(torch.int32),
             'norm2_0': ws[off[3]:off[3] + 4 * b * n].view(torch.float32),
             'norm2_1': ws[off[4]:off[4] + 4 * b * m].view(torch.float32)}
 

@@ -44,7 +44,7 @@ def case(B, n, m, D, maxd=5.0, cc=True, seed=0, norm=True, verbose=True):
     ratio = float((err / bound).max())
     if verbose:
         print(f'B={B} n={n} m={m} D={D} maxd={maxd} cc={cc}: equal={ok} matches={int(c1.sum())} '
-              f'n_exact={int(dbg["n_exact"][0])} max_err={float(err.max()):.3e} err/bound={ratio:.3f}', flush=True)
+              f'n_exact={int(dbg["n_exact"][0])} n_pair={int(dbg["n_pair"][0])} max_err={float(err.max()):.3e} err/bound={ratio:.3f}', flush=True)
     return ok and ratio < 1.0
 
 
