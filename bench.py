@@ -44,6 +44,7 @@ def parse_args():
     ap.add_argument('--kind', default='uniform', help='synthetic score-map kind (uniform | alike)')
     ap.add_argument('--cpu-pairs', type=int, default=2, help='pairs timed on the host for cpu_baseline (0 = skip)')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='launch every kernel from Python instead of replaying a CUDA graph')
     return ap.parse_args()
 
 
@@ -260,41 +261,82 @@ def main():
     batch, hms = make_batch(cfg, cfg_index, P, rank * P, device, args.kind)
     task_rep = cfg.desc_dim == 0
 
-    def step(timer=None):
+    def step(timer=None, b=None):
+        b = batch if b is None else b
         if task_rep:
-            res = pipeline.repeatability_counts(batch, cfg, 3.0, timer)
+            res = pipeline.repeatability_counts(b, cfg, 3.0, timer)
             return res, pipeline.accumulate_repeatability(res)
-        res = pipeline.extract_match(batch, cfg, algo=algo, timer=timer)
+        res = pipeline.extract_match(b, cfg, algo=algo, timer=timer)
         return res, pipeline.accumulate_matches(res)
 
     sampler = ClockSampler(local_rank)
     for _ in range(max(args.warmup, 3)):
         step()
     torch.cuda.synchronize()
+    # per-stage device times: every stage alone, 5 back-to-back calls between two CUDA events on the launch
+    # stream (the stage's kernels queue up behind each other, so host launch gaps do not count)
+    l0 = ops.launches()
+    res0, _ = step()
+    launches_per_step = ops.launches() - l0
+    torch.cuda.synchronize()
+
+    def time_stage(fn, reps=5):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    stage_ms = {'detect': time_stage(lambda: ops.detect_batched(batch.score, cfg.extractor_params)),
+                'warp': time_stage(lambda: ops.warp_batched(res0['kpts'], res0['n_kpts'], batch.h33, batch.wh))}
+    if task_rep:
+        kv, kw, nv = res0['kcov'], res0['kwarp'], res0['n_cov']
+        stage_ms['repeat'] = time_stage(lambda: ops.repeat_batched(kv[:P], kw[:P], nv[:P], kv[P:], kw[P:], nv[P:], 512.0,
+                                                                   512.0, 3.0, want_errors=True))
+    else:
+        kv, nv, dd = res0['kcov'], res0['n_cov'], res0['desc']
+        stage_ms['sample'] = time_stage(lambda: ops.sample_batched(batch.desc, kv, nv))
+        stage_ms['match'] = time_stage(lambda: ops.match_batched(dd[:P], dd[P:], nv[:P], nv[P:], cfg.max_distance,
+                                                                 cfg.cross_check, algo=algo))
+    # steady state: the launch sequence of one step replayed as a CUDA graph (same kernels, same buffers)
+    graphed = None
+    if not args.no_graph:
+        try:
+            graphed = pipeline.GraphedStep(step)
+        except Exception as e:      # noqa: BLE001 -- fall back to eager launches, say so in the JSON line
+            config['cuda_graph_error'] = repr(e)[:200]
+            graphed = None
+            torch.cuda.synchronize()
+    config['launch'] = 'cuda graph replay of the step' if graphed is not None else 'eager launches from Python'
+    run = graphed if graphed is not None else step
+    for _ in range(2):
+        run()
+    torch.cuda.synchronize()
     parallel.barrier()
     torch.cuda.synchronize()
-    launches0 = ops.launches()
-    timer = StageTimer()
     acc = None
     ev0 = torch.cuda.Event(enable_timing=True)
     ev1 = torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
-        res, a = step(timer)
-        acc = a if acc is None else acc + a
+        res, a = run()
+        acc = a.clone() if acc is None else acc + a
     acc = parallel.reduce_counts(acc)               # the run's single collective
     ev1.record()
     torch.cuda.synchronize()
     parallel.barrier()
     torch.cuda.synchronize()
-    n_launch = ops.launches() - launches0
+    n_launch = launches_per_step * args.steps
     ms = ev0.elapsed_time(ev1)
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=device)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         ms = float(t.item())
     value = world * P * args.steps / (ms / 1000.0)
-    stage_ms = {k: v / args.steps for k, v in timer.totals().items()}
 
     # ---- end to end through the public API with HOST buffers -----------------------------------
     e2e = None
@@ -309,15 +351,24 @@ def main():
         out_n = torch.empty((P,), dtype=torch.int32).pin_memory()
         out_stats = torch.empty((P, 4), dtype=torch.float64).pin_memory()
 
+        e2e_run = None
+        if graphed is not None:
+            try:
+                e2e_run = pipeline.GraphedStep(lambda: step(None, hb))
+            except Exception:       # noqa: BLE001
+                e2e_run = None
+                torch.cuda.synchronize()
+        if e2e_run is None:
+            e2e_run = lambda: step(None, hb)        # noqa: E731
+
         def e2e_step():
             dev_score.copy_(host_score, non_blocking=True)
             if dev_desc is not None:
                 dev_desc.copy_(host_desc, non_blocking=True)
+            r, _ = e2e_run()
             if task_rep:
-                r = pipeline.repeatability_counts(hb, cfg, 3.0)
                 out_stats.copy_(r['stats'], non_blocking=True)
             else:
-                r = pipeline.extract_match(hb, cfg, algo=algo)
                 out_pairs.copy_(r['matches'], non_blocking=True)
                 out_n.copy_(r['n_matches'], non_blocking=True)
             torch.cuda.synchronize()                 # the caller consumes the result every step

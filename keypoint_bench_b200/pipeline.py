@@ -76,7 +76,7 @@ def repeatability_counts(batch: PairBatch, cfg: PathConfig, th: float = 3.0, tim
     num_feat = torch.minimum(count[:P], count[P:])
     empty = (nv[:P] == 0) | (nv[P:] == 0)                     # repeatability.py:61-67 -> zeros
     return {'stats': stats, 'errors': errors, 'num_feat': torch.where(empty, torch.zeros_like(num_feat), num_feat),
-            'n_kpts': count, 'n_cov': nv, 'empty': empty}
+            'kpts': xyp, 'n_kpts': count, 'kcov': kv, 'kwarp': kw, 'n_cov': nv, 'empty': empty}
 
 
 def accumulate_repeatability(res: dict) -> torch.Tensor:
@@ -90,11 +90,35 @@ def accumulate_repeatability(res: dict) -> torch.Tensor:
     mean_err = torch.where(has, st[:, 1] / gt.clamp(min=1), torch.zeros_like(gt))
     # pairs with no covisible keypoints report mean_error 0 (not NaN) in the reference
     counted = has | res['empty']
-    return torch.stack([rep.sum(), torch.tensor(float(st.shape[0]), dtype=torch.float64, device=st.device),
-                        mean_err.sum(), counted.to(torch.float64).sum(), nf.sum()])
+    return torch.stack([rep.sum(), st.new_full((), float(st.shape[0])), mean_err.sum(), counted.to(torch.float64).sum(),
+                        nf.sum()])
 
 
 def accumulate_matches(res: dict) -> torch.Tensor:
     """float64 [sum matches, n_pairs] (the stream / AUC configs count matches per pair)."""
     n = res['n_matches'].to(torch.float64)
-    return torch.stack([n.sum(), torch.tensor(float(n.numel()), dtype=torch.float64, device=n.device)])
+    return torch.stack([n.sum(), n.new_full((), float(n.numel()))])
+
+
+class GraphedStep:
+    """One pipeline step captured in a CUDA graph: the ~15 kernel launches of a step cost more host time than
+    device time when issued one by one from Python, so steady-state callers replay the captured launch
+    sequence instead.  ``fn`` must read its inputs from fixed device tensors (e.g. a PairBatch whose tensors
+    are refilled in place) and return a tuple/dict of device tensors, which keep their addresses."""
+
+    def __init__(self, fn, warmup: int = 2):
+        self.fn = fn
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                fn()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = fn()
+
+    def __call__(self):
+        self.graph.replay()
+        return self.out
