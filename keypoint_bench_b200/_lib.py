@@ -30,6 +30,8 @@ PROTOTYPES = {
     'kb_detect_workspace_bytes': (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_float]),
     'kb_detect': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_int, c_void_p, c_void_p,
                           c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'kb_detect_phases': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_int, c_void_p, c_void_p,
+                                 c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
     'kb_sample_desc': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
                                c_int, c_void_p, c_void_p]),
     'kb_match_workspace_bytes': (c_size_t, [c_int, c_int, c_int, c_int, c_int]),

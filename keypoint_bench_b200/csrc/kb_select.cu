@@ -14,7 +14,8 @@ int kb_nms_rounds_inplace(float* v, const float* src, int B, int H, int W, int n
 size_t kb_sparse_workspace_bytes(int B, int H, int W, int nms_dist, int top_k);
 int kb_sparse_detect(const float* score, int B, int H, int W, int nms_dist, int border, float threshold,
                      float min_score, int top_k, float* xyp, int* raster, int* count, int* path,
-                     int** need_fallback_out, int** any_fallback_out, void* ws, size_t ws_bytes, cudaStream_t st);
+                     int** need_fallback_out, int** any_fallback_out, void* ws, size_t ws_bytes, int phases,
+                     cudaStream_t st);
 
 namespace {
 
@@ -256,12 +257,12 @@ extern "C" size_t kb_detect_workspace_bytes(int B, int H, int W, int nms_dist, i
     return n + 1024;
 }
 
-extern "C" int kb_detect(const float* score, int B, int H, int W, int nms_dist, int border_dist, float threshold,
+extern "C" int kb_detect_phases(const float* score, int B, int H, int W, int nms_dist, int border_dist, float threshold,
                          float min_score, int top_k, float* xyp, int* raster, int* count, int* path, void* ws,
-                         size_t ws_bytes, kb_stream_t stream) {
+                         size_t ws_bytes, int phases, kb_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (!score || !xyp || !raster || !count || B <= 0 || H <= 0 || W <= 0 || nms_dist < 0 || border_dist < 0 ||
-        top_k <= 0)
+        top_k <= 0 || phases <= 0 || phases > 7)
         return KB_ERR_BAD_ARG;
     if (top_k > SORT_CAP) return KB_ERR_UNSUPPORTED;
     if (B > 2048) return KB_ERR_UNSUPPORTED;         // callers split larger batches
@@ -282,9 +283,10 @@ extern "C" int kb_detect(const float* score, int B, int H, int W, int nms_dist, 
     if (sparse) {
         // 1. sparse exact path for every map; maps it cannot certify are flagged on the device
         int rc = kb_sparse_detect(score, B, H, W, nms_dist, border_dist, threshold, min_score, top_k, xyp, raster,
-                                  count, path, &need_fallback, &any_fallback, sp_ws, sp_bytes, st);
+                                  count, path, &need_fallback, &any_fallback, sp_ws, sp_bytes, phases, st);
         if (rc != KB_OK) return rc;
     }
+    if (!(phases & 4)) return KB_OK;
     // 2. round-faithful NMS (each map on its own stopping rule) for the flagged maps -- all maps when
     //    the sparse path does not apply.  With nothing flagged both launches exit immediately.
     const float* sel_map = score;
@@ -299,4 +301,11 @@ extern "C" int kb_detect(const float* score, int B, int H, int W, int nms_dist, 
     p.total = nullptr; p.skip = need_fallback; p.want = 1;
     p.path = path; p.path_code = 2;      // round-faithful path
     return launch_select(p, st);
+}
+
+extern "C" int kb_detect(const float* score, int B, int H, int W, int nms_dist, int border_dist, float threshold,
+                         float min_score, int top_k, float* xyp, int* raster, int* count, int* path, void* ws,
+                         size_t ws_bytes, kb_stream_t stream) {
+    return kb_detect_phases(score, B, H, W, nms_dist, border_dist, threshold, min_score, top_k, xyp, raster, count,
+                            path, ws, ws_bytes, 7, stream);
 }

@@ -110,9 +110,11 @@ def select_batched(nms_map: torch.Tensor, border_dist: int, threshold: float, mi
     return xyp, count, raster, total
 
 
-def detect_batched(score: torch.Tensor, params: dict | None = None):
+def detect_batched(score: torch.Tensor, params: dict | None = None, phases: int = 7, state=None):
     """``detection`` (utils/extracter.py:193-221) for every map of the batch independently.
-    -> xyp[B,top_k,3] (x,y,p), count[B], raster[B,top_k], path[B]."""
+    -> xyp[B,top_k,3] (x,y,p), count[B], raster[B,top_k], path[B].
+    ``phases`` / ``state`` are a measurement hook (bench.py): ``state=[]`` receives the buffers of a full call,
+    a later call with the same ``state`` and ``phases`` in {1,2,4} re-runs just that kernel on them."""
     _require_cuda(score, 'score')
     if params is None:
         nms_dist, threshold, border_dist, top_k, min_score = 4, 0.0, 8, 300, 0.0   # extracter.py:200-205
@@ -121,16 +123,21 @@ def detect_batched(score: torch.Tensor, params: dict | None = None):
         top_k, min_score = params['top_k'], params['min_score']
     s = _maps3(score)
     b, h, w = s.shape
-    xyp = torch.zeros(b, top_k, 3, dtype=torch.float32, device=s.device)
-    raster = torch.zeros(b, top_k, dtype=torch.int32, device=s.device)
-    count = torch.zeros(b, dtype=torch.int32, device=s.device)
-    path = torch.zeros(b, dtype=torch.int32, device=s.device)
-    ws = _ws(lib.kb_detect_workspace_bytes(b, h, w, int(nms_dist), int(top_k), float(threshold)), s.device)
+    if state:
+        xyp, raster, count, path, ws = state
+    else:
+        xyp = torch.zeros(b, top_k, 3, dtype=torch.float32, device=s.device)
+        raster = torch.zeros(b, top_k, dtype=torch.int32, device=s.device)
+        count = torch.zeros(b, dtype=torch.int32, device=s.device)
+        path = torch.zeros(b, dtype=torch.int32, device=s.device)
+        ws = _ws(lib.kb_detect_workspace_bytes(b, h, w, int(nms_dist), int(top_k), float(threshold)), s.device)
+        if state is not None:
+            state.extend([xyp, raster, count, path, ws])
     with torch.cuda.device(s.device):
-        check(lib.kb_detect(s.data_ptr(), b, h, w, int(nms_dist), int(border_dist), float(threshold),
-                            float(min_score), int(top_k), xyp.data_ptr(), raster.data_ptr(), count.data_ptr(),
-                            path.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), 'kb_detect')
-    _count(2)
+        check(lib.kb_detect_phases(s.data_ptr(), b, h, w, int(nms_dist), int(border_dist), float(threshold),
+                                   float(min_score), int(top_k), xyp.data_ptr(), raster.data_ptr(), count.data_ptr(),
+                                   path.data_ptr(), ws.data_ptr(), ws.numel(), int(phases), _stream()), 'kb_detect')
+    _count(5 if phases == 7 else 1)       # threshold estimate, round-1, resolve, (fallback NMS, fallback select: early exit)
     return xyp, count, raster, path
 
 
