@@ -126,6 +126,7 @@ struct Tile {
     static constexpr int MWW = (MW + 31) / 32;                    // mask words per region row
     static constexpr int NBY = SH / BS, NBX = SW / BS;            // blocks of the staged tile
     static constexpr int OW = DTW / 32;                           // mask words per output row
+    static constexpr int SWW = (SW + 31) / 32;                    // mask words per staged row
     static constexpr size_t smem_bytes() {
         return (size_t)SH * SP * 4 + (size_t)NBY * NBX * 4 + (size_t)NBY * NBX + 16 +
                (size_t)(2 * MH + DTH) * MWW * 4 + (size_t)DTH * OW * 4 + 64;
@@ -154,9 +155,34 @@ __global__ void __launch_bounds__(DNT) round1_kernel(SparseParams p) {
     const float tau = p.tau[b];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-    // ---- stage the tile with a 2R halo (zero padding, extracter.py:58): one warp per row -------
+    // ---- stage the tile with a 2R halo (zero padding, extracter.py:58) ---------------------------
+    // 16-byte chunks when rows are 16-byte aligned (chunks then never straddle the image border),
+    // otherwise one warp per row with scalar loads.
     bool neg = false;
-    {
+    const bool vec = (R % 2 == 0) && (Wd % 4 == 0) && ((reinterpret_cast<uintptr_t>(img) & 15u) == 0);
+    if (vec) {
+        constexpr int C4 = T::SW / 4;                               // chunks per staged row
+        constexpr int N4 = T::SH * C4;
+        constexpr int PER = (N4 + DNT - 1) / DNT;
+        float4 val[PER];
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            const int idx = threadIdx.x + k * DNT;
+            const int sy = idx / C4, c4 = idx - sy * C4;
+            const int gy = y0 + sy - 2 * R, gx = x0 - 2 * R + 4 * c4;
+            val[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (idx < N4 && gy >= 0 && gy < H && gx >= 0 && gx < Wd)
+                val[k] = __ldg(reinterpret_cast<const float4*>(img + (size_t)gy * Wd + gx));
+        }
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            const int idx = threadIdx.x + k * DNT;
+            if (idx < N4) {
+                neg |= (val[k].x < 0.0f) | (val[k].y < 0.0f) | (val[k].z < 0.0f) | (val[k].w < 0.0f);
+                *reinterpret_cast<float4*>(S + 4 * idx) = val[k];   // SP == SW: the staged tile is dense
+            }
+        }
+    } else {
         constexpr int CH = (T::SW + 31) / 32;
         const int gx_base = x0 - 2 * R + lane;
         for (int sy = warp; sy < T::SH; sy += DNT / 32) {
@@ -205,7 +231,10 @@ __global__ void __launch_bounds__(DNT) round1_kernel(SparseParams p) {
     }
     __syncthreads();
 
-    // ---- 2. + 3. prefilter against whole neighbouring blocks, exact window check of the survivors
+    // ---- 2. + 3. prefilter against whole neighbouring blocks, exact check of the survivors -------
+    // Only maxima above tau matter: a maximum <= tau neither gets listed nor covers a pixel > tau, because
+    // everything within R of it scores lower.  The exact check is one warp per survivor, lanes over the
+    // (2R+1)^2 window entries.
     {
         constexpr int NB = T::NBY * T::NBX;
         for (int base = 0; base < NB; base += DNT) {
@@ -219,8 +248,8 @@ __global__ void __launch_bounds__(DNT) round1_kernel(SparseParams p) {
                 const int oy = pos / BS, ox = pos - oy * BS;
                 sy = by * BS + oy; sx = bx * BS + ox;
                 c = BV[blk];
-                // only pixels of the region (R inside the staged tile) can matter, and 0 is never a maximum
-                surv = c > 0.0f && sy >= R && sy < T::SH - R && sx >= R && sx < T::SW - R;
+                // only pixels of the region (R inside the staged tile) can matter
+                surv = c > tau && sy >= R && sy < T::SH - R && sx >= R && sx < T::SW - R;
                 if (surv) {
                     // blocks by+dy with BS*(by+dy) >= sy-R and BS*(by+dy)+BS-1 <= sy+R are inside the window
                     const int dy0 = -((R - oy) / BS), dy1 = (oy + R - BS + 1) / BS;
