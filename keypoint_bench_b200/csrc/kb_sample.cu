@@ -137,7 +137,13 @@ __global__ void __launch_bounds__(PL_NT, 2) sample_planes_kernel(SampleParams p)
     } else {
         for (int i = threadIdx.x; i < nc * hw; i += PL_NT) planes[i] = __ldg(src + i);
     }
-    // keypoint geometry of this thread's first keypoint while the copy is in flight
+    // keypoint coordinates go to shared memory while the plane copy is in flight (their global-load latency
+    // would otherwise sit on every thread's critical path once per keypoint)
+    float2* kxy = reinterpret_cast<float2*>(pl_smem + (size_t)PL_C * hw * 4);
+    for (int k = threadIdx.x; k < n; k += PL_NT) {
+        const float* pt = p.pts + ((size_t)b * p.n_max + k) * p.stride;
+        kxy[k] = make_float2(__ldg(pt), __ldg(pt + 1));
+    }
     __syncthreads();
     if (bulk) {
         uint32_t ok = 0;
@@ -150,8 +156,8 @@ __global__ void __launch_bounds__(PL_NT, 2) sample_planes_kernel(SampleParams p)
         }
     }
     for (int k = threadIdx.x; k < n; k += PL_NT) {
-        const float* pt = p.pts + ((size_t)b * p.n_max + k) * p.stride;
-        const float kx = pt[0], ky = pt[1];
+        const float2 kp = kxy[k];
+        const float kx = kp.x, ky = kp.y;
         float gx, gy;
         if (p.coord_mode == 0) {                        // matcher.py:221-222
             gx = (kx - 0.5f) * 2.0f;
@@ -192,8 +198,10 @@ __global__ void __launch_bounds__(PL_NT, 2) sample_planes_kernel(SampleParams p)
             }
         }
         float* o = p.out + ((size_t)b * p.n_max + k) * p.C + c0;
-        if (nc == PL_C && ((reinterpret_cast<uintptr_t>(o) & 15u) == 0)) {
-            *reinterpret_cast<float4*>(o) = make_float4(val[0], val[1], val[2], val[3]);
+        if (PL_C == 4 && nc == PL_C && ((reinterpret_cast<uintptr_t>(o) & 15u) == 0)) {
+            *reinterpret_cast<float4*>(o) = make_float4(val[0], val[1], val[2], val[PL_C - 1]);
+        } else if (PL_C == 2 && nc == PL_C && ((reinterpret_cast<uintptr_t>(o) & 7u) == 0)) {
+            *reinterpret_cast<float2*>(o) = make_float2(val[0], val[1]);
         } else {
             for (int c = 0; c < nc; ++c) o[c] = val[c];
         }
@@ -215,8 +223,8 @@ extern "C" int kb_sample_desc(const float* desc, int B, int C, int h, int w, con
     p.normalize = normalize; p.coord_mode = coord_mode; p.s = s;
     // low-resolution, densely sampled maps: stage whole planes (see sample_planes_kernel)
     const size_t plane_bytes = (size_t)h * w * 4;
-    if (!normalize && plane_bytes * PL_C <= 100 * 1024 && (size_t)n_max * 16 > (size_t)h * w) {
-        const size_t smem = plane_bytes * PL_C;
+    if (!normalize && plane_bytes * PL_C + (size_t)n_max * 8 <= 110 * 1024 && (size_t)n_max * 16 > (size_t)h * w) {
+        const size_t smem = plane_bytes * PL_C + (size_t)n_max * 8;
         KB_CUDA_TRY(cudaFuncSetAttribute(sample_planes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 grid((C + PL_C - 1) / PL_C, B);
         sample_planes_kernel<<<grid, PL_NT, smem, (cudaStream_t)stream>>>(p);
