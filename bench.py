@@ -393,6 +393,7 @@ def main():
     clocks = sampler.stop()
 
     if rank != 0:
+        parallel.shutdown()
         return 0
 
     # ---- roofline of the dominant kernel ---------------------------------------------------------
@@ -460,6 +461,7 @@ def main():
             'e2e': e2e, 'gpu_launches': n_launch, 'roofline': roof, 'cpu_baseline': cpu,
             'counts': {'sum_matches_or_rep': float(acc[0]), 'pairs': float(acc[1])}}
     print(json.dumps(line))
+    parallel.shutdown()
     return 0
 
 

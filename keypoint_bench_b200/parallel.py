@@ -23,7 +23,8 @@ def init(backend: str | None = None) -> tuple[int, int]:
         if backend == 'nccl':
             torch.cuda.set_device(local)
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+        kw = {'device_id': torch.device('cuda', local)} if backend == 'nccl' else {}
+        dist.init_process_group(backend=backend, rank=rank, world_size=world, **kw)
     return rank, world
 
 
@@ -53,6 +54,11 @@ def finalize_repeatability(acc: torch.Tensor) -> dict:
     a = acc.tolist()
     return {'repeatability': a[0] / a[1] if a[1] else 0.0, 'rep_mean_err': a[2] / a[3] if a[3] else float('nan'),
             'num_feat': a[4] / a[1] if a[1] else 0.0, 'pairs': int(a[1])}
+
+
+def shutdown() -> None:
+    if dist.is_initialized():
+        dist.destroy_process_group()
 
 
 def barrier() -> None:
