@@ -94,7 +94,7 @@ __device__ __forceinline__ float dist_mutual(const RepParams& p, const float2 a,
     const float d01 = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
     const float ex = __fsub_rn(bq.x, a1.x), ey = __fsub_rn(bq.y, a1.y);
     const float d10 = __fsqrt_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)));
-    float d = __fdiv_rn(__fadd_rn(d01, d10), 2.0f);         // repeatability.py:71
+    float d = __fmul_rn(__fadd_rn(d01, d10), 0.5f);         // repeatability.py:71 (x/2 == x*0.5 exactly in IEEE fp32)
     if (i == j && i < nd) d = 99999.0f;                     // repeatability.py:72-73
     return d;
 }

@@ -237,6 +237,19 @@ __global__ void __launch_bounds__(DNT) round1_kernel(SparseParams p) {
     // (2R+1)^2 window entries.
     {
         constexpr int NB = T::NBY * T::NBX;
+        constexpr int NK = (W * W + 31) / 32;
+        // lane-constant part of the exact check: offsets of this lane's window entries and whether they come
+        // earlier in raster order (bit k of `early`); entries past the window are parked on the centre
+        int woff[NK];
+        unsigned early = 0u;
+#pragma unroll
+        for (int k = 0; k < NK; ++k) {
+            const int idx = lane + 32 * k;
+            const int dy = idx / W - R, dx = idx - (idx / W) * W - R;
+            const bool in = idx < W * W;
+            woff[k] = in ? dy * T::SP + dx : 0;
+            if (in && (dy < 0 || (dy == 0 && dx < 0))) early |= 1u << k;
+        }
         for (int base = 0; base < NB; base += DNT) {
             const int blk = base + threadIdx.x;
             bool surv = false;
@@ -266,15 +279,11 @@ __global__ void __launch_bounds__(DNT) round1_kernel(SparseParams p) {
                 const int cy = __shfl_sync(0xffffffffu, sy, src), cx = __shfl_sync(0xffffffffu, sx, src);
                 const float cc = __shfl_sync(0xffffffffu, c, src);
                 bool bad = false;
+                const float* centre = S + cy * T::SP + cx;
 #pragma unroll
-                for (int k = 0; k < (W * W + 31) / 32; ++k) {
-                    const int idx = lane + 32 * k;
-                    if (idx < W * W) {
-                        const int dy = idx / W - R, dx = idx - (idx / W) * W - R;
-                        const float v = S[(cy + dy) * T::SP + cx + dx];
-                        const bool earlier = dy < 0 || (dy == 0 && dx < 0);
-                        bad |= earlier ? (v >= cc) : (v > cc);                 // the centre itself: v > cc is false
-                    }
+                for (int k = 0; k < NK; ++k) {
+                    const float v = centre[woff[k]];
+                    bad |= ((early >> k) & 1u) ? (v >= cc) : (v > cc);         // the centre itself: v > cc is false
                 }
                 if (!__any_sync(0xffffffffu, bad) && lane == 0) {
                     const int my = cy - R, mx = cx - R;                         // region coordinates
@@ -282,13 +291,6 @@ __global__ void __launch_bounds__(DNT) round1_kernel(SparseParams p) {
                 }
             }
         }
-    }
-    // ---- score > tau for the output pixels: one ballot per 32 pixels ----------------------------
-    for (int w = warp; w < DTH * T::OW; w += DNT / 32) {
-        const int y = w / T::OW, xw = w - y * T::OW;
-        const float v = S[(y + 2 * R) * T::SP + 2 * R + 32 * xw + lane];   // pixels outside the image hold 0 <= tau
-        const unsigned hb = __ballot_sync(0xffffffffu, v > tau);
-        if (lane == 0) TB[w] = hb;
     }
     __syncthreads();
 
@@ -326,7 +328,19 @@ __global__ void __launch_bounds__(DNT) round1_kernel(SparseParams p) {
         const uint32_t m_lo = mrow[ew], m_hi = ew + 1 < T::MWW ? mrow[ew + 1] : 0u;
         const uint32_t c_lo = crow[ew], c_hi = ew + 1 < T::MWW ? crow[ew + 1] : 0u;
         const uint32_t m1w = __funnelshift_r(m_lo, m_hi, R), covw = __funnelshift_r(c_lo, c_hi, R);
-        const uint32_t hitw = TB[threadIdx.x];
+        // score > tau of this thread's 32 output pixels (pixels outside the image hold 0 <= tau)
+        const float* srow = S + (ey + 2 * R) * T::SP + 2 * R + 32 * ew;
+        uint32_t hitw = 0u;
+        if ((2 * R) % 4 == 0) {                                     // 16-byte aligned rows
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float4 v = reinterpret_cast<const float4*>(srow)[q];
+                hitw |= ((v.x > tau ? 1u : 0u) | (v.y > tau ? 2u : 0u) | (v.z > tau ? 4u : 0u) | (v.w > tau ? 8u : 0u)) << (4 * q);
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 32; ++q) hitw |= (srow[q] > tau ? 1u : 0u) << q;
+        }
         emM = hitw & m1w;
         emO = hitw & ~m1w & ~covw;
     }

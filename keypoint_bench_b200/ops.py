@@ -17,6 +17,24 @@ from . import _lib
 from ._lib import check, lib
 
 _launches = 0          # kernels launched through this module (bench.py reports it)
+_zero_fill = True      # outputs are zero-initialised (rows beyond `count` read as zeros)
+
+
+class no_zero_fill:
+    """Context manager for steady-state callers (pipeline.py): outputs are allocated uninitialised, rows
+    beyond the per-map counts are then unspecified.  Saves a dozen fill kernels per step."""
+
+    def __enter__(self):
+        global _zero_fill
+        self.prev, _zero_fill = _zero_fill, False
+
+    def __exit__(self, *exc):
+        global _zero_fill
+        _zero_fill = self.prev
+
+
+def _out(*shape, dtype, device):
+    return torch.zeros(*shape, dtype=dtype, device=device) if _zero_fill else torch.empty(*shape, dtype=dtype, device=device)
 
 
 def launches() -> int:
@@ -97,8 +115,8 @@ def select_batched(nms_map: torch.Tensor, border_dist: int, threshold: float, mi
     b, h, w = s.shape
     if cap is None:
         cap = top_k if top_k > 0 else h * w
-    xyp = torch.zeros(b, cap, 3, dtype=torch.float32, device=s.device)
-    raster = torch.zeros(b, cap, dtype=torch.int32, device=s.device)
+    xyp = _out(b, cap, 3, dtype=torch.float32, device=s.device)
+    raster = _out(b, cap, dtype=torch.int32, device=s.device)
     count = torch.zeros(b, dtype=torch.int32, device=s.device)
     total = torch.zeros(b, dtype=torch.int32, device=s.device)
     ws = _ws(lib.kb_select_workspace_bytes(b, h, w, int(top_k)), s.device)
@@ -126,8 +144,8 @@ def detect_batched(score: torch.Tensor, params: dict | None = None, phases: int 
     if state:
         xyp, raster, count, path, ws = state
     else:
-        xyp = torch.zeros(b, top_k, 3, dtype=torch.float32, device=s.device)
-        raster = torch.zeros(b, top_k, dtype=torch.int32, device=s.device)
+        xyp = _out(b, top_k, 3, dtype=torch.float32, device=s.device)
+        raster = _out(b, top_k, dtype=torch.int32, device=s.device)
         count = torch.zeros(b, dtype=torch.int32, device=s.device)
         path = torch.zeros(b, dtype=torch.int32, device=s.device)
         ws = _ws(lib.kb_detect_workspace_bytes(b, h, w, int(nms_dist), int(top_k), float(threshold)), s.device)
@@ -157,7 +175,7 @@ def sample_batched(desc: torch.Tensor, pts: torch.Tensor, count: torch.Tensor | 
     if p.dim() != 3 or p.shape[0] != b or p.shape[2] < 2:
         raise _lib.KbError(f'pts must be [B,n,>=2] with B={b}, got {tuple(p.shape)}')
     n = p.shape[1]
-    out = torch.zeros(b, max(n, 1), c, dtype=torch.float32, device=d.device)
+    out = _out(b, max(n, 1), c, dtype=torch.float32, device=d.device)
     if n == 0:
         return out[:, :0]
     cnt = _i32(count)
@@ -183,8 +201,8 @@ def match_batched(d0: torch.Tensor, d1: torch.Tensor, n0: torch.Tensor | None = 
     m = bm.shape[1]
     if bm.shape[0] != b or bm.shape[2] != dd:
         raise ValueError('Descriptor length must equal.')
-    pairs = torch.zeros(b, max(n, 1), 2, dtype=torch.int32, device=a.device)
-    dist = torch.zeros(b, max(n, 1), dtype=torch.float64, device=a.device)
+    pairs = _out(b, max(n, 1), 2, dtype=torch.int32, device=a.device)
+    dist = _out(b, max(n, 1), dtype=torch.float64, device=a.device)
     count = torch.zeros(b, dtype=torch.int32, device=a.device)
     if n == 0 or m == 0:
         return pairs[:, :n], dist[:, :n], count
@@ -232,10 +250,10 @@ def warp_batched(pts: torch.Tensor, count: torch.Tensor | None, h33: torch.Tenso
     b, n = p.shape[0], p.shape[1]
     hm = _f32(h33).reshape(b, 9)
     whf = _f32(wh).reshape(b, 2)
-    kv = torch.zeros(b, max(n, 1), 2, dtype=torch.float32, device=p.device)
-    kw = torch.zeros_like(kv)
-    ids = torch.zeros(b, max(n, 1), dtype=torch.int32, device=p.device)
-    ids_out = torch.zeros_like(ids)
+    kv = _out(b, max(n, 1), 2, dtype=torch.float32, device=p.device)
+    kw = _out(b, max(n, 1), 2, dtype=torch.float32, device=p.device)
+    ids = _out(b, max(n, 1), dtype=torch.int32, device=p.device)
+    ids_out = _out(b, max(n, 1), dtype=torch.int32, device=p.device)
     nv = torch.zeros(b, dtype=torch.int32, device=p.device)
     if n == 0:
         return kv[:, :0], kw[:, :0], ids[:, :0], ids_out[:, :0], nv

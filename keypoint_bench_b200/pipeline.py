@@ -37,7 +37,13 @@ class PairBatch:
 def extract_match(batch: PairBatch, cfg: PathConfig, algo: int = -1, covisible_only: bool = True, timer=None) -> dict:
     """detect -> (covisible) -> sample -> match for every pair.  Returns padded device tensors:
     kpts [2P,top_k,3] + n_kpts [2P]; kcov [2P,top_k,2] + n_cov [2P] (when covisible_only);
-    matches [P,top_k,2] int32 (indices into the rows fed to the matcher) + n_matches [P]."""
+    matches [P,top_k,2] int32 (indices into the rows fed to the matcher) + n_matches [P].
+    Rows beyond the per-map counts are unspecified (outputs are not zero-filled here)."""
+    with ops.no_zero_fill():
+        return _extract_match(batch, cfg, algo, covisible_only, timer)
+
+
+def _extract_match(batch, cfg, algo, covisible_only, timer) -> dict:
     P = batch.pairs
     t = timer or (lambda name: None)
     t('detect')

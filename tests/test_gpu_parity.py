@@ -395,3 +395,58 @@ def test_sampling_plane_staged_path_cfg2_shape():
         ref = ref_ops.sample_brute_force(d[b].numpy(), p[b, :n].numpy())
         assert np.allclose(out[b, :n].cpu().numpy(), ref, rtol=1e-5, atol=1e-5)
     assert float(out[1, 873:].abs().max()) == 0.0          # rows beyond the count stay untouched (zero)
+
+
+# ------------------------------------------------------------------------------------------------ full-size configs
+
+@pytest.mark.parametrize('kind,h,w,r,top_k,want_path', [
+    ('alike', 480, 640, 6, 1000, 1),        # smooth, ALIKE-like map: blobs collapse to round-1 maxima
+    ('uniform', 480, 640, 4, 4096, 1),      # cfg3: top_k binds only with every listed candidate on chip
+    ('uniform', 376, 1241, 6, 1000, 1),     # cfg5: odd width, rows not 16-byte aligned (scalar staging)
+    ('relu', 480, 640, 6, 1000, 1),         # exact zeros (KeyNet-like)
+    ('ties', 480, 640, 6, 1000, None),      # eight distinct values: whichever path, result must be exact
+    ('alike', 240, 320, 3, 300, None),      # odd radius (unaligned halo)
+])
+def test_detection_full_size_configs_against_greedy_oracle(kind, h, w, r, top_k, want_path):
+    params = dict(nms_dist=r, threshold=0.0, border_dist=8, top_k=top_k, min_score=0.0)
+    m = synth.score_map(kind, h, w, 77 + r)
+    want, want_r = ref_ops.detection(m, params, nms='greedy')
+    xyp, count, raster, path = ops().detect_batched(m.to(DEV), params)
+    n = int(count[0])
+    assert n == want.shape[0], (kind, n, want.shape[0], int(path[0]))
+    assert np.array_equal(raster[0, :n].cpu().numpy().astype(np.int64), want_r), (kind, int(path[0]))
+    assert np.array_equal(xyp[0, :n].cpu().numpy(), want)
+    if want_path is not None:
+        assert int(path[0]) == want_path, (kind, int(path[0]))
+
+
+def test_pipeline_matches_per_pair_dropins_and_graph_replay():
+    """The batched pipeline (what bench.py times), its CUDA-graph replay and the per-pair drop-ins agree."""
+    from keypoint_bench_b200 import pipeline
+    from keypoint_bench_b200.utils.extracter import detection
+    from keypoint_bench_b200.utils.matcher import brute_force_matcher
+    from keypoint_bench_b200.utils.projection import warp
+    cfg = synth.PathConfig('t', 120, 160, 64, 8, True, 4, 200)
+    pairs = [synth.make_pair(cfg, 7, i) for i in range(3)]
+    P = len(pairs)
+    score = torch.cat([p['score0'] for p in pairs] + [p['score1'] for p in pairs]).to(DEV)
+    desc = torch.cat([p['desc0'] for p in pairs] + [p['desc1'] for p in pairs]).to(DEV)
+    h01 = torch.stack([p['H'] for p in pairs]).reshape(P, 9)
+    h10 = torch.stack([torch.linalg.inv(p['H'].double()).float() for p in pairs]).reshape(P, 9)
+    wh = torch.tensor([[160.0, 120.0]]).expand(2 * P, 2).contiguous()
+    batch = pipeline.PairBatch(score, desc, torch.cat([h01, h10]).to(DEV), wh.to(DEV))
+    res = pipeline.extract_match(batch, cfg)
+    graphed = pipeline.GraphedStep(lambda: pipeline.extract_match(batch, cfg))
+    res_g = graphed()
+    torch.cuda.synchronize()
+    for i, p in enumerate(pairs):
+        k0 = detection(p['score0'].to(DEV), cfg.extractor_params)
+        k1 = detection(p['score1'].to(DEV), cfg.extractor_params)
+        k0c, _, _, _ = warp(k0, p['warp01'])
+        k1c, _, _, _ = warp(k1, p['warp10'])
+        m0, m1 = brute_force_matcher(k0c, k1c, p['desc0'].to(DEV), p['desc1'].to(DEV), cfg.matcher_params)
+        for r in (res, res_g):
+            n = int(r['n_matches'][i])
+            assert n == m0.shape[0]
+            idx = r['matches'][i, :n].long()
+            assert torch.equal(r['kcov'][i][idx[:, 0]], m0[:, :2]) and torch.equal(r['kcov'][P + i][idx[:, 1]], m1[:, :2])
