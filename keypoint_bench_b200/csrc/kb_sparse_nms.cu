@@ -376,8 +376,12 @@ __device__ __forceinline__ void emit(const SparseParams& p, int b, int slot, flo
     p.raster[(size_t)b * p.top_k + slot] = (int)ras;
 }
 
+// Descending bitonic sort of a[0..n) (n a power of two) by the whole CTA.  Element i is always touched by
+// thread i % SP_NT or by its partner i ^ j, which lives in the same warp whenever j < 32: only the steps
+// with j >= 32 (and the first step of every merge) need a block-wide barrier, the rest a warp barrier.
 __device__ void bitonic_desc(uint64_t* a, int n) {
     for (int k = 2; k <= n; k <<= 1) {
+        if (k > 32) __syncthreads();
         for (int j = k >> 1; j > 0; j >>= 1) {
             for (int i = threadIdx.x; i < n; i += SP_NT) {
                 const int l = i ^ j;
@@ -387,9 +391,10 @@ __device__ void bitonic_desc(uint64_t* a, int n) {
                     if (desc ? (x < y) : (x > y)) { a[i] = y; a[l] = x; }
                 }
             }
-            __syncthreads();
+            if (j >= 32) __syncthreads(); else __syncwarp();
         }
     }
+    __syncthreads();
 }
 
 __device__ __forceinline__ int block_sum(int v, int* s_part) {
@@ -438,19 +443,30 @@ __global__ void __launch_bounds__(SP_NT, 1) sparse_kernel(SparseParams p) {
             // (any cut is exact, so the 12 low bits of the score key are not resolved)
             constexpr int PER = LIST_CAP / SP_NT;                 // 16
             const int per = (nM + SP_NT - 1) / SP_NT;
-            uint32_t k32[PER];
+            if (per <= 2) {                                       // the usual case: at most 2048 maxima listed
+                const uint32_t ka = threadIdx.x < nM ? (uint32_t)(LM[threadIdx.x] >> 32) : 0u;
+                const uint32_t kb2 = SP_NT + threadIdx.x < nM ? (uint32_t)(LM[SP_NT + threadIdx.x] >> 32) : 0u;
+                for (int bit = 31; bit >= 12; --bit) {
+                    const uint32_t t = tkey | (1u << bit);
+                    int c = __syncthreads_count(ka >= t);
+                    if (per == 2) c += __syncthreads_count(kb2 >= t);
+                    if ((long long)c >= ksel) tkey = t;
+                }
+            } else {
+                uint32_t k32[PER];
 #pragma unroll
-            for (int i = 0; i < PER; ++i) {
-                const int idx = i * SP_NT + threadIdx.x;
-                k32[i] = (i < per && idx < nM) ? (uint32_t)(LM[idx] >> 32) : 0u;
-            }
-            for (int bit = 31; bit >= 12; --bit) {
-                const uint32_t t = tkey | (1u << bit);
-                int c = 0;
+                for (int i = 0; i < PER; ++i) {
+                    const int idx = i * SP_NT + threadIdx.x;
+                    k32[i] = (i < per && idx < nM) ? (uint32_t)(LM[idx] >> 32) : 0u;
+                }
+                for (int bit = 31; bit >= 12; --bit) {
+                    const uint32_t t = tkey | (1u << bit);
+                    int c = 0;
 #pragma unroll
-                for (int i = 0; i < PER; ++i)
-                    if (i < per) c += __syncthreads_count(k32[i] >= t);
-                if ((long long)c >= ksel) tkey = t;
+                    for (int i = 0; i < PER; ++i)
+                        if (i < per) c += __syncthreads_count(k32[i] >= t);
+                    if ((long long)c >= ksel) tkey = t;
+                }
             }
         }
         const bool cut_complete = lists_complete && tkey == 0u;
