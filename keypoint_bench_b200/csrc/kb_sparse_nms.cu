@@ -12,10 +12,11 @@
 //   tau_kernel     per map: 4096 sampled pixels (128 runs of 32 floats) give the score tau above which
 //                  ~1/12 of the pixels lie; lower pixels are not listed at all.
 //   round1_kernel  THE streaming kernel (one read of every pixel, 32x128 tiles + 2r halo staged in shared
-//                  memory): separable (2r+1)-window maximum in registers (row strips, then column strips
-//                  with warp ballots), exact first-of-ties rule, 1-bit maxima mask dilated by r on 32-bit
-//                  words; emits two candidate lists per map as 64-bit priority keys: round-1 maxima > tau
-//                  and pixels > tau not covered by any round-1 maximum.  Everything else is decided.
+//                  memory with 16-byte loads): round-1 maxima found hierarchically (4x4 block maxima, a
+//                  prefilter against whole neighbouring blocks, an exact warp-wide window check of the few
+//                  survivors with the first-of-ties rule), 1-bit maxima mask dilated by r on 32-bit words;
+//                  emits two candidate lists per map as 64-bit priority keys: round-1 maxima > tau and
+//                  pixels > tau not covered by any round-1 maximum.  Everything else is decided.
 //   sparse_kernel  one CTA per map: takes the ~1.25*top_k best round-1 maxima and every uncovered
 //                  candidate at or above the weakest of them, bins them on a coarse cell grid in shared
 //                  memory and resolves the remaining keep/suppress decisions by priority (a candidate is
