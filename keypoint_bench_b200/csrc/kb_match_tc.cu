@@ -265,9 +265,11 @@ __global__ void __launch_bounds__(NT, 1) nn_top2_kernel(const __grid_constant__ 
     const uint32_t bars = b_slots + NSLOT * SLOT_BYTES;
     if (base - raw > (uint32_t)p.align_slack) __trap();             // the host sized the allocation for this slack
     // barrier map (8 bytes each)
-    const uint32_t bar_a_full = bars, bar_a_free = bars + 8;
-    const uint32_t bar_b_full = bars + 16, bar_b_empty = bars + 16 + 8 * MAX_SLOTS;
-    const uint32_t bar_t_full = bars + 16 + 16 * MAX_SLOTS, bar_t_empty = bar_t_full + 16;
+    // one (full, free) barrier pair per 64-wide K block of the query tile, so that the next item's query
+    // blocks are reloaded while the last column tile of the current item is still being multiplied
+    const uint32_t bar_a_full = bars, bar_a_free = bars + 32;
+    const uint32_t bar_b_full = bars + 64, bar_b_empty = bars + 64 + 8 * MAX_SLOTS;
+    const uint32_t bar_t_full = bars + 64 + 16 * MAX_SLOTS, bar_t_empty = bar_t_full + 16;
     const uint32_t tmem_slot = bar_t_empty + 16;
     float* cbuf = reinterpret_cast<float*>(smem_dyn + (tmem_slot + 16 - raw));     // [2][BN]
     volatile uint32_t* tmem_slot_ptr =
@@ -275,8 +277,7 @@ __global__ void __launch_bounds__(NT, 1) nn_top2_kernel(const __grid_constant__ 
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        mbar_init(bar_a_full, 1);
-        mbar_init(bar_a_free, 1);
+        for (int kb = 0; kb < 4; ++kb) { mbar_init(bar_a_full + 8 * kb, 1); mbar_init(bar_a_free + 8 * kb, 1); }
         for (int s = 0; s < NSLOT; ++s) { mbar_init(bar_b_full + 8 * s, 1); mbar_init(bar_b_empty + 8 * s, 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(bar_t_full + 8 * s, 1); mbar_init(bar_t_empty + 8 * s, EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -306,11 +307,14 @@ __global__ void __launch_bounds__(NT, 1) nn_top2_kernel(const __grid_constant__ 
             if (!decode_item(p, item, it)) continue;
             const CUtensorMap* qmap = it.dir ? &map1 : &map0;
             const CUtensorMap* dmap = it.dir ? &map0 : &map1;
-            mbar_wait(bar_a_free, a_phase ^ 1);                     // previous item's MMAs are done with A
-            if (issuer) {
-                mbar_expect_tx(bar_a_full, (uint32_t)(2 * KB) * TILE_BYTES);
-                for (int t = 0; t < 2 * KB; ++t)
-                    tma_load_2d(a_tiles + t * TILE_BYTES, qmap, t * BK, it.q_base + it.q_row0, bar_a_full);
+            for (int kb = 0; kb < KB; ++kb) {
+                mbar_wait(bar_a_free + 8 * kb, a_phase ^ 1);        // the previous item is done with this K block
+                if (issuer) {
+                    mbar_expect_tx(bar_a_full + 8 * kb, 2 * TILE_BYTES);
+                    tma_load_2d(a_tiles + kb * TILE_BYTES, qmap, kb * BK, it.q_base + it.q_row0, bar_a_full + 8 * kb);
+                    tma_load_2d(a_tiles + (KB + kb) * TILE_BYTES, qmap, (KB + kb) * BK, it.q_base + it.q_row0,
+                                bar_a_full + 8 * kb);
+                }
             }
             a_phase ^= 1;
             const int n_ct = (it.n_db + BN - 1) / BN;
@@ -341,15 +345,16 @@ __global__ void __launch_bounds__(NT, 1) nn_top2_kernel(const __grid_constant__ 
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             Item it;
             if (!decode_item(p, item, it)) continue;
-            mbar_wait(bar_a_full, a_phase);
-            a_phase ^= 1;
-            tc_fence_after();
             const int n_ct = (it.n_db + BN - 1) / BN;
             for (int ct = 0; ct < n_ct; ++ct) {
                 mbar_wait(bar_t_empty + 8 * acc_buf, ((t_phase >> acc_buf) & 1u) ^ 1u);   // epilogue drained this buffer
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc_buf * BN;
                 for (int kb = 0; kb < KB; ++kb) {
+                    if (ct == 0) {                                  // this item's query block has landed
+                        mbar_wait(bar_a_full + 8 * kb, a_phase);
+                        tc_fence_after();
+                    }
                     const uint64_t a_hi = desc0 | (uint64_t)((a_tiles + kb * TILE_BYTES) >> 4);
                     const uint64_t a_lo = desc0 | (uint64_t)((a_tiles + (KB + kb) * TILE_BYTES) >> 4);
                     // ---- database hi block: hi.hi and lo.hi
@@ -379,7 +384,10 @@ __global__ void __launch_bounds__(NT, 1) nn_top2_kernel(const __grid_constant__ 
                         tc_mma(d_tmem, a_hi + 4, bt + 4, IDESC, 1u);
                         tc_mma(d_tmem, a_hi + 6, bt + 6, IDESC, 1u);
                     }
-                    if (issuer) tc_commit(bar_b_empty + 8 * slot);
+                    if (issuer) {
+                        tc_commit(bar_b_empty + 8 * slot);
+                        if (ct == n_ct - 1) tc_commit(bar_a_free + 8 * kb);      // query block kb may be overwritten
+                    }
                     __syncwarp();
                     if (++slot == (uint32_t)NSLOT) { slot = 0; b_phase ^= 1; }
                 }
@@ -388,8 +396,7 @@ __global__ void __launch_bounds__(NT, 1) nn_top2_kernel(const __grid_constant__ 
                 t_phase ^= 1u << acc_buf;
                 acc_buf ^= 1;
             }
-            if (issuer) tc_commit(bar_a_free);                      // A tiles may be overwritten
-            __syncwarp();
+            a_phase ^= 1;
         }
     } else if (warp >= 4) {
         // ================================ epilogue ==============================================

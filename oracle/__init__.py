@@ -8,8 +8,8 @@ package; only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s
 Parity pinning: the reference ships no tests or golden vectors,
 so the restatements in ``oracle/ref_ops.py`` are pinned against OUTPUTS OF THE
 REFERENCE ITSELF, imported read-only from /root/reference in the authoring
-container by ``oracle/make_golden.py`` (fixtures in ``tests/golden/*.npz``) and by
-``oracle/check_against_reference.py`` (live equality run, log in
+container by ``oracle/make_golden.py`` (fixtures in ``tests/golden/*.npz``; the same run
+asserts live equality of every restatement with the reference and logs it in
 ``oracle/REFCHECK.log``).  The one third-party function on the path that is absent
 from the tree, ``skimage.feature.match_descriptors`` (scikit-image, unpinned in
 requirements.txt:13), is restated from its published algorithm over
