@@ -149,17 +149,21 @@ __device__ __forceinline__ float prep_finish_row(const PrepParams& p, int b, int
     return ss;
 }
 
-__global__ void __launch_bounds__(256) prep_kernel(PrepParams p) {
-    const int warp = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+struct PrepPair {
+    PrepParams side[2];       // d0 and d1 of the matcher, handled by one launch (blockIdx.z)
+};
+
+__global__ void __launch_bounds__(256) prep_kernel(PrepPair pp) {
+    const PrepParams& p = pp.side[blockIdx.z];
+    const int warp0 = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int n_warps = gridDim.x * 8;
     const int b = blockIdx.y;
-    const int row0 = warp * PREP_ROWS;
     __shared__ float s_max[8];
     float wmax = 0.0f;                      // max |row|^2 over this warp's rows (one atomic per CTA, not per row)
     const int n = p.cnt ? p.cnt[b] : p.n_max;
     const bool vec = (p.D & 3) == 0 && (reinterpret_cast<uintptr_t>(p.d) & 15u) == 0;
-    if (row0 >= p.cs) {
-        // nothing
-    } else if (vec && row0 + PREP_ROWS <= n) {
+    for (int row0 = warp0 * PREP_ROWS; row0 < p.cs; row0 += n_warps * PREP_ROWS)
+    if (vec && row0 + PREP_ROWS <= n) {
         // fast path: four valid rows, 4 components per lane and step
         const float* x = p.d + ((size_t)b * p.n_max + row0) * p.D;
         __nv_bfloat16* out = p.S + ((size_t)b * p.n_max + row0) * (2 * p.Dp);
@@ -511,6 +515,7 @@ __global__ void __launch_bounds__(NT, 1) nn_top2_kernel(const __grid_constant__ 
 // ------------------------------------------------------------------------------------------------
 // certification / exact resolution (one warp per query)
 // ------------------------------------------------------------------------------------------------
+struct RescanPart;
 struct ResolveParams {
     const float* d0;         // [B,n_max,D]
     const float* d1;         // [B,m_max,D]
@@ -528,6 +533,8 @@ struct ResolveParams {
     int* n_pair;             // [1] rows settled by the two-candidate exact check (statistics)
     int2* list;              // [list_cap] queued rows: (dir | b << 1, query row)
     int list_cap;
+    struct RescanPart* parts;   // [list_cap, RESCAN_SPLIT] partial minima of the split rescan
+    int* tickets;            // [list_cap] arrival counters of the splits (zeroed per call)
     int B, n_max, m_max, D, n_dirs;
 };
 
@@ -611,13 +618,15 @@ __global__ void __launch_bounds__(256) resolve_kernel(ResolveParams p) {
 // Exact float64 resolution of the queued rows (best/second closer than the error bound of the split
 // product, e.g. duplicated descriptors): one CTA per row, lanes over components, eight candidates in
 // flight per warp (16 independent 16-byte loads per lane at D=256).  First of ties wins, as np.argmin.
-constexpr int RESCAN_WARPS = 32;      // a queued row is rare but must not become a long tail: whole-SM CTA per row
+constexpr int RESCAN_WARPS = 8;
+constexpr int RESCAN_SPLIT = 8;       // a queued row is rare but must not become a long tail: one SM reads the
+                                      // database at ~60 GB/s, so every row is scanned by 8 CTAs (last one to finish merges)
 
 template <bool VEC>
-__device__ __forceinline__ void rescan_row(const float* xs, const float* DBs, int D, int ndb, int warp, int lane,
+__device__ __forceinline__ void rescan_row(const float* xs, const float* DBs, int D, int c_begin, int ndb, int warp, int lane,
                                            double& bd, int& bj) {
     constexpr int G = 8;
-    for (int c0 = warp * G; c0 < ndb; c0 += RESCAN_WARPS * G) {
+    for (int c0 = c_begin + warp * G; c0 < ndb; c0 += RESCAN_WARPS * G) {
         double acc[G];
 #pragma unroll
         for (int u = 0; u < G; ++u) acc[u] = 0.0;
@@ -658,15 +667,22 @@ __device__ __forceinline__ void rescan_row(const float* xs, const float* DBs, in
     }
 }
 
+struct RescanPart {
+    double d2;
+    int j, pad;
+};
+
 __global__ void __launch_bounds__(RESCAN_WARPS * 32) rescan_kernel(ResolveParams p) {
     extern __shared__ __align__(16) float xs[];
     __shared__ double s_d[RESCAN_WARPS];
     __shared__ int s_j[RESCAN_WARPS];
+    __shared__ int s_last;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int split = blockIdx.x;
     int total = *p.n_exact;
     if (total > p.list_cap) total = p.list_cap;
     const bool vec = (p.D & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.d0) | reinterpret_cast<uintptr_t>(p.d1)) & 15u) == 0;
-    for (int e = blockIdx.x; e < total; e += gridDim.x) {
+    for (int e = blockIdx.y; e < total; e += gridDim.y) {
         const int2 ent = p.list[e];
         const int dir = ent.x & 1, b = ent.x >> 1, q = ent.y;
         const int n = p.n0 ? p.n0[b] : p.n_max, m = p.n1 ? p.n1[b] : p.m_max;
@@ -674,13 +690,15 @@ __global__ void __launch_bounds__(RESCAN_WARPS * 32) rescan_kernel(ResolveParams
         const int q_stride = dir ? p.m_max : p.n_max, db_stride = dir ? p.n_max : p.m_max;
         const float* Q = (dir ? p.d1 : p.d0) + ((size_t)b * q_stride + q) * p.D;
         const float* DBs = (dir ? p.d0 : p.d1) + (size_t)b * db_stride * p.D;
+        const int chunk = ((ndb + RESCAN_SPLIT - 1) / RESCAN_SPLIT + 7) & ~7;
+        const int c_begin = split * chunk, c_end = min(ndb, c_begin + chunk);
         __syncthreads();
         for (int k = threadIdx.x; k < p.D; k += RESCAN_WARPS * 32) xs[k] = Q[k];
         __syncthreads();
         double bd = CUDART_INF;
         int bj = 0x7fffffff;
-        if (vec) rescan_row<true>(xs, DBs, p.D, ndb, warp, lane, bd, bj);
-        else rescan_row<false>(xs, DBs, p.D, ndb, warp, lane, bd, bj);
+        if (vec) rescan_row<true>(xs, DBs, p.D, c_begin, c_end, warp, lane, bd, bj);
+        else rescan_row<false>(xs, DBs, p.D, c_begin, c_end, warp, lane, bd, bj);
         if (lane == 0) { s_d[warp] = bd; s_j[warp] = bj; }
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -688,7 +706,23 @@ __global__ void __launch_bounds__(RESCAN_WARPS * 32) rescan_kernel(ResolveParams
             int j = s_j[0];
             for (int w = 1; w < RESCAN_WARPS; ++w)
                 if (s_d[w] < d2 || (s_d[w] == d2 && s_j[w] < j)) { d2 = s_d[w]; j = s_j[w]; }
-            (dir ? p.nn1 : p.nn0)[(size_t)b * q_stride + q] = j;
+            RescanPart part;
+            part.d2 = d2; part.j = j; part.pad = 0;
+            p.parts[(size_t)e * RESCAN_SPLIT + split] = part;
+            __threadfence();
+            s_last = atomicAdd(&p.tickets[e], 1) == RESCAN_SPLIT - 1;
+            if (s_last) {                                              // every split of this row has been published
+                __threadfence();
+                const volatile RescanPart* pp = p.parts + (size_t)e * RESCAN_SPLIT;
+                double best = pp[0].d2;
+                int bjj = pp[0].j;
+                for (int t = 1; t < RESCAN_SPLIT; ++t) {
+                    const double dt = pp[t].d2;
+                    const int jt = pp[t].j;
+                    if (dt < best || (dt == best && jt < bjj)) { best = dt; bjj = jt; }
+                }
+                (dir ? p.nn1 : p.nn0)[(size_t)b * q_stride + q] = bjj;
+            }
         }
     }
 }
@@ -869,6 +903,8 @@ static TcLayout tc_layout(int B, int n_max, int m_max, int D) {
     add(256);                                   // n_exact
     add((size_t)B * (n_max + m_max) * 8);       // rescan list
     add((size_t)B * n_max * 4);                 // keep_j
+    add((size_t)B * (n_max + m_max) * 8 * 16);  // rescan partial minima
+    add((size_t)B * (n_max + m_max) * 4);       // rescan tickets
     L.bytes = n + 1024;
     return L;
 }
@@ -883,6 +919,8 @@ struct TcBuffers {
     int* n_exact;
     int2* list;
     int* keep_j;
+    void* parts;
+    int* tickets;
     bool ok;
 };
 
@@ -905,6 +943,8 @@ static TcBuffers tc_carve(void* ws, size_t ws_bytes, int B, int n_max, int m_max
     t.n_exact = arena.take<int>(2);
     t.list = arena.take<int2>((size_t)B * (n_max + m_max));
     t.keep_j = arena.take<int>((size_t)B * n_max);
+    t.parts = arena.take<char>((size_t)B * (n_max + m_max) * 8 * 16);
+    t.tickets = arena.take<int>((size_t)B * (n_max + m_max));
     t.ok = arena.ok();
     return t;
 }
@@ -944,15 +984,25 @@ int kb_match_tc_run(const float* d0, const float* d1, const int* n0, const int* 
     KB_CUDA_TRY(cudaMemsetAsync(maxn0, 0, (size_t)B * 4, st));
     KB_CUDA_TRY(cudaMemsetAsync(maxn1, 0, (size_t)B * 4, st));
     KB_CUDA_TRY(cudaMemsetAsync(n_exact, 0, 8, st));
+    int dev = 0, sms = 0;
+    KB_CUDA_TRY(cudaGetDevice(&dev));
+    KB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     {
-        PrepParams q;
-        q.d = d0; q.cnt = n0; q.S = S0; q.c = c0; q.norm2 = norm2_0; q.maxn = maxn0;
-        q.B = B; q.n_max = n_max; q.D = D; q.Dp = L.Dp; q.cs = L.cs0;
-        prep_kernel<<<dim3(((L.cs0 + PREP_ROWS - 1) / PREP_ROWS * 32 + 255) / 256, B), 256, 0, st>>>(q);
-        KB_LAUNCH_CHECK();
-        q.d = d1; q.cnt = n1; q.S = S1; q.c = c1; q.norm2 = norm2_1; q.maxn = maxn1;
-        q.n_max = m_max; q.cs = L.cs1;
-        prep_kernel<<<dim3(((L.cs1 + PREP_ROWS - 1) / PREP_ROWS * 32 + 255) / 256, B), 256, 0, st>>>(q);
+        PrepPair pp;
+        PrepParams& q0 = pp.side[0];
+        q0.d = d0; q0.cnt = n0; q0.S = S0; q0.c = c0; q0.norm2 = norm2_0; q0.maxn = maxn0;
+        q0.B = B; q0.n_max = n_max; q0.D = D; q0.Dp = L.Dp; q0.cs = L.cs0;
+        PrepParams& q1 = pp.side[1];
+        q1 = q0;
+        q1.d = d1; q1.cnt = n1; q1.S = S1; q1.c = c1; q1.norm2 = norm2_1; q1.maxn = maxn1;
+        q1.n_max = m_max; q1.cs = L.cs1;
+        // one wave of CTAs: every warp walks over groups of PREP_ROWS rows
+        const int cs_max = L.cs0 > L.cs1 ? L.cs0 : L.cs1;
+        int ctas = (cs_max / PREP_ROWS + 7) / 8;                     // CTAs that give every warp one group
+        const int wave = (sms * 8 + 2 * B - 1) / (2 * B);               // CTAs per (batch, side) in one resident wave
+        if (ctas > wave) ctas = wave;
+        if (ctas < 1) ctas = 1;
+        prep_kernel<<<dim3(ctas, B, 2), 256, 0, st>>>(pp);
         KB_LAUNCH_CHECK();
     }
     CUtensorMap map0, map1;
@@ -980,9 +1030,6 @@ int kb_match_tc_run(const float* d0, const float* d1, const int* n0, const int* 
     const size_t smem = used + slack;
     { const char* e = getenv("KB_TC_DEBUG"); mp.dbg = e ? atoi(e) : 0; }
     KB_CUDA_TRY(cudaFuncSetAttribute(nn_top2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int dev = 0, sms = 0;
-    KB_CUDA_TRY(cudaGetDevice(&dev));
-    KB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int n_items = mp.n_dirs == 2 ? B * (L.tiles0 + L.tiles1) : B * L.tiles0;
     const int grid = n_items < sms ? n_items : sms;
     nn_top2_kernel<<<grid, NT, smem, st>>>(map0, map1, mp);
@@ -993,12 +1040,14 @@ int kb_match_tc_run(const float* d0, const float* d1, const int* n0, const int* 
     rp.norm2_0 = norm2_0; rp.norm2_1 = norm2_1; rp.maxn0 = maxn0; rp.maxn1 = maxn1;
     rp.nn0 = nn0; rp.nn1 = nn1; rp.n_exact = n_exact; rp.n_pair = n_exact + 1;
     rp.list = tb.list; rp.list_cap = B * (n_max + m_max);
+    rp.parts = (RescanPart*)tb.parts; rp.tickets = tb.tickets;
+    KB_CUDA_TRY(cudaMemsetAsync(tb.tickets, 0, (size_t)B * (n_max + m_max) * 4, st));
     rp.B = B; rp.n_max = n_max; rp.m_max = m_max; rp.D = D; rp.n_dirs = mp.n_dirs;
     const int qmax = n_max > m_max ? n_max : m_max;
     resolve_kernel<<<dim3((qmax + 255) / 256, B, mp.n_dirs), 256, 0, st>>>(rp);
     KB_LAUNCH_CHECK();
     if ((size_t)D * 4 > 48 * 1024) return KB_ERR_UNSUPPORTED;
-    rescan_kernel<<<sms, RESCAN_WARPS * 32, (size_t)D * 4, st>>>(rp);
+    rescan_kernel<<<dim3(RESCAN_SPLIT, sms), RESCAN_WARPS * 32, (size_t)D * 4, st>>>(rp);
     KB_LAUNCH_CHECK();
 
     GateParams gp;

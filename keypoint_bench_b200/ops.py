@@ -212,7 +212,7 @@ def match_batched(d0: torch.Tensor, d1: torch.Tensor, n0: torch.Tensor | None = 
         check(lib.kb_match_mnn(a.data_ptr(), bm.data_ptr(), _ptr(c0), _ptr(c1), b, n, m, dd, float(max_distance),
                                int(bool(cross_check)), int(algo), pairs.data_ptr(), dist.data_ptr(), count.data_ptr(),
                                ws.data_ptr(), ws.numel(), _stream()), 'kb_match_mnn')
-    _count(2 if (algo == 0 or dd > 256) else 7)
+    _count(2 if (algo == 0 or dd > 256) else 6)
     if return_ws:
         return pairs, dist, count, ws
     return pairs, dist, count
