@@ -540,9 +540,19 @@ struct ResolveParams {
 
 __device__ __forceinline__ double warp_dist2(const float* x, const float* y, int D, int lane) {
     double acc = 0.0;
-    for (int k = lane; k < D; k += 32) {
-        const double d = (double)x[k] - (double)y[k];
-        acc = fma(d, d, acc);
+    if ((D & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15u) == 0) {
+        for (int k = 4 * lane; k < D; k += 128) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(x + k)), b = __ldg(reinterpret_cast<const float4*>(y + k));
+            double d = (double)a.x - (double)b.x; acc = fma(d, d, acc);
+            d = (double)a.y - (double)b.y; acc = fma(d, d, acc);
+            d = (double)a.z - (double)b.z; acc = fma(d, d, acc);
+            d = (double)a.w - (double)b.w; acc = fma(d, d, acc);
+        }
+    } else {
+        for (int k = lane; k < D; k += 32) {
+            const double d = (double)x[k] - (double)y[k];
+            acc = fma(d, d, acc);
+        }
     }
     for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
     return acc;
