@@ -151,6 +151,24 @@ KB_API int kb_warp_homography(const float* pts, int pts_stride, const int* count
                        int* ids_out, int* n_valid, kb_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Stage 4a' -- warp_se3 + interpolate_depth                      utils/projection.py:194-267, 270-372
+ *
+ * Depth-based covisibility (warp(mode='se3'), the MegaDepth-style warp01_params of datasets/megadepth.py:333-352).
+ * pts [B,n_max,pts_stride] normalised (x,y); depth0 [B,h0,w0], depth1 [B,h1,w1]; kinv0 [B,9] = inverse of
+ * intrinsics0 (the reference inverts it on the fly, projection.py:46), k1 [B,9] = intrinsics1, pose01 [B,16]
+ * row-major 4x4, bbox0 / bbox1 [B,2] = (row, col) crop offsets.  A keypoint is scaled by (w0,h0), needs an
+ * interpolated depth in view 0 (four corners inside a 10-pixel border, all > 0), is unprojected (+bbox0 +0.5),
+ * moved, projected (-bbox1 -0.5) and compared with view 1's interpolated depth (|dz| < 0.05).  Outputs, in input
+ * order: kp_valid / kp_warp [B,n_max,2] (divided by (w0,h0) / (w1,h1)), ids [B,n_max], n_valid [B];
+ * ids_out [B,n_max] = points projected outside view 1's valid-corner area followed by the occluded ones,
+ * n_out [B].  Points without depth in either view appear in neither list (as in the reference).
+ * ------------------------------------------------------------------------------------------- */
+KB_API int kb_warp_se3(const float* pts, int pts_stride, const int* count, int B, int n_max, const float* depth0,
+                int h0, int w0, const float* depth1, int h1, int w1, const float* kinv0, const float* k1,
+                const float* pose01, const float* bbox0, const float* bbox1, float* kp_valid, float* kp_warp,
+                int* ids, int* ids_out, int* n_valid, int* n_out, kb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Stage 4b -- val_key_points core                              tasks/repeatability.py:39-51, 9-36, 69-85
  *
  * k0c/k01c [B,a_max,2], k1c/k10c [B,b_max,2] (outputs of kb_warp_homography both ways), na/nb [B].

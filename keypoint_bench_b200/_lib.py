@@ -40,6 +40,9 @@ PROTOTYPES = {
     'kb_match_tc_debug_offsets': (c_int, [c_int, c_int, c_int, c_int, c_void_p]),
     'kb_warp_homography': (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_void_p]),
+    'kb_warp_se3': (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p,
+                            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                            c_void_p]),
     'kb_repeat_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
     'kb_repeat_counts': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                  c_float, c_float, c_float, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_size_t,

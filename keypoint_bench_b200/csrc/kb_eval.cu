@@ -294,6 +294,119 @@ __global__ void corner_error_kernel(const double* h_est, const double* h_real, c
     for (int t = 0; t < n_th; ++t) flags[(size_t)b * n_th + t] = (ok && md <= th[t]) ? 1.0 : 0.0;   // MHA.py:68-72
 }
 
+// ------------------------------------------------------------------------------------------------
+// warp_se3 (utils/projection.py:194-267 with interpolate_depth :270-372): depth-based covisibility.
+// One CTA per map; every keypoint is classified (no depth in view 0 / projected outside view 1's
+// valid-corner area / no depth in view 1 / occluded / valid) and the lists are compacted in input order.
+// ------------------------------------------------------------------------------------------------
+struct Se3Params {
+    const float* pts;
+    const int* count;
+    const float* depth0;     // [B,h0,w0]
+    const float* depth1;     // [B,h1,w1]
+    const float* kinv0;      // [B,9]  inverse intrinsics of view 0
+    const float* k1;         // [B,9]
+    const float* pose;       // [B,16] row-major 4x4 (pose01)
+    const float* bbox0;      // [B,2] (row, col)
+    const float* bbox1;
+    float* kp_valid;
+    float* kp_warp;
+    int* ids;
+    int* ids_out;
+    int* n_valid;
+    int* n_out;
+    int stride, B, n_max, h0, w0, h1, w1;
+};
+
+// interpolate_depth for one point (x, y) in pixels: corners floor/ceil inside a 10-pixel border
+// (projection.py:289-301), all four corner depths > 0 (:321-324), bilinear weights from the floor corner
+// (:346-357).  Returns 0 = corners invalid, 1 = corners valid but a corner depth is missing, 2 = ok.
+__device__ __forceinline__ int interp_depth(const float* depth, int h, int w, float x, float y, float* z) {
+    const float border = 10.0f;
+    const float i0 = floorf(y), j0 = floorf(x), i1 = ceilf(y), j1 = ceilf(x);
+    // written so that NaN coordinates fail (torch's NaN -> long conversion never yields a valid corner)
+    const bool corners = (i0 >= border) && (j0 >= border) && (j1 < (float)w - border) && (i1 < (float)h - border);
+    if (!corners) return 0;
+    const int ii0 = (int)i0, jj0 = (int)j0, ii1 = (int)i1, jj1 = (int)j1;
+    const float d_tl = __ldg(depth + (size_t)ii0 * w + jj0), d_tr = __ldg(depth + (size_t)ii0 * w + jj1);
+    const float d_bl = __ldg(depth + (size_t)ii1 * w + jj0), d_br = __ldg(depth + (size_t)ii1 * w + jj1);
+    if (!(d_tl > 0.0f && d_tr > 0.0f && d_bl > 0.0f && d_br > 0.0f)) return 1;
+    const float di = __fsub_rn(y, i0), dj = __fsub_rn(x, j0);
+    const float omi = __fsub_rn(1.0f, di), omj = __fsub_rn(1.0f, dj);
+    const float w_tl = __fmul_rn(omi, omj), w_tr = __fmul_rn(omi, dj), w_bl = __fmul_rn(di, omj), w_br = __fmul_rn(di, dj);
+    *z = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w_tl, d_tl), __fmul_rn(w_tr, d_tr)), __fmul_rn(w_bl, d_bl)),
+                   __fmul_rn(w_br, d_br));
+    return 2;
+}
+
+constexpr int SE3_NT = 1024;
+
+__global__ void __launch_bounds__(SE3_NT) warp_se3_kernel(Se3Params p) {
+    extern __shared__ int s_occ[];            // ids of occluded points (appended after the outside ones)
+    __shared__ int s_scan[33];
+    const int b = blockIdx.x;
+    const int n = p.count ? p.count[b] : p.n_max;
+    const float* d0 = p.depth0 + (size_t)b * p.h0 * p.w0;
+    const float* d1 = p.depth1 + (size_t)b * p.h1 * p.w1;
+    const float* Ki = p.kinv0 + (size_t)b * 9;
+    const float* K1 = p.k1 + (size_t)b * 9;
+    const float* T = p.pose + (size_t)b * 16;
+    const float b0r = p.bbox0[b * 2 + 0], b0c = p.bbox0[b * 2 + 1], b1r = p.bbox1[b * 2 + 0], b1c = p.bbox1[b * 2 + 1];
+    const float fw0 = (float)p.w0, fh0 = (float)p.h0, fw1 = (float)p.w1, fh1 = (float)p.h1;
+    int n_in = 0, n_outside = 0, n_occ = 0;
+    for (int base = 0; base < n; base += SE3_NT) {
+        const int i = base + threadIdx.x;
+        int cls = 0;                          // 0 dropped, 1 valid, 2 outside, 3 occluded
+        float x = 0, y = 0, ux = 0, vy = 0;
+        if (i < n) {
+            const float* pt = p.pts + ((size_t)b * p.n_max + i) * p.stride;
+            x = __fmul_rn(pt[0], fw0);                                        // projection.py:202
+            y = __fmul_rn(pt[1], fh0);
+            float z0;
+            if (interp_depth(d0, p.h0, p.w0, x, y, &z0) == 2) {               // projection.py:209
+                const float bx = __fadd_rn(__fadd_rn(x, b0c), 0.5f);          // COLMAP convention (:212)
+                const float by = __fadd_rn(__fadd_rn(y, b0r), 0.5f);
+                const float du = __fmul_rn(bx, z0), dv = __fmul_rn(by, z0);   // unproject (:44-48)
+                const float X = fmaf(Ki[2], z0, fmaf(Ki[1], dv, __fmul_rn(Ki[0], du)));
+                const float Y = fmaf(Ki[5], z0, fmaf(Ki[4], dv, __fmul_rn(Ki[3], du)));
+                const float Z = fmaf(Ki[8], z0, fmaf(Ki[7], dv, __fmul_rn(Ki[6], du)));
+                const float X1 = __fadd_rn(fmaf(T[2], Z, fmaf(T[1], Y, __fmul_rn(T[0], X))), T[3]);     // pose01 (:219)
+                const float Y1 = __fadd_rn(fmaf(T[6], Z, fmaf(T[5], Y, __fmul_rn(T[4], X))), T[7]);
+                const float Z1 = __fadd_rn(fmaf(T[10], Z, fmaf(T[9], Y, __fmul_rn(T[8], X))), T[11]);
+                const float qx = fmaf(K1[2], Z1, fmaf(K1[1], Y1, __fmul_rn(K1[0], X1)));                // project (:71-77)
+                const float qy = fmaf(K1[5], Z1, fmaf(K1[4], Y1, __fmul_rn(K1[3], X1)));
+                const float qz = fmaf(K1[8], Z1, fmaf(K1[7], Y1, __fmul_rn(K1[6], X1)));
+                ux = __fsub_rn(__fsub_rn(qx / qz, b1c), 0.5f);                // projection.py:225
+                vy = __fsub_rn(__fsub_rn(qy / qz, b1r), 0.5f);
+                float z1;
+                const int r1 = interp_depth(d1, p.h1, p.w1, ux, vy, &z1);     // projection.py:232
+                if (r1 == 0) cls = 2;                                         // :234-237 projected outside
+                else if (r1 == 2) cls = (fabsf(__fsub_rn(qz, z1)) < 0.05f) ? 1 : 3;     // :244-247
+            }
+        }
+        int t_in, t_outside, t_occ;
+        const int o_in = n_in + kb::block_exclusive_scan(cls == 1 ? 1 : 0, s_scan, &t_in);
+        const int o_outside = n_outside + kb::block_exclusive_scan(cls == 2 ? 1 : 0, s_scan, &t_outside);
+        const int o_occ = n_occ + kb::block_exclusive_scan(cls == 3 ? 1 : 0, s_scan, &t_occ);
+        if (cls == 1) {
+            const size_t o = ((size_t)b * p.n_max + o_in) * 2;
+            p.kp_valid[o + 0] = x / fw0;                                      // projection.py:265-266
+            p.kp_valid[o + 1] = y / fh0;
+            p.kp_warp[o + 0] = ux / fw1;
+            p.kp_warp[o + 1] = vy / fh1;
+            p.ids[(size_t)b * p.n_max + o_in] = i;
+        } else if (cls == 2) {
+            p.ids_out[(size_t)b * p.n_max + o_outside] = i;
+        } else if (cls == 3) {
+            s_occ[o_occ] = i;
+        }
+        n_in += t_in; n_outside += t_outside; n_occ += t_occ;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < n_occ; k += SE3_NT) p.ids_out[(size_t)b * p.n_max + n_outside + k] = s_occ[k];   // :259
+    if (threadIdx.x == 0) { p.n_valid[b] = n_in; p.n_out[b] = n_outside + n_occ; }
+}
+
 }  // namespace
 
 extern "C" int kb_warp_homography(const float* pts, int pts_stride, const int* count, int B, int n_max,
@@ -360,6 +473,26 @@ extern "C" int kb_corner_error(const double* h_est, const double* h_real, const 
         return KB_ERR_BAD_ARG;
     corner_error_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h_est, h_real, valid, B, w, h, resize_h,
                                                                             resize_w, th, n_th, mean_dist, flags);
+    KB_LAUNCH_CHECK();
+    return KB_OK;
+}
+
+extern "C" int kb_warp_se3(const float* pts, int pts_stride, const int* count, int B, int n_max, const float* depth0,
+                           int h0, int w0, const float* depth1, int h1, int w1, const float* kinv0, const float* k1,
+                           const float* pose01, const float* bbox0, const float* bbox1, float* kp_valid,
+                           float* kp_warp, int* ids, int* ids_out, int* n_valid, int* n_out, kb_stream_t stream) {
+    if (!pts || !depth0 || !depth1 || !kinv0 || !k1 || !pose01 || !bbox0 || !bbox1 || !kp_valid || !kp_warp || !ids ||
+        !ids_out || !n_valid || !n_out || B <= 0 || n_max <= 0 || pts_stride < 2 || h0 <= 0 || w0 <= 0 || h1 <= 0 || w1 <= 0)
+        return KB_ERR_BAD_ARG;
+    if ((size_t)n_max * 4 > 200 * 1024) return KB_ERR_UNSUPPORTED;
+    Se3Params p;
+    p.pts = pts; p.count = count; p.depth0 = depth0; p.depth1 = depth1; p.kinv0 = kinv0; p.k1 = k1; p.pose = pose01;
+    p.bbox0 = bbox0; p.bbox1 = bbox1; p.kp_valid = kp_valid; p.kp_warp = kp_warp; p.ids = ids; p.ids_out = ids_out;
+    p.n_valid = n_valid; p.n_out = n_out; p.stride = pts_stride; p.B = B; p.n_max = n_max;
+    p.h0 = h0; p.w0 = w0; p.h1 = h1; p.w1 = w1;
+    const size_t smem = (size_t)n_max * 4;
+    KB_CUDA_TRY(cudaFuncSetAttribute(warp_se3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    warp_se3_kernel<<<B, SE3_NT, smem, (cudaStream_t)stream>>>(p);
     KB_LAUNCH_CHECK();
     return KB_OK;
 }

@@ -266,6 +266,38 @@ def warp_batched(pts: torch.Tensor, count: torch.Tensor | None, h33: torch.Tenso
     return kv, kw, ids, ids_out, nv
 
 
+def warp_se3_batched(pts: torch.Tensor, count: torch.Tensor | None, depth0: torch.Tensor, depth1: torch.Tensor,
+                     k0: torch.Tensor, k1: torch.Tensor, pose01: torch.Tensor, bbox0: torch.Tensor, bbox1: torch.Tensor):
+    """``warp_se3`` (utils/projection.py:194-267) per map.  pts [B,n,>=2]; depth0 [B,h0,w0]; depth1 [B,h1,w1];
+    k0 / k1 [B,3,3] intrinsics; pose01 [B,4,4]; bbox0 / bbox1 [B,2] (row, col).
+    -> kp_valid[B,n,2], kp_warp[B,n,2], ids[B,n], ids_out[B,n], n_valid[B], n_out[B]."""
+    _require_cuda(pts, 'pts')
+    p = _f32(pts)
+    b, n = p.shape[0], p.shape[1]
+    d0, d1 = _f32(depth0).reshape(b, depth0.shape[-2], depth0.shape[-1]), _f32(depth1).reshape(b, depth1.shape[-2], depth1.shape[-1])
+    # the reference inverts intrinsics0 in float32 on the fly (projection.py:46); float64 here, rounded once
+    kinv = torch.linalg.inv(k0.to(device=p.device, dtype=torch.float64)).to(torch.float32).reshape(b, 9).contiguous()
+    k1f = _f32(k1.to(p.device)).reshape(b, 9)
+    pose = _f32(pose01.to(p.device)).reshape(b, 16)
+    bb0, bb1 = _f32(bbox0.to(p.device)).reshape(b, 2), _f32(bbox1.to(p.device)).reshape(b, 2)
+    kv = _out(b, max(n, 1), 2, dtype=torch.float32, device=p.device)
+    kw = _out(b, max(n, 1), 2, dtype=torch.float32, device=p.device)
+    ids = _out(b, max(n, 1), dtype=torch.int32, device=p.device)
+    ids_out = _out(b, max(n, 1), dtype=torch.int32, device=p.device)
+    nv = torch.zeros(b, dtype=torch.int32, device=p.device)
+    no = torch.zeros(b, dtype=torch.int32, device=p.device)
+    if n == 0:
+        return kv[:, :0], kw[:, :0], ids[:, :0], ids_out[:, :0], nv, no
+    cnt = _i32(count)
+    with torch.cuda.device(p.device):
+        check(lib.kb_warp_se3(p.data_ptr(), p.shape[2], _ptr(cnt), b, n, d0.data_ptr(), d0.shape[1], d0.shape[2], d1.data_ptr(),
+                              d1.shape[1], d1.shape[2], kinv.data_ptr(), k1f.data_ptr(), pose.data_ptr(), bb0.data_ptr(),
+                              bb1.data_ptr(), kv.data_ptr(), kw.data_ptr(), ids.data_ptr(), ids_out.data_ptr(), nv.data_ptr(),
+                              no.data_ptr(), _stream()), 'kb_warp_se3')
+    _count(1)
+    return kv, kw, ids, ids_out, nv, no
+
+
 def repeat_batched(k0c, k01c, na, k1c, k10c, nb, scale01: float, scale10: float, th: float, want_errors: bool = True,
                    pair_cap: int = 0):
     """Counting core of ``val_key_points`` (tasks/repeatability.py:69-85).

@@ -184,3 +184,48 @@ def make_pair(cfg: PathConfig, cfg_index: int, pair_idx: int, kind: str = 'unifo
         d1 = warp_map(d0, hd, 'bilinear') + 0.05 * torch.randn(d0.shape, generator=g, device=device)
         out['desc0'], out['desc1'] = d0, d1
     return out
+
+
+def se3_scene(h: int, w: int, seed: int, device="cpu") -> dict:
+    """Synthetic two-view depth scene with the ``warp01_params`` schema of datasets/megadepth.py:333-352
+    (mode 'se3'): a smooth depth map for view 0, a small rigid motion, and view 1's depth rendered by
+    forward-warping view 0 (nearest pixel, nearest depth wins) -- which leaves holes (depth 0), the
+    'no depth' branch of utils/projection.py:interpolate_depth -- plus a closer occluder patch."""
+    g = _gen(seed)
+    ys, xs = torch.meshgrid(torch.arange(h, dtype=torch.float64), torch.arange(w, dtype=torch.float64), indexing='ij')
+    depth0 = 4.0 + 0.8 * torch.sin(xs / 37.0) * torch.cos(ys / 29.0) + 0.002 * xs
+    holes = torch.rand(h, w, generator=g, dtype=torch.float64) < 0.03
+    depth0 = torch.where(holes, torch.zeros_like(depth0), depth0)
+    f = 0.9 * w
+    k0 = torch.tensor([[f, 0.0, w / 2.0 + 3.0], [0.0, f * 1.02, h / 2.0 - 2.0], [0.0, 0.0, 1.0]], dtype=torch.float64)
+    k1 = torch.tensor([[f * 0.97, 0.0, w / 2.0 - 4.0], [0.0, f, h / 2.0 + 1.0], [0.0, 0.0, 1.0]], dtype=torch.float64)
+    ang = torch.tensor([0.02, -0.03, 0.015], dtype=torch.float64) * (1 + 0.2 * (2 * torch.rand(3, generator=g, dtype=torch.float64) - 1))
+    cx, cy, cz = torch.cos(ang)
+    sx, sy, sz = torch.sin(ang)
+    rx = torch.tensor([[1, 0, 0], [0, cx, -sx], [0, sx, cx]], dtype=torch.float64)
+    ry = torch.tensor([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]], dtype=torch.float64)
+    rz = torch.tensor([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]], dtype=torch.float64)
+    pose = torch.eye(4, dtype=torch.float64)
+    pose[:3, :3] = rz @ ry @ rx
+    pose[:3, 3] = torch.tensor([0.25, -0.1, 0.15], dtype=torch.float64)
+    bbox0 = torch.tensor([3.0, 5.0])          # (row, col) offsets of the crops, COLMAP convention
+    bbox1 = torch.tensor([2.0, 7.0])
+    # render depth1: unproject every valid pixel of view 0, move it, project, keep the nearest depth
+    valid = depth0 > 0
+    u = xs[valid] + bbox0[1].double() + 0.5
+    v = ys[valid] + bbox0[0].double() + 0.5
+    d = depth0[valid]
+    pts = torch.linalg.inv(k0) @ torch.stack([u * d, v * d, d])
+    pts1 = pose[:3, :3] @ pts + pose[:3, 3:4]
+    q = k1 @ pts1
+    z = q[2]
+    px = torch.round(q[0] / z - bbox1[1].double() - 0.5).long()
+    py = torch.round(q[1] / z - bbox1[0].double() - 0.5).long()
+    ok = (px >= 0) & (px < w) & (py >= 0) & (py < h) & (z > 0)
+    depth1 = torch.full((h * w,), float('inf'), dtype=torch.float64)
+    depth1.scatter_reduce_(0, (py[ok] * w + px[ok]), z[ok], reduce='amin')
+    depth1 = torch.where(torch.isinf(depth1), torch.zeros_like(depth1), depth1).reshape(h, w)
+    depth1[h // 3:h // 3 + h // 8, w // 2:w // 2 + w // 6] *= 0.7          # an occluder in view 1
+    f32 = lambda t: t.to(torch.float32).to(device)      # noqa: E731
+    return {'mode': 'se3', 'width': w, 'height': h, 'pose01': f32(pose), 'bbox0': bbox0.to(device), 'bbox1': bbox1.to(device),
+            'depth0': f32(depth0), 'depth1': f32(depth1), 'intrinsics0': f32(k0), 'intrinsics1': f32(k1)}

@@ -229,6 +229,31 @@ def gen_eval(ref):
     np.savez_compressed(os.path.join(GOLD, 'ref_eval.npz'), **out)
 
 
+SE3_CASES = [('se3_240x320', 240, 320, 31, 600), ('se3_480x640', 480, 640, 32, 1000)]
+
+
+def gen_se3(ref):
+    """warp(mode='se3') (utils/projection.py:194-267) on synthetic two-view depth scenes."""
+    out = {}
+    for tag, h, w, seed, n in SE3_CASES:
+        params = synth.se3_scene(h, w, seed)
+        g = torch.Generator().manual_seed(seed + 1)
+        kp = torch.rand(n, 3, generator=g)
+        a, b, ids, ids_out = ref.projection.warp(kp, params)
+        ma, mb, mids, mids_out = ref_ops.warp(kp.numpy(), params)
+        assert np.array_equal(ids.numpy(), mids) and np.array_equal(ids_out.numpy(), mids_out), tag
+        assert np.allclose(a.numpy(), ma, rtol=1e-5, atol=1e-6) and np.allclose(b.numpy(), mb, rtol=1e-5, atol=1e-5), tag
+        log(f'warp se3 {tag}: n={n} valid={ids.shape[0]} out={ids_out.shape[0]} '
+            f'(no-depth {n - ids.shape[0] - ids_out.shape[0]}) restatement equal')
+        out[f'{tag}__kp'] = kp.numpy()
+        out[f'{tag}__valid'] = a.numpy()
+        out[f'{tag}__proj'] = b.numpy()
+        out[f'{tag}__ids'] = ids.numpy()
+        out[f'{tag}__ids_out'] = ids_out.numpy()
+        out[f'{tag}__depth_sha'] = np.array(sha(params['depth0'].numpy()) + sha(params['depth1'].numpy()))
+    np.savez_compressed(os.path.join(GOLD, 'ref_se3.npz'), **out)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
@@ -238,6 +263,7 @@ def main():
     gen_detect(ref)
     gen_match(ref)
     gen_eval(ref)
+    gen_se3(ref)
     with open(os.path.join(ROOT, 'oracle', 'REFCHECK.log'), 'w') as f:
         f.write('\n'.join(LOG) + '\n')
 

@@ -373,10 +373,79 @@ def warp_homography(kpts, params: dict):
     return (p[valid] / scale).astype(np.float32), (uv[valid] / scale).astype(np.float32), ids, ids_out
 
 
+def _np32(v):
+    return (v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)).astype(np.float32)
+
+
+def interpolate_depth(pos: np.ndarray, depth: np.ndarray):
+    """utils/projection.py:270-372 -- pos [N,2] (x,y) in pixels.  Corners floor/ceil of (i=y, j=x) must lie
+    inside a 10-pixel border (:289-301), all four corner depths must be > 0 (:321-324), bilinear weights
+    from the floor corner (:346-357).  Returns (depth, pos_valid, ids, ids_valid_corners, ids_valid_depth)."""
+    border = 10
+    pos = np.asarray(pos, dtype=np.float32)
+    h, w = depth.shape
+    i, j = pos[:, 1], pos[:, 0]
+    with np.errstate(invalid='ignore'):
+        i0, j0 = np.floor(i).astype(np.int64), np.floor(j).astype(np.int64)
+        i1, j1 = np.ceil(i).astype(np.int64), np.ceil(j).astype(np.int64)
+    valid_corners = (i0 >= border) & (j0 >= border) & (j1 < w - border) & (i1 < h - border)
+    ids_c = np.flatnonzero(valid_corners).astype(np.int64)
+    i0c, j0c, i1c, j1c = i0[ids_c], j0[ids_c], i1[ids_c], j1[ids_c]
+    vd = (depth[i0c, j0c] > 0) & (depth[i0c, j1c] > 0) & (depth[i1c, j0c] > 0) & (depth[i1c, j1c] > 0)
+    ids = ids_c[vd]
+    i0v, j0v, i1v, j1v = i0c[vd], j0c[vd], i1c[vd], j1c[vd]
+    di = (i[ids] - i0v.astype(np.float32)).astype(np.float32)
+    dj = (j[ids] - j0v.astype(np.float32)).astype(np.float32)
+    one = np.float32(1)
+    w_tl, w_tr = (one - di) * (one - dj), (one - di) * dj
+    w_bl, w_br = di * (one - dj), di * dj
+    z = (w_tl * depth[i0v, j0v] + w_tr * depth[i0v, j1v] + w_bl * depth[i1v, j0v] + w_br * depth[i1v, j1v]).astype(np.float32)
+    return z, pos[ids], ids, ids_c, ids
+
+
+def warp_se3(kpts, params: dict):
+    """utils/projection.py:194-267 -- depth-based covisibility: keypoints (normalised x,y) are scaled by
+    (w0,h0), given a depth by interpolate_depth (view 0), unprojected with K0 (crop offset bbox0 + 0.5, COLMAP
+    convention), moved by pose01, projected with K1, and checked against view 1's interpolated depth
+    (|z_proj - z_interp| < 0.05).  Returns (kpts0_valid, kpts01_valid, ids_valid, ids_out) with
+    ids_out = [projected outside view 1's valid-corner area] ++ [occluded]."""
+    k = np.asarray(kpts, dtype=np.float32)[:, :2]
+    depth0, depth1 = _np32(params['depth0']), _np32(params['depth1'])
+    k0m, k1m, pose = _np32(params['intrinsics0']), _np32(params['intrinsics1']), _np32(params['pose01'])
+    bbox0, bbox1 = _np32(params['bbox0']), _np32(params['bbox1'])
+    wh0 = np.array([depth0.shape[1], depth0.shape[0]], dtype=np.float32)
+    wh1 = np.array([depth1.shape[1], depth1.shape[0]], dtype=np.float32)
+    px = k * wh0
+    z0, k0v, ids0, _, _ = interpolate_depth(px, depth0)
+    bk = k0v + bbox0[[1, 0]][None, :] + np.float32(0.5)
+    duv1 = np.concatenate([bk * z0[:, None], z0[:, None]], axis=1).astype(np.float32)
+    kinv = np.linalg.inv(k0m.astype(np.float64)).astype(np.float32)
+    p3 = (duv1 @ kinv.T).astype(np.float32)
+    p3h = np.concatenate([p3, np.ones((p3.shape[0], 1), np.float32)], axis=1)
+    p31 = (p3h @ pose.T)[:, :3].astype(np.float32)
+    zuv = (p31 @ k1m.T).astype(np.float32)
+    with np.errstate(divide='ignore', invalid='ignore'):
+        uv = (zuv / zuv[:, 2:3])[:, :2]
+    z01 = zuv[:, 2]
+    uv01 = (uv - bbox1[[1, 0]][None, :] - np.float32(0.5)).astype(np.float32)
+    z01i, k01v, ids01, ids01_c, _ = interpolate_depth(uv01, depth1)
+    outside = np.ones(ids0.shape[0], bool)
+    outside[ids01_c] = False
+    ids_outside = ids0[outside]
+    ids_valid = ids0[ids01]
+    k0v = k0v[ids01]
+    inlier = np.abs(z01[ids01] - z01i) < 0.05
+    ids_occ = ids_valid[~inlier]
+    return ((k0v[inlier] / wh0).astype(np.float32), (k01v[inlier] / wh1).astype(np.float32), ids_valid[inlier],
+            np.concatenate([ids_outside, ids_occ]))
+
+
 def warp(kpts, params: dict):
-    """utils/projection.py:185-192 -- dispatch on params['mode']; only 'homo' is on the path."""
+    """utils/projection.py:185-192 -- dispatch on params['mode']."""
     if params['mode'] == 'homo':
         return warp_homography(np.asarray(kpts)[:, 0:2], params)
+    if params['mode'] == 'se3':
+        return warp_se3(np.asarray(kpts)[:, 0:2], params)
     raise ValueError('unknown mode!')
 
 

@@ -450,3 +450,35 @@ def test_pipeline_matches_per_pair_dropins_and_graph_replay():
             assert n == m0.shape[0]
             idx = r['matches'][i, :n].long()
             assert torch.equal(r['kcov'][i][idx[:, 0]], m0[:, :2]) and torch.equal(r['kcov'][P + i][idx[:, 1]], m1[:, :2])
+
+
+# ------------------------------------------------------------------------------------------------ warp(mode='se3')
+
+def test_warp_se3_matches_reference_fixtures_and_oracle(golden):
+    """utils/projection.py:194-267: ids exact, coordinates 1e-5 (the reference's own torch.inverse /
+    einsum roundings are not reproducible bit for bit)."""
+    from keypoint_bench_b200.utils.projection import warp
+    from oracle.make_golden import SE3_CASES
+    g = golden('ref_se3.npz')
+    for tag, h, w, seed, n in SE3_CASES:
+        params = synth.se3_scene(h, w, seed)
+        kp = torch.from_numpy(g[f'{tag}__kp']).to(DEV)
+        a, b, ids, ids_out = warp(kp, params)
+        assert np.array_equal(ids.cpu().numpy(), g[f'{tag}__ids']), tag
+        assert np.array_equal(ids_out.cpu().numpy(), g[f'{tag}__ids_out']), tag
+        assert np.allclose(a.cpu().numpy(), g[f'{tag}__valid'], rtol=1e-5, atol=1e-6)
+        assert np.allclose(b.cpu().numpy(), g[f'{tag}__proj'], rtol=1e-5, atol=1e-5)
+    # batched entry point, ragged counts, against the oracle
+    params = [synth.se3_scene(120, 160, 50 + i) for i in range(3)]
+    gen = torch.Generator().manual_seed(9)
+    pts = torch.rand(3, 300, 2, generator=gen)
+    cnt = torch.tensor([300, 17, 0], dtype=torch.int32)
+    st = lambda k: torch.stack([p[k] for p in params]).to(DEV)      # noqa: E731
+    kv, kw, ids, ids_out, nv, no = ops().warp_se3_batched(pts.to(DEV), cnt.to(DEV), st('depth0'), st('depth1'), st('intrinsics0'),
+                                                          st('intrinsics1'), st('pose01'), st('bbox0'), st('bbox1'))
+    for i in range(3):
+        wa, wb, wids, wout = ref_ops.warp_se3(pts[i, :int(cnt[i])].numpy(), params[i])
+        a, o = int(nv[i]), int(no[i])
+        assert np.array_equal(ids[i, :a].cpu().numpy().astype(np.int64), wids), i
+        assert np.array_equal(ids_out[i, :o].cpu().numpy().astype(np.int64), wout), i
+        assert np.allclose(kv[i, :a].cpu().numpy(), wa, rtol=1e-5, atol=1e-6) and np.allclose(kw[i, :a].cpu().numpy(), wb, rtol=1e-5, atol=1e-5)

@@ -149,3 +149,15 @@ def test_greedy_equals_rounds_on_random_positive_maps():
             if trial == 1:
                 v = np.floor(v * 6) / 6            # heavy ties, includes exact zeros
             assert np.array_equal(ref_ops.nms_greedy(v, r), ref_ops.nms_rounds_separable(v, r))
+
+
+def test_warp_se3_restatement_matches_reference(golden):
+    """warp(mode='se3') (utils/projection.py:194-267): ids exact, coordinates 1e-5."""
+    from oracle.make_golden import SE3_CASES
+    g = golden('ref_se3.npz')
+    for tag, h, w, seed, n in SE3_CASES:
+        params = synth.se3_scene(h, w, seed)
+        assert sha(params['depth0'].numpy()) + sha(params['depth1'].numpy()) == str(g[f'{tag}__depth_sha']), tag
+        a, b, ids, ids_out = ref_ops.warp(g[f'{tag}__kp'], params)
+        assert np.array_equal(ids, g[f'{tag}__ids']) and np.array_equal(ids_out, g[f'{tag}__ids_out']), tag
+        assert np.allclose(a, g[f'{tag}__valid'], rtol=1e-5, atol=1e-6) and np.allclose(b, g[f'{tag}__proj'], rtol=1e-5, atol=1e-5)
