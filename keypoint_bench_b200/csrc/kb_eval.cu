@@ -80,6 +80,7 @@ struct RepParams {
     unsigned int* rowmin;   // [B,a_max] float bits (distances are >= 0: uint order == float order)
     unsigned int* colmin;   // [B,b_max]
     unsigned int* gmax;     // [B]
+    const int* only_flagged; // [B] or null: the exhaustive kernels skip maps with only_flagged[b] == 0
     double* stats;          // [B,4]
     float* errors;          // [B,a_max] or null
     int* pairs;             // [B,pair_cap,2] or null
@@ -104,6 +105,7 @@ constexpr int RB = 8;
 
 __global__ void __launch_bounds__(RT) rep_minima_kernel(RepParams p) {
     const int b = blockIdx.y;
+    if (p.only_flagged && !p.only_flagged[b]) return;
     const int A = p.na ? p.na[b] : p.a_max, Bn = p.nb ? p.nb[b] : p.b_max;
     const int i0 = blockIdx.x * RB;
     if (i0 >= A || Bn <= 0) return;
@@ -162,6 +164,7 @@ __global__ void __launch_bounds__(RT) rep_minima_kernel(RepParams p) {
 
 __global__ void __launch_bounds__(RT) rep_mutual_kernel(RepParams p) {
     const int b = blockIdx.y;
+    if (p.only_flagged && !p.only_flagged[b]) return;
     const int A = p.na ? p.na[b] : p.a_max, Bn = p.nb ? p.nb[b] : p.b_max;
     const int i0 = blockIdx.x * RB;
     if (i0 >= A || Bn <= 0) return;
@@ -229,6 +232,183 @@ __global__ void rep_init_kernel(RepParams p) {
     if (i < (size_t)p.B) p.gmax[i] = 0u;
     if (i < (size_t)p.B * 4) p.stats[i] = 0.0;
     if (p.errors && i < na) p.errors[i] = 0.0f;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Pruned variant of the two sweeps above (the default): eight lanes own one row (or column) of dist_mutual
+// and walk over the other side's points staged in shared memory.  Since
+//     dist_mutual = (|a - b0| + |bq - a1|) / 2  >=  max(|a - b0|, |bq - a1|) / 2,
+// an entry whose squared lower bound exceeds the (squared) running minimum cannot lower it and is skipped
+// before the two IEEE square roots -- almost every entry is.  The values that ARE evaluated use exactly the
+// arithmetic of dist_mutual(), so minima, counts and sums are identical to the exhaustive sweeps.
+// Precondition (rep_bound_kernel): every distance is < 99999, so min(-dist_mutual) = -99999 comes from the
+// masked diagonal (repeatability.py:72-73); maps that violate it take the exhaustive kernels.
+// ------------------------------------------------------------------------------------------------
+constexpr int PT = 128;      // threads per block
+constexpr int PL = 8;        // lanes that share one row (column): they split the other side's points
+constexpr int PR = PT / PL;  // rows (columns) per block
+constexpr int PTILE = 512;   // points of the other side per shared-memory tile
+
+__global__ void __launch_bounds__(256) rep_bound_kernel(RepParams p, int* need_bf) {
+    __shared__ float s_m[8];
+    const int b = blockIdx.x;
+    const int A = p.na ? p.na[b] : p.a_max, Bn = p.nb ? p.nb[b] : p.b_max;
+    float m = 0.0f;
+    bool bad = false;
+    for (int i = threadIdx.x; i < 2 * A; i += 256) {
+        const float v0 = fabsf(p.k0c[(size_t)b * p.a_max * 2 + i]), v1 = fabsf(p.k01c[(size_t)b * p.a_max * 2 + i]);
+        bad |= !(v0 <= 1e30f) || !(v1 <= 1e30f);
+        m = fmaxf(m, fmaxf(v0, v1));
+    }
+    for (int i = threadIdx.x; i < 2 * Bn; i += 256) {
+        const float v0 = fabsf(p.k1c[(size_t)b * p.b_max * 2 + i]), v1 = fabsf(p.k10c[(size_t)b * p.b_max * 2 + i]);
+        bad |= !(v0 <= 1e30f) || !(v1 <= 1e30f);
+        m = fmaxf(m, fmaxf(v0, v1));
+    }
+    if (bad) m = CUDART_INF_F;
+    for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
+    if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) m = fmaxf(m, s_m[w]);
+        // |p - q| <= 2*sqrt(2)*m per term, so every distance is <= 3*m
+        const bool ok = A > 0 && Bn > 0 && (3.0f * m < 99999.0f);
+        need_bf[b] = ok ? 0 : 1;
+        if (ok) p.gmax[b] = __float_as_uint(99999.0f);
+    }
+}
+
+// SIDE 0: one thread per row i (minimum over the columns); SIDE 1: one thread per column j.
+template <int SIDE>
+__global__ void __launch_bounds__(PT) rep_min_pruned_kernel(RepParams p, const int* need_bf) {
+    __shared__ float4 s_pts[PTILE];
+    const int b = blockIdx.y;
+    if (need_bf[b]) return;
+    const int A = p.na ? p.na[b] : p.a_max, Bn = p.nb ? p.nb[b] : p.b_max;
+    const int n_own = SIDE ? Bn : A, n_oth = SIDE ? A : Bn;
+    if (blockIdx.x * PR >= n_own) return;
+    const int nd = A < Bn ? A : Bn;
+    const int own = blockIdx.x * PR + threadIdx.x / PL, sub = threadIdx.x % PL;
+    const bool live = own < n_own;
+    // the two point sets of this map: "first" pairs with image-0 coordinates, "second" with image-1 coordinates
+    const float2* own1 = reinterpret_cast<const float2*>(SIDE ? p.k10c : p.k0c) + (size_t)b * (SIDE ? p.b_max : p.a_max);
+    const float2* own2 = reinterpret_cast<const float2*>(SIDE ? p.k1c : p.k01c) + (size_t)b * (SIDE ? p.b_max : p.a_max);
+    const float2* oth1 = reinterpret_cast<const float2*>(SIDE ? p.k0c : p.k10c) + (size_t)b * (SIDE ? p.a_max : p.b_max);
+    const float2* oth2 = reinterpret_cast<const float2*>(SIDE ? p.k01c : p.k1c) + (size_t)b * (SIDE ? p.a_max : p.b_max);
+    const float2 P = live ? own1[own] : make_float2(0.f, 0.f), Q = live ? own2[own] : make_float2(0.f, 0.f);
+    float best = CUDART_INF_F, thr = CUDART_INF_F;
+    for (int t0 = 0; t0 < n_oth; t0 += PTILE) {
+        __syncthreads();
+        for (int t = threadIdx.x; t < PTILE && t0 + t < n_oth; t += PT) {
+            const float2 o1 = oth1[t0 + t], o2 = oth2[t0 + t];
+            s_pts[t] = make_float4(o1.x, o1.y, o2.x, o2.y);
+        }
+        __syncthreads();
+        const int nt = min(PTILE, n_oth - t0);
+        for (int t = sub; live && t < nt; t += PL) {
+            const float4 o = s_pts[t];
+            // (x - y)^2 == (y - x)^2 exactly, so the operand order of dist_mutual() does not matter here
+            const float dx = __fsub_rn(P.x, o.x), dy = __fsub_rn(P.y, o.y);
+            const float s1 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+            if (s1 * 0.25f > thr) continue;
+            const float ex = __fsub_rn(o.z, Q.x), ey = __fsub_rn(o.w, Q.y);
+            const float s2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+            if (s2 * 0.25f > thr) continue;
+            float d = __fmul_rn(__fadd_rn(__fsqrt_rn(s1), __fsqrt_rn(s2)), 0.5f);         // repeatability.py:69-71
+            if (t0 + t == own && own < nd) d = 99999.0f;                                  // repeatability.py:72-73
+            if (d < best) { best = d; thr = d * d * 1.0001f; }
+        }
+        // the PL lanes of a row share their running minimum once per tile (tighter pruning)
+#pragma unroll
+        for (int m = PL / 2; m > 0; m >>= 1) best = fminf(best, __shfl_xor_sync(0xffffffffu, best, m));
+        thr = best * best * 1.0001f;
+    }
+    if (live && sub == 0) {
+        if (SIDE == 0) {
+            p.rowmin[(size_t)b * p.a_max + own] = __float_as_uint(best);
+            if (p.errors) p.errors[(size_t)b * p.a_max + own] = __fmul_rn(best, p.scale10);      // :78,85
+        } else {
+            p.colmin[(size_t)b * p.b_max + own] = __float_as_uint(best);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(PT) rep_mutual_pruned_kernel(RepParams p, const int* need_bf) {
+    __shared__ float4 s_pts[PTILE];
+    __shared__ unsigned int s_cmin[PTILE];
+    __shared__ int s_gt[PT / 32], s_np[PT / 32];
+    __shared__ double s_sum[PT / 32];
+    const int b = blockIdx.y;
+    if (need_bf[b]) return;
+    const int A = p.na ? p.na[b] : p.a_max, Bn = p.nb ? p.nb[b] : p.b_max;
+    if (blockIdx.x * PR >= A) return;
+    const int nd = A < Bn ? A : Bn;
+    const int i = blockIdx.x * PR + threadIdx.x / PL, sub = threadIdx.x % PL;
+    const bool live = i < A;
+    const float2* k0c = reinterpret_cast<const float2*>(p.k0c) + (size_t)b * p.a_max;
+    const float2* k01c = reinterpret_cast<const float2*>(p.k01c) + (size_t)b * p.a_max;
+    const float2* k1c = reinterpret_cast<const float2*>(p.k1c) + (size_t)b * p.b_max;
+    const float2* k10c = reinterpret_cast<const float2*>(p.k10c) + (size_t)b * p.b_max;
+    const float vmin = -__uint_as_float(p.gmax[b]);          // = -99999: value.min() of repeatability.py:18
+    const float2 a = live ? k0c[i] : make_float2(0.f, 0.f), a1 = live ? k01c[i] : make_float2(0.f, 0.f);
+    const float rmin = live ? __uint_as_float(p.rowmin[(size_t)b * p.a_max + i]) : 0.0f;
+    const float rq = __fsub_rn(-rmin, vmin);                 // row maximum of v = (-d) - min(-d)
+    // v has a resolution of one ulp of 99999 (2^-7): every d that rounds onto rq lies within 2 ulps of the
+    // row minimum; everything farther is skipped before the square roots
+    const float lim = rmin + 0.0172f;
+    const float thr = lim * lim * 1.0001f;
+    int gt = 0, np = 0;
+    double sum = 0.0;
+    for (int t0 = 0; t0 < Bn; t0 += PTILE) {
+        __syncthreads();
+        for (int t = threadIdx.x; t < PTILE && t0 + t < Bn; t += PT) {
+            const float2 o1 = k10c[t0 + t], o2 = k1c[t0 + t];
+            s_pts[t] = make_float4(o1.x, o1.y, o2.x, o2.y);
+            s_cmin[t] = p.colmin[(size_t)b * p.b_max + t0 + t];
+        }
+        __syncthreads();
+        const int nt = min(PTILE, Bn - t0);
+        for (int t = sub; live && t < nt; t += PL) {
+            const float4 o = s_pts[t];
+            const float dx = __fsub_rn(a.x, o.x), dy = __fsub_rn(a.y, o.y);
+            const float s1 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+            const int j = t0 + t;
+            const bool diag = (j == i && i < nd);
+            if (!diag && s1 * 0.25f > thr) continue;
+            const float ex = __fsub_rn(o.z, a1.x), ey = __fsub_rn(o.w, a1.y);
+            const float s2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+            if (!diag && s2 * 0.25f > thr) continue;
+            float d = __fmul_rn(__fadd_rn(__fsqrt_rn(s1), __fsqrt_rn(s2)), 0.5f);
+            if (diag) d = 99999.0f;
+            const float v = __fsub_rn(-d, vmin);
+            if (v == rq) {
+                const float cq = __fsub_rn(-__uint_as_float(s_cmin[t]), vmin);           // column maximum of v
+                if (v == cq) {                                                           // repeatability.py:25-28
+                    const float ds = __fmul_rn(d, p.scale01);                            // :76-80
+                    ++np;
+                    if (ds <= p.th) { ++gt; sum += (double)ds; }                         // :82-83
+                }
+            }
+        }
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+        gt += __shfl_xor_sync(0xffffffffu, gt, d);
+        np += __shfl_xor_sync(0xffffffffu, np, d);
+        sum += __shfl_xor_sync(0xffffffffu, sum, d);
+    }
+    if ((threadIdx.x & 31) == 0) { s_gt[threadIdx.x >> 5] = gt; s_np[threadIdx.x >> 5] = np; s_sum[threadIdx.x >> 5] = sum; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int g = 0, q = 0;
+        double sm = 0.0;
+        for (int w = 0; w < PT / 32; ++w) { g += s_gt[w]; q += s_np[w]; sm += s_sum[w]; }
+        if (q) {
+            atomicAdd(&p.stats[b * 4 + 0], (double)g);
+            atomicAdd(&p.stats[b * 4 + 1], sm);
+            atomicAdd(&p.stats[b * 4 + 2], (double)q);
+        }
+    }
 }
 
 // second variant of the mutual sweep that also lists the pairs (unordered)
@@ -426,7 +606,7 @@ extern "C" int kb_warp_homography(const float* pts, int pts_stride, const int* c
 extern "C" size_t kb_repeat_workspace_bytes(int B, int a_max, int b_max) {
     if (B <= 0 || a_max <= 0 || b_max <= 0) return 0;
     return kb_align_up((size_t)B * a_max * 4, 256) + kb_align_up((size_t)B * b_max * 4, 256) +
-           kb_align_up((size_t)B * 4, 256) * 2 + 1024;
+           kb_align_up((size_t)B * 4, 256) * 3 + 1024;
 }
 
 extern "C" int kb_repeat_counts(const float* k0c, const float* k01c, const int* na, const float* k1c,
@@ -443,7 +623,9 @@ extern "C" int kb_repeat_counts(const float* k0c, const float* k01c, const int* 
     p.colmin = arena.take<unsigned int>((size_t)B * b_max);
     p.gmax = arena.take<unsigned int>(B);
     int* pair_count = arena.take<int>(B);
+    int* need_bf = arena.take<int>(B);
     if (!arena.ok()) return KB_ERR_WORKSPACE;
+    p.only_flagged = nullptr;
     p.k0c = k0c; p.k01c = k01c; p.k1c = k1c; p.k10c = k10c; p.na = na; p.nb = nb; p.stats = stats;
     p.errors = errors; p.pairs = pairs; p.B = B; p.a_max = a_max; p.b_max = b_max; p.pair_cap = pair_cap;
     p.scale01 = scale01; p.scale10 = scale10; p.th = th;
@@ -451,13 +633,25 @@ extern "C" int kb_repeat_counts(const float* k0c, const float* k01c, const int* 
     const size_t n_init2 = n_init > (size_t)B * 4 ? n_init : (size_t)B * 4;
     rep_init_kernel<<<(unsigned)((n_init2 + 255) / 256), 256, 0, st>>>(p);
     KB_LAUNCH_CHECK();
+    // pruned sweeps for every map whose distances are provably below the 99999 diagonal mask ...
+    rep_bound_kernel<<<B, 256, 0, st>>>(p, need_bf);
+    KB_LAUNCH_CHECK();
+    rep_min_pruned_kernel<0><<<dim3((a_max + PR - 1) / PR, B), PT, 0, st>>>(p, need_bf);
+    KB_LAUNCH_CHECK();
+    rep_min_pruned_kernel<1><<<dim3((b_max + PR - 1) / PR, B), PT, 0, st>>>(p, need_bf);
+    KB_LAUNCH_CHECK();
+    rep_mutual_pruned_kernel<<<dim3((a_max + PR - 1) / PR, B), PT, 0, st>>>(p, need_bf);
+    KB_LAUNCH_CHECK();
+    // ... the exhaustive sweeps for the rest (they return at once for all other maps)
     dim3 grid((a_max + RB - 1) / RB, B);
+    p.only_flagged = need_bf;
     rep_minima_kernel<<<grid, RT, 0, st>>>(p);
     KB_LAUNCH_CHECK();
     RepParams q = p;
     q.pairs = nullptr;
     rep_mutual_kernel<<<grid, RT, 0, st>>>(q);
     KB_LAUNCH_CHECK();
+    p.only_flagged = nullptr;
     if (pairs) {
         KB_CUDA_TRY(cudaMemsetAsync(pair_count, 0, (size_t)B * sizeof(int), st));
         rep_pairs_kernel<<<grid, RT, 0, st>>>(p, pair_count);

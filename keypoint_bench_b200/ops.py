@@ -318,7 +318,7 @@ def repeat_batched(k0c, k01c, na, k1c, k10c, nb, scale01: float, scale10: float,
                                    a_max, b_max, float(scale01), float(scale10), float(th), stats.data_ptr(),
                                    _ptr(errors), _ptr(pairs), int(pair_cap), ws.data_ptr(), ws.numel(), _stream()),
               'kb_repeat_counts')
-    _count(3 + (1 if pair_cap > 0 else 0))
+    _count(7 + (1 if pair_cap > 0 else 0))     # init, bound, 2 pruned minima, pruned mutual, 2 exhaustive (early exit)
     return stats, errors, pairs
 
 
