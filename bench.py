@@ -412,9 +412,16 @@ def main():
         kernels['sample kernel'] = {'ms': stage_ms['sample'], 'bound': 'hbm', 'algorithmic_bytes':
                                     min(16 * npts * cfg.desc_dim, 4.0 * cfg.desc_dim * hw * n_img) + 4 * npts * cfg.desc_dim + 8 * npts}
         ncov = res['n_cov'].float()
-        kernels['match stage (prep x2, nn_top2 tcgen05, resolve, rescan, gate, pairs)'] = {
-            'ms': stage_ms['match'], 'bound': 'tensor',
-            'algorithmic_flops': float((2.0 * ncov[:P] * ncov[P:] * cfg.desc_dim).sum().item()) * (2 if cfg.cross_check else 1)}
+        flops = float((2.0 * ncov[:P] * ncov[P:] * cfg.desc_dim).sum().item()) * (2 if cfg.cross_check else 1)
+        if tc:      # the tcgen05 search kernel alone (kb_match_mnn_phases), on the buffers of a full call
+            mst = []
+            margs = (res['desc'][:P], res['desc'][P:], res['n_cov'][:P], res['n_cov'][P:], cfg.max_distance, cfg.cross_check)
+            ops.match_batched(*margs, algo=1, state=mst)
+            top2_ms = time_stage(lambda: ops.match_batched(*margs, algo=1, phases=2, state=mst))
+            kernels['nn_top2_kernel (match, tcgen05 Gram + fused top-3 epilogue)'] = {
+                'ms': top2_ms, 'bound': 'tensor', 'algorithmic_flops': flops}
+        else:
+            kernels['match stage (float64 SIMT)'] = {'ms': stage_ms['match'], 'bound': 'tensor', 'algorithmic_flops': flops}
     for k in kernels.values():
         if k['bound'] == 'hbm':
             k['achieved'] = k['algorithmic_bytes'] / (k['ms'] / 1e3) / 1e9
@@ -424,13 +431,18 @@ def main():
             k['unit'], k['peak'] = 'TFLOP/s', pk['bf16_tflops_sustained']
         k['frac'] = k['achieved'] / k['peak']
     dom = max(kernels, key=lambda n: kernels[n]['ms'])
+    # ncu --set full figures captured for this workload (profiles/traffic.json): DRAM bytes per launch, tensor-pipe %
     traffic = None
     tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
-    if os.path.exists(tpath) and dom.startswith('round1'):
+    if os.path.exists(tpath):
         with open(tpath) as f:
-            t = json.load(f).get('round1_kernel', {})
-        if t.get('workload') == cfg.name and t.get('maps') == n_img:
-            traffic = t.get('dram_bytes_per_launch')
+            tj = json.load(f)
+        for name, k in kernels.items():
+            t = tj.get(name.split(' ')[0].replace('sample', 'sample_planes_kernel') if name.startswith('sample') else name.split(' ')[0], {})
+            if t.get('workload') == cfg.name and t.get('maps') == n_img:
+                k['ncu'] = {kk: vv for kk, vv in t.items() if kk not in ('workload', 'maps', 'source')}
+                if name == dom:
+                    traffic = t.get('dram_bytes_per_launch')
     d = kernels[dom]
     roof = {'kernel': dom, 'bound': d['bound'], 'achieved': d['achieved'], 'peak': d['peak'], 'unit': d['unit'],
             'frac': d['frac'], 'traffic': traffic, 'stage_ms': stage_ms, 'kernels': kernels,

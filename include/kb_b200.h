@@ -130,6 +130,12 @@ KB_API size_t kb_match_workspace_bytes(int B, int n_max, int m_max, int D, int a
 KB_API int kb_match_mnn(const float* d0, const float* d1, const int* n0, const int* n1, int B, int n_max,
                  int m_max, int D, double max_distance, int cross_check, int algo, int* pairs,
                  double* dist, int* count, void* ws, size_t ws_bytes, kb_stream_t stream);
+/* Measurement hook: kb_match_mnn restricted to the parts selected by `phases` (bit 0 operand preparation,
+ * bit 1 tensor-core search kernel, bit 2 certification / rescans / gate / pair compaction) on a workspace that
+ * a full call (phases = 7) has filled before; tensor-core path only.  kb_match_mnn == phases 7. */
+KB_API int kb_match_mnn_phases(const float* d0, const float* d1, const int* n0, const int* n1, int B, int n_max,
+                        int m_max, int D, double max_distance, int cross_check, int algo, int* pairs, double* dist,
+                        int* count, void* ws, size_t ws_bytes, int phases, kb_stream_t stream);
 /* Diagnostics (tests only): byte offsets inside an algo=1 workspace after kb_match_mnn returned:
  * off[0] records of direction 0: per row FOUR records (one per column slice of the epilogue) of 32 B
  * (float best, second, third, pad; int argbest, argsecond, pad, pad), off[1] same for direction 1, off[2] int32[2] = rows that needed the exact float64 rescan,

@@ -37,6 +37,8 @@ PROTOTYPES = {
     'kb_match_workspace_bytes': (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     'kb_match_mnn': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_double, c_int,
                              c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'kb_match_mnn_phases': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_double, c_int,
+                                    c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
     'kb_match_tc_debug_offsets': (c_int, [c_int, c_int, c_int, c_int, c_void_p]),
     'kb_warp_homography': (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_void_p]),

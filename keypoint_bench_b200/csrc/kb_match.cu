@@ -12,7 +12,7 @@
 
 int kb_match_tc_run(const float* d0, const float* d1, const int* n0, const int* n1, int B, int n_max, int m_max,
                     int D, double max_distance, int cross_check, int* pairs, double* dist, int* count, void* ws,
-                    size_t ws_bytes, cudaStream_t st);
+                    size_t ws_bytes, int phases, cudaStream_t st);
 size_t kb_match_tc_workspace_bytes(int B, int n_max, int m_max, int D);
 
 namespace {
@@ -210,16 +210,29 @@ extern "C" size_t kb_match_workspace_bytes(int B, int n_max, int m_max, int D, i
     return f64;
 }
 
+extern "C" int kb_match_mnn_phases(const float* d0, const float* d1, const int* n0, const int* n1, int B, int n_max,
+                                   int m_max, int D, double max_distance, int cross_check, int algo, int* pairs,
+                                   double* dist, int* count, void* ws, size_t ws_bytes, int phases, kb_stream_t stream);
+
 extern "C" int kb_match_mnn(const float* d0, const float* d1, const int* n0, const int* n1, int B, int n_max,
                             int m_max, int D, double max_distance, int cross_check, int algo, int* pairs,
                             double* dist, int* count, void* ws, size_t ws_bytes, kb_stream_t stream) {
+    return kb_match_mnn_phases(d0, d1, n0, n1, B, n_max, m_max, D, max_distance, cross_check, algo, pairs, dist, count, ws,
+                               ws_bytes, 7, stream);
+}
+
+extern "C" int kb_match_mnn_phases(const float* d0, const float* d1, const int* n0, const int* n1, int B, int n_max,
+                                   int m_max, int D, double max_distance, int cross_check, int algo, int* pairs,
+                                   double* dist, int* count, void* ws, size_t ws_bytes, int phases, kb_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
+    if (phases <= 0 || phases > 7) return KB_ERR_BAD_ARG;
     if (!d0 || !d1 || !pairs || !count || B <= 0 || n_max <= 0 || m_max <= 0 || D <= 0) return KB_ERR_BAD_ARG;
     if (algo < 0) algo = (D <= 256) ? 1 : 0;       // auto: tensor cores whenever the query tile fits on chip
     if (algo == 1)
         return kb_match_tc_run(d0, d1, n0, n1, B, n_max, m_max, D, max_distance, cross_check, pairs, dist, count,
-                               ws, ws_bytes, st);
+                               ws, ws_bytes, phases, st);
     if (algo != 0) return KB_ERR_BAD_ARG;
+    if (phases != 7) return KB_ERR_UNSUPPORTED;      // the float64 path has no separately timed parts
     if (B > 65535) return KB_ERR_UNSUPPORTED;
     MatchParams p;
     p.tiles_i = (n_max + TM - 1) / TM;

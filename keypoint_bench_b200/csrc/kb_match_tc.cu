@@ -975,9 +975,11 @@ size_t kb_match_tc_workspace_bytes(int B, int n_max, int m_max, int D) {
     return tc_layout(B, n_max, m_max, D).bytes;
 }
 
+// `phases` (bit 0 operand preparation, bit 1 tensor-core search, bit 2 certification / rescans / gate / pairs)
+// lets the benchmark time one part alone on a workspace that a full call has filled; product calls pass 7.
 int kb_match_tc_run(const float* d0, const float* d1, const int* n0, const int* n1, int B, int n_max, int m_max,
                     int D, double max_distance, int cross_check, int* pairs, double* dist, int* count, void* ws,
-                    size_t ws_bytes, cudaStream_t st) {
+                    size_t ws_bytes, int phases, cudaStream_t st) {
     using namespace kbtc;
     if (B > 65535) return KB_ERR_UNSUPPORTED;
     const TcLayout L = tc_layout(B, n_max, m_max, D);
@@ -991,9 +993,11 @@ int kb_match_tc_run(const float* d0, const float* d1, const int* n0, const int* 
     int *nn0 = tb.nn0, *nn1 = tb.nn1, *n_exact = tb.n_exact;
     double* d2_0 = tb.d2_0;
 
-    KB_CUDA_TRY(cudaMemsetAsync(maxn0, 0, (size_t)B * 4, st));
-    KB_CUDA_TRY(cudaMemsetAsync(maxn1, 0, (size_t)B * 4, st));
-    KB_CUDA_TRY(cudaMemsetAsync(n_exact, 0, 8, st));
+    if (phases & 1) {
+        KB_CUDA_TRY(cudaMemsetAsync(maxn0, 0, (size_t)B * 4, st));
+        KB_CUDA_TRY(cudaMemsetAsync(maxn1, 0, (size_t)B * 4, st));
+    }
+    if (phases & 4) KB_CUDA_TRY(cudaMemsetAsync(n_exact, 0, 8, st));
     int dev = 0, sms = 0;
     KB_CUDA_TRY(cudaGetDevice(&dev));
     KB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -1012,8 +1016,10 @@ int kb_match_tc_run(const float* d0, const float* d1, const int* n0, const int* 
         const int wave = (sms * 8 + 2 * B - 1) / (2 * B);               // CTAs per (batch, side) in one resident wave
         if (ctas > wave) ctas = wave;
         if (ctas < 1) ctas = 1;
-        prep_kernel<<<dim3(ctas, B, 2), 256, 0, st>>>(pp);
-        KB_LAUNCH_CHECK();
+        if (phases & 1) {
+            prep_kernel<<<dim3(ctas, B, 2), 256, 0, st>>>(pp);
+            KB_LAUNCH_CHECK();
+        }
     }
     CUtensorMap map0, map1;
     int rc = make_map(&map0, S0, (uint64_t)B * n_max, (uint64_t)2 * L.Dp);
@@ -1042,8 +1048,11 @@ int kb_match_tc_run(const float* d0, const float* d1, const int* n0, const int* 
     KB_CUDA_TRY(cudaFuncSetAttribute(nn_top2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int n_items = mp.n_dirs == 2 ? B * (L.tiles0 + L.tiles1) : B * L.tiles0;
     const int grid = n_items < sms ? n_items : sms;
-    nn_top2_kernel<<<grid, NT, smem, st>>>(map0, map1, mp);
-    KB_LAUNCH_CHECK();
+    if (phases & 2) {
+        nn_top2_kernel<<<grid, NT, smem, st>>>(map0, map1, mp);
+        KB_LAUNCH_CHECK();
+    }
+    if (!(phases & 4)) return KB_OK;
 
     ResolveParams rp;
     rp.d0 = d0; rp.d1 = d1; rp.n0 = n0; rp.n1 = n1; rp.res0 = res0; rp.res1 = res1;
