@@ -301,7 +301,7 @@ def main():
         kv, nv, dd = res0['kcov'], res0['n_cov'], res0['desc']
         stage_ms['sample'] = time_stage(lambda: ops.sample_batched(batch.desc, kv, nv))
         stage_ms['match'] = time_stage(lambda: ops.match_batched(dd[:P], dd[P:], nv[:P], nv[P:], cfg.max_distance,
-                                                                 cfg.cross_check, algo=algo))
+                                                                 cfg.cross_check, algo=algo, want_dist=False))
     # steady state: the launch sequence of one step replayed as a CUDA graph (same kernels, same buffers)
     graphed = None
     if not args.no_graph:
@@ -416,8 +416,8 @@ def main():
         if tc:      # the tcgen05 search kernel alone (kb_match_mnn_phases), on the buffers of a full call
             mst = []
             margs = (res['desc'][:P], res['desc'][P:], res['n_cov'][:P], res['n_cov'][P:], cfg.max_distance, cfg.cross_check)
-            ops.match_batched(*margs, algo=1, state=mst)
-            top2_ms = time_stage(lambda: ops.match_batched(*margs, algo=1, phases=2, state=mst))
+            ops.match_batched(*margs, algo=1, state=mst, want_dist=False)
+            top2_ms = time_stage(lambda: ops.match_batched(*margs, algo=1, phases=2, state=mst, want_dist=False))
             kernels['nn_top2_kernel (match, tcgen05 Gram + fused top-3 epilogue)'] = {
                 'ms': top2_ms, 'bound': 'tensor', 'algorithmic_flops': flops}
         else:

@@ -531,6 +531,7 @@ struct ResolveParams {
     int* nn1;                // [B*m_max]
     int* n_exact;            // [1] number of rows queued for the exact rescan
     int* n_pair;             // [1] rows settled by the two-candidate exact check (statistics)
+    float* tsel;             // [B*n_max] tensor-core score t = x.y - |y|^2/2 of the direction-0 winner (NaN: unknown)
     int2* list;              // [list_cap] queued rows: (dir | b << 1, query row)
     int list_cap;
     struct RescanPart* parts;   // [list_cap, RESCAN_SPLIT] partial minima of the split rescan
@@ -572,6 +573,7 @@ __global__ void __launch_bounds__(256) resolve_kernel(ResolveParams p) {
     const int q_stride = dir ? p.m_max : p.n_max, db_stride = dir ? p.n_max : p.m_max;
     int mode = 0;                        // 0 nothing to do, 1 certified, 2 two candidates, 3 rescan
     int j1 = 0, j2 = 0;
+    float tbest = 0.0f, tsecond = 0.0f;
     if (q < nq) {
         Top2 r = (dir ? p.res1 : p.res0)[((size_t)b * q_stride + q) * EPI_SLICES];
 #pragma unroll
@@ -596,6 +598,7 @@ __global__ void __launch_bounds__(256) resolve_kernel(ResolveParams p) {
         // accumulation in the tensor core (K/16 roundings) and the fp32 -|y|^2/2 term; generous factor on top
         const float e = 6.2e-5f * sqrtf(nq2) * sqrtf(dbmax2) + 3.1e-5f * dbmax2;
         j1 = r.idx; j2 = r.idx2;
+        tbest = r.best; tsecond = r.second;
         const bool ok1 = j1 >= 0 && j1 < ndb, ok2 = j2 >= 0 && j2 < ndb && j2 != j1;
         if (ok1 && (r.best - r.second) > 2.0f * e) mode = 1;
         else if (ok1 && ok2 && (r.best - r.third) > 2.0f * e) mode = 2;
@@ -603,10 +606,12 @@ __global__ void __launch_bounds__(256) resolve_kernel(ResolveParams p) {
     }
     int* nn = dir ? p.nn1 : p.nn0;
     if (mode == 1) nn[(size_t)b * q_stride + q] = j1;
+    if (dir == 0 && mode != 0) p.tsel[(size_t)b * q_stride + q] = mode == 1 ? tbest : CUDART_NAN_F;
     if (mode == 3) {
         const int slot = atomicAdd(p.n_exact, 1);
         if (slot < p.list_cap) p.list[slot] = make_int2(dir | (b << 1), q);
     }
+    __syncwarp();                       // the NaN placeholders above are ordered before lane 0's final values
     unsigned pend = __ballot_sync(0xffffffffu, mode == 2);
     const float* Qb = (dir ? p.d1 : p.d0) + (size_t)b * q_stride * p.D;
     const float* DBs = (dir ? p.d0 : p.d1) + (size_t)b * db_stride * p.D;
@@ -617,9 +622,11 @@ __global__ void __launch_bounds__(256) resolve_kernel(ResolveParams p) {
         const int a1 = __shfl_sync(0xffffffffu, j1, src), a2 = __shfl_sync(0xffffffffu, j2, src);
         const double d1 = warp_dist2(Qb + (size_t)qq * p.D, DBs + (size_t)a1 * p.D, p.D, lane);
         const double d2 = warp_dist2(Qb + (size_t)qq * p.D, DBs + (size_t)a2 * p.D, p.D, lane);
+        const float t1 = __shfl_sync(0xffffffffu, tbest, src), t2 = __shfl_sync(0xffffffffu, tsecond, src);
         if (lane == 0) {
             const bool first = d1 < d2 || (d1 == d2 && a1 < a2);
             nn[(size_t)b * q_stride + qq] = first ? a1 : a2;
+            if (dir == 0) p.tsel[(size_t)b * q_stride + qq] = first ? t1 : t2;
             if (p.n_pair) atomicAdd(p.n_pair, 1);
         }
     }
@@ -747,7 +754,10 @@ struct GateParams {
     const int* nn1;
     int* keep_j;             // [B*n_max] matched column or -1
     double* dist_i;          // [B*n_max]
-    int n_max, m_max, D, cross_check;
+    const float* tsel;       // [B*n_max] tensor-core score of the winner (NaN: unknown)
+    const float* norm2_0;    // [B*n_max] |x|^2
+    const unsigned int* maxn1;   // [B] max |y|^2 (float bits)
+    int n_max, m_max, D, cross_check, want_dist;
     double max_distance;
 };
 
@@ -764,6 +774,38 @@ __global__ void __launch_bounds__(256) gate_kernel(GateParams p) {
         const int i = i0 + g;
         jj[g] = i < n ? p.nn0[(size_t)b * p.n_max + i] : 0;
         live[g] = i < n && (!p.cross_check || p.nn1[(size_t)b * p.m_max + jj[g]] == i);
+    }
+    if (!p.want_dist) {
+        // The caller only wants the pairs: |x - y|^2 = |x|^2 - 2 t with t = x.y - |y|^2/2 from the tensor cores,
+        // known to within `err`; the float64 distance is evaluated only where that cannot decide d < max_distance.
+        const float ymax2 = __uint_as_float(p.maxn1[b]);
+        const double md2 = p.max_distance * p.max_distance;
+        bool any_exact = false;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            if (!live[g]) continue;
+            const size_t row = (size_t)b * p.n_max + i0 + g;
+            const float t = p.tsel[row], x2 = p.norm2_0[row];
+            const float e = 6.2e-5f * sqrtf(x2) * sqrtf(ymax2) + 3.1e-5f * ymax2;
+            const double d2 = (double)x2 - 2.0 * (double)t, err = 2.0 * (double)e + 4e-6 * (double)x2;
+            if (d2 + err < md2) {                       // certainly inside the gate
+                if (lane == 0) p.keep_j[row] = jj[g];
+                live[g] = false;
+            } else if (d2 - err >= md2) {               // certainly outside
+                live[g] = false;                        // (keep_j is written as -1 below)
+                if (lane == 0) p.keep_j[row] = -1;
+            } else {
+                any_exact = true;                       // NaN or too close to call: exact evaluation below
+            }
+        }
+        // rows that were not live at all
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const int i = i0 + g;
+            if (lane == 0 && i < n && !(!p.cross_check || p.nn1[(size_t)b * p.m_max + jj[g]] == i))
+                p.keep_j[(size_t)b * p.n_max + i] = -1;
+        }
+        if (!any_exact) return;
     }
     double acc[G] = {0.0, 0.0, 0.0, 0.0};
     const bool vec = (p.D & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.d0) | reinterpret_cast<uintptr_t>(p.d1)) & 15u) == 0;
@@ -804,7 +846,7 @@ __global__ void __launch_bounds__(256) gate_kernel(GateParams p) {
         double a = acc[g];
         for (int s = 16; s > 0; s >>= 1) a += __shfl_xor_sync(0xffffffffu, a, s);
         const int i = i0 + g;
-        if (lane == 0 && i < n) {
+        if (lane == 0 && i < n && (p.want_dist || live[g])) {
             const double d = sqrt(a);
             p.keep_j[(size_t)b * p.n_max + i] = (live[g] && d < p.max_distance) ? jj[g] : -1;
             p.dist_i[(size_t)b * p.n_max + i] = d;
@@ -915,6 +957,7 @@ static TcLayout tc_layout(int B, int n_max, int m_max, int D) {
     add((size_t)B * n_max * 4);                 // keep_j
     add((size_t)B * (n_max + m_max) * 8 * 16);  // rescan partial minima
     add((size_t)B * (n_max + m_max) * 4);       // rescan tickets
+    add((size_t)B * n_max * 4);                 // tensor-core score of the direction-0 winners
     L.bytes = n + 1024;
     return L;
 }
@@ -931,6 +974,7 @@ struct TcBuffers {
     int* keep_j;
     void* parts;
     int* tickets;
+    float* tsel;
     bool ok;
 };
 
@@ -955,6 +999,7 @@ static TcBuffers tc_carve(void* ws, size_t ws_bytes, int B, int n_max, int m_max
     t.keep_j = arena.take<int>((size_t)B * n_max);
     t.parts = arena.take<char>((size_t)B * (n_max + m_max) * 8 * 16);
     t.tickets = arena.take<int>((size_t)B * (n_max + m_max));
+    t.tsel = arena.take<float>((size_t)B * n_max);
     t.ok = arena.ok();
     return t;
 }
@@ -1059,7 +1104,7 @@ int kb_match_tc_run(const float* d0, const float* d1, const int* n0, const int* 
     rp.norm2_0 = norm2_0; rp.norm2_1 = norm2_1; rp.maxn0 = maxn0; rp.maxn1 = maxn1;
     rp.nn0 = nn0; rp.nn1 = nn1; rp.n_exact = n_exact; rp.n_pair = n_exact + 1;
     rp.list = tb.list; rp.list_cap = B * (n_max + m_max);
-    rp.parts = (RescanPart*)tb.parts; rp.tickets = tb.tickets;
+    rp.parts = (RescanPart*)tb.parts; rp.tickets = tb.tickets; rp.tsel = tb.tsel;
     KB_CUDA_TRY(cudaMemsetAsync(tb.tickets, 0, (size_t)B * (n_max + m_max) * 4, st));
     rp.B = B; rp.n_max = n_max; rp.m_max = m_max; rp.D = D; rp.n_dirs = mp.n_dirs;
     const int qmax = n_max > m_max ? n_max : m_max;
@@ -1072,6 +1117,7 @@ int kb_match_tc_run(const float* d0, const float* d1, const int* n0, const int* 
     GateParams gp;
     gp.d0 = d0; gp.d1 = d1; gp.n0 = n0; gp.n1 = n1; gp.nn0 = nn0; gp.nn1 = nn1; gp.keep_j = tb.keep_j; gp.dist_i = d2_0;
     gp.n_max = n_max; gp.m_max = m_max; gp.D = D; gp.cross_check = cross_check; gp.max_distance = max_distance;
+    gp.tsel = tb.tsel; gp.norm2_0 = norm2_0; gp.maxn1 = maxn1; gp.want_dist = dist != nullptr;
     gate_kernel<<<dim3(((n_max + 3) / 4 * 32 + 255) / 256, B), 256, 0, st>>>(gp);
     KB_LAUNCH_CHECK();
 

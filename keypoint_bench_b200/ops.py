@@ -192,9 +192,10 @@ def sample_batched(desc: torch.Tensor, pts: torch.Tensor, count: torch.Tensor | 
 
 def match_batched(d0: torch.Tensor, d1: torch.Tensor, n0: torch.Tensor | None = None, n1: torch.Tensor | None = None,
                   max_distance: float = math.inf, cross_check: bool = True, algo: int = -1, return_ws: bool = False,
-                  phases: int = 7, state=None):
+                  phases: int = 7, state=None, want_dist: bool = True):
     """Mutual-NN matching (utils/matcher.py:227-234).  d0 [B,n,D], d1 [B,m,D]
-    -> pairs[B,n,2] int32 (sorted by first index), dist[B,n] float64, count[B]."""
+    -> pairs[B,n,2] int32 (sorted by first index), dist[B,n] float64 (None with ``want_dist=False``: the
+    tensor-core path then evaluates float64 distances only where the max_distance gate needs them), count[B]."""
     _require_cuda(d0, 'd0')
     _require_cuda(d1, 'd1')
     a, bm = _f32(d0), _f32(d1)
@@ -206,11 +207,11 @@ def match_batched(d0: torch.Tensor, d1: torch.Tensor, n0: torch.Tensor | None = 
         pairs, dist, count, ws = state
     else:
         pairs = _out(b, max(n, 1), 2, dtype=torch.int32, device=a.device)
-        dist = _out(b, max(n, 1), dtype=torch.float64, device=a.device)
+        dist = _out(b, max(n, 1), dtype=torch.float64, device=a.device) if want_dist else None
         count = torch.zeros(b, dtype=torch.int32, device=a.device)
         ws = None
     if n == 0 or m == 0:
-        return pairs[:, :n], dist[:, :n], count
+        return pairs[:, :n], (dist[:, :n] if dist is not None else None), count
     c0, c1 = _i32(n0), _i32(n1)
     if ws is None:
         ws = _ws(lib.kb_match_workspace_bytes(b, n, m, dd, int(algo)), a.device)
@@ -218,7 +219,7 @@ def match_batched(d0: torch.Tensor, d1: torch.Tensor, n0: torch.Tensor | None = 
             state.extend([pairs, dist, count, ws])
     with torch.cuda.device(a.device):
         check(lib.kb_match_mnn_phases(a.data_ptr(), bm.data_ptr(), _ptr(c0), _ptr(c1), b, n, m, dd, float(max_distance),
-                                      int(bool(cross_check)), int(algo), pairs.data_ptr(), dist.data_ptr(), count.data_ptr(),
+                                      int(bool(cross_check)), int(algo), pairs.data_ptr(), _ptr(dist), count.data_ptr(),
                                       ws.data_ptr(), ws.numel(), int(phases), _stream()), 'kb_match_mnn')
     _count(2 if (algo == 0 or dd > 256) else (6 if phases == 7 else 1))
     if return_ws:

@@ -59,9 +59,10 @@ def _extract_match(batch, cfg, algo, covisible_only, timer) -> dict:
         t('sample')
         d = ops.sample_batched(batch.desc, pts, n_pts)        # utils/matcher.py:221-226
         t('match')
-        pairs, dist, n_m = ops.match_batched(d[:P], d[P:], n_pts[:P], n_pts[P:], cfg.max_distance, cfg.cross_check,
-                                             algo=algo)       # utils/matcher.py:227-231
-        out.update(desc=d, matches=pairs, match_dist=dist, n_matches=n_m)
+        # the reference returns matched rows only (utils/matcher.py:227-233): no distances are requested
+        pairs, _, n_m = ops.match_batched(d[:P], d[P:], n_pts[:P], n_pts[P:], cfg.max_distance, cfg.cross_check,
+                                          algo=algo, want_dist=False)
+        out.update(desc=d, matches=pairs, n_matches=n_m)
     t(None)
     return out
 

@@ -35,7 +35,7 @@ def brute_force_matcher(pts0: torch.Tensor, pts1: torch.Tensor, desc_map_0: torc
     max_distance = math.inf if max_distance is None else float(max_distance)
     algo = int(params.get('algo', -1))       # -1: tcgen05 path when D <= 256, float64 SIMT otherwise
     pairs, _, count = ops.match_batched(desc0[None], desc1[None], None, None, max_distance, bool(params['cross_check']),
-                                        algo=algo)
+                                        algo=algo, want_dist=False)
     k = int(count[0].item())
     matches = pairs[0, :k].to(torch.int64)
     matches = like(matches, pts0)

@@ -198,6 +198,37 @@ def test_matcher_against_oracle_sizes(algo, n, m, dim):
 
 
 @pytest.mark.parametrize('algo', [0, 1])
+@pytest.mark.parametrize('dim,scale', [(256, 1.0), (64, 1.0), (128, 37.5)])
+def test_matcher_without_distances_gives_same_pairs(algo, dim, scale):
+    """``want_dist=False`` (what the pipeline uses: matcher.py:227-233 keeps only the index pairs) lets the tensor-core
+    path decide ``d < max_distance`` from its certified score and fall back to float64 only inside the error band;
+    the pairs must be identical, including for a max_distance that equals one pair's float64 distance exactly
+    (the comparison is strict)."""
+    gen = torch.Generator().manual_seed(dim)
+    n, m = 900, 1000
+    a = torch.nn.functional.normalize(torch.randn(2, n, dim, generator=gen), dim=2) * scale
+    b = torch.nn.functional.normalize(torch.randn(2, m, dim, generator=gen), dim=2) * scale
+    b[:, :600] = a[:, :600] + scale * torch.linspace(0.0, 0.12, 600)[None, :, None] * torch.randn(2, 600, dim, generator=gen)
+    full, dist, cnt = ops().match_batched(a.to(DEV), b.to(DEV), None, None, math.inf, True, algo=algo)
+    d_sorted = np.sort(dist[0, :int(cnt[0])].cpu().numpy())
+    gates = [float(d_sorted[len(d_sorted) // 2]), float(np.nextafter(d_sorted[len(d_sorted) // 2], np.inf)),
+             float(d_sorted[len(d_sorted) // 3]) * (1 + 1e-7), 0.9 * scale, 5.0 * scale, 1e-3 * scale]
+    for maxd in gates:
+        for cc in (True, False):
+            p_ref, _, c_ref = ops().match_batched(a.to(DEV), b.to(DEV), None, None, maxd, cc, algo=algo)
+            p_got, d_got, c_got = ops().match_batched(a.to(DEV), b.to(DEV), None, None, maxd, cc, algo=algo,
+                                                      want_dist=False)
+            assert d_got is None
+            assert torch.equal(c_ref, c_got), (maxd, cc)
+            for i in range(2):
+                k = int(c_ref[i])
+                assert torch.equal(p_ref[i, :k], p_got[i, :k]), (maxd, cc, i)
+            if algo == 1:
+                _exact_pairs_or_near_tie(p_got[0, :int(c_got[0])].cpu().numpy().astype(np.int64), a[0].numpy(),
+                                         b[0].numpy(), maxd, cc)
+
+
+@pytest.mark.parametrize('algo', [0, 1])
 def test_matcher_ragged_batch_and_ties(algo):
     gen = torch.Generator().manual_seed(11)
     a = torch.randn(3, 300, 64, generator=gen)
