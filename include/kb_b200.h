@@ -101,6 +101,21 @@ KB_API int kb_detect_phases(const float* score, int B, int H, int W, int nms_dis
                      size_t ws_bytes, int phases, kb_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * simple_nms(scores, nms_radius)                                   models/lightglue.py:904-920
+ *
+ * The max-pool NMS of the LightGlue-style extractor on B independent [H,W]
+ * maps: M = (s == pool(s)); twice { supp = pool(M) > 0; ss = supp ? 0 : s;
+ * M |= (ss == pool(ss)) & ~supp }; out = M ? s : 0, pool = (2r+1)^2 maximum with -inf outside the
+ * image.  Ties are all kept (the comparison is ==).  0 <= nms_radius <= 16.  `out` may not alias
+ * `score`.  The rest of the reference's extract() (border = -1, `> threshold`, torch.topk,
+ * sample_descriptors, models/lightglue.py:929-979) is kb_select + kb_sample_desc(normalize=1,
+ * coord_mode=1).
+ * ------------------------------------------------------------------------------------------- */
+KB_API size_t kb_simple_nms_workspace_bytes(int B, int H, int W);
+KB_API int kb_simple_nms(const float* score, float* out, int B, int H, int W, int nms_radius, void* ws,
+                  size_t ws_bytes, kb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Stage 2 -- descriptor sampling      utils/matcher.py:221-226 and models/lightglue.py:24-41
  *
  * desc [B,C,h,w] (NCHW as the backbones emit it); pts [B,n_max,pts_stride] with (x,y) in the first

@@ -106,6 +106,22 @@ def fast_nms_batched(score: torch.Tensor, nms_dist: int = 4, max_iter: int = -1,
     return (out, rounds) if return_rounds else out
 
 
+def simple_nms_batched(score: torch.Tensor, nms_radius: int) -> torch.Tensor:
+    """``simple_nms`` of the LightGlue-style extractor (models/lightglue.py:904-920) on every map of the batch."""
+    _require_cuda(score, 'score')
+    if nms_radius < 0:
+        raise AssertionError('nms_radius must be >= 0')       # lightglue.py:906
+    s = _maps3(score)
+    b, h, w = s.shape
+    out = torch.empty_like(s)
+    ws = _ws(lib.kb_simple_nms_workspace_bytes(b, h, w), s.device)
+    with torch.cuda.device(s.device):
+        check(lib.kb_simple_nms(s.data_ptr(), out.data_ptr(), b, h, w, int(nms_radius), ws.data_ptr(), ws.numel(),
+                                _stream()), 'kb_simple_nms')
+    _count(3)
+    return out.reshape(score.shape) if score.dim() != 2 else out[0]
+
+
 def select_batched(nms_map: torch.Tensor, border_dist: int, threshold: float, min_score: float, top_k: int,
                    cap: int | None = None):
     """Border + threshold + (top-k) + min_score on already-suppressed maps

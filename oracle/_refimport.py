@@ -41,3 +41,22 @@ def load():
     ns.repeatability = importlib.import_module('tasks.repeatability')
     ns.mha = importlib.import_module('tasks.MHA')
     return ns
+
+
+def load_lightglue_extract():
+    """The LightGlue-style extract helpers of ``models/lightglue.py`` live inside its
+    ``if __name__ == '__main__'`` demo block (:904-979) and the module itself needs packages that
+    are not installed, so the function definitions are taken from the parsed source (never
+    copied into this repo) and executed in a namespace that holds only torch."""
+    import ast
+    import torch
+    path = os.path.join(REFERENCE_ROOT, 'models', 'lightglue.py')
+    with open(path) as f:
+        tree = ast.parse(f.read(), filename=path)
+    want = {'sample_descriptors', 'simple_nms', 'top_k_kps', 'extract'}
+    found = [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef) and n.name in want]
+    assert {n.name for n in found} == want, [n.name for n in found]
+    mod = ast.Module(body=found, type_ignores=[])
+    ns = {'torch': torch}
+    exec(compile(mod, path, 'exec'), ns)
+    return types.SimpleNamespace(**{k: ns[k] for k in want})

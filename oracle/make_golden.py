@@ -254,6 +254,51 @@ def gen_se3(ref):
     np.savez_compressed(os.path.join(GOLD, 'ref_se3.npz'), **out)
 
 
+LG_CASES = [  # tag, score kind, H, W, seed, desc C, s (cell size of the descriptor map)
+    ('lg_uniform', 'uniform', 120, 160, 61, 64, 8),
+    ('lg_alike', 'alike', 96, 128, 62, 32, 8),
+    ('lg_ties', 'ties', 64, 80, 63, 16, 1),
+    ('lg_relu_few', 'relu', 72, 88, 64, 16, 2),
+    ('lg_topk', 'uniform', 480, 640, 65, 32, 8),      # > 1000 candidates: torch.topk binds
+]
+
+
+def gen_lightglue():
+    """simple_nms / extract of the LightGlue-style extractor (models/lightglue.py:904-979)."""
+    lg = _refimport.load_lightglue_extract()
+    out = {}
+    for tag, kind, h, w, seed, c, s in LG_CASES:
+        sc = synth.score_map(kind, h, w, seed)                       # [1,1,H,W]
+        g = torch.Generator().manual_seed(seed + 7)
+        dm = torch.randn(1, c, h // s, w // s, generator=g)
+        for r in (0, 2, 5):
+            want = lg.simple_nms(sc[0], r).numpy()
+            mine = ref_ops.simple_nms(sc[0].numpy(), r)
+            assert np.array_equal(want, mine), (tag, r)
+            if h * w <= 40000 or r == 5:
+                out[f'{tag}__nms{r}'] = want[0]
+        feats = lg.extract(lambda img: (sc.clone(), dm.clone()), torch.zeros(1, 3, h, w), s)
+        kp, val, desc, raster = ref_ops.lightglue_extract(sc.numpy(), dm.numpy(), s)
+        rkp, rval, rdesc = feats['keypoints'][0].numpy(), feats['keypoint_scores'][0].numpy(), feats['descriptors'][0].numpy()
+        assert rkp.shape == kp.shape and rdesc.shape == desc.shape, tag
+        # torch.topk orders ties arbitrarily: compare as sets of (x, y, score), verbatim where scores are unique
+        rr = (rkp[:, 1].astype(np.int64) * w + rkp[:, 0].astype(np.int64))
+        assert np.array_equal(np.sort(rr), np.sort(raster)), tag
+        uniq, cnt = np.unique(rval, return_counts=True)
+        single = np.isin(rval, uniq[cnt == 1])
+        assert np.array_equal(rkp[single], kp[np.isin(val, uniq[cnt == 1])]), tag
+        o_r, o_m = np.argsort(rr), np.argsort(raster)
+        assert np.array_equal(rval[o_r], val[o_m]), tag
+        assert np.allclose(rdesc[o_r], desc[o_m], rtol=1e-5, atol=1e-6), tag
+        log(f'lightglue extract {tag}: {h}x{w} C={c} s={s} -> n={kp.shape[0]} '
+            f'(ties {int((~single).sum())}) simple_nms r=0/2/5 bit-equal, extract restatement equal')
+        out[f'{tag}__kp'] = rkp
+        out[f'{tag}__val'] = rval
+        out[f'{tag}__desc'] = rdesc
+        out[f'{tag}__dm'] = dm.numpy()
+    np.savez_compressed(os.path.join(GOLD, 'ref_lightglue.npz'), **out)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
@@ -264,6 +309,7 @@ def main():
     gen_match(ref)
     gen_eval(ref)
     gen_se3(ref)
+    gen_lightglue()
     with open(os.path.join(ROOT, 'oracle', 'REFCHECK.log'), 'w') as f:
         f.write('\n'.join(LOG) + '\n')
 

@@ -294,6 +294,58 @@ def sample_lightglue(desc_map: np.ndarray, kpts_px: np.ndarray, s: int = 8) -> n
 
 
 # --------------------------------------------------------------------------------------
+# LightGlue-style extraction  (models/lightglue.py:904-979)
+# --------------------------------------------------------------------------------------
+
+
+def simple_nms(scores: np.ndarray, nms_radius: int) -> np.ndarray:
+    """models/lightglue.py:904-920 -- max-pool NMS: maxima of the (2r+1)^2 window (ties all kept),
+    then two rounds in which pixels outside the dilated maxima may become maxima of the
+    zero-suppressed map.  ``max_pool2d`` pads with -inf.  [H,W] or [B,H,W] -> same shape."""
+    from scipy.ndimage import maximum_filter
+    assert nms_radius >= 0                                          # :906
+    s = np.asarray(scores, dtype=np.float32)
+    k = 2 * nms_radius + 1
+    size = (1,) * (s.ndim - 2) + (k, k)
+
+    def pool(x):                                                    # :908-911
+        return maximum_filter(x, size=size, mode='constant', cval=-np.inf)
+
+    keep = s == pool(s)                                             # :914
+    for _ in range(2):                                              # :915-919
+        near = pool(keep.astype(np.float32)) > 0
+        rest = np.where(near, np.float32(0), s)
+        keep = keep | ((rest == pool(rest)) & ~near)
+    return np.where(keep, s, np.float32(0))                         # :920
+
+
+def lightglue_extract(scores: np.ndarray, desc_map: np.ndarray, s: int, detection_threshold: float = 0.0,
+                      pad: int = 4, nms_radius: int = 5, max_num_kps: int | None = 1000):
+    """models/lightglue.py:929-979 after the network call, for ONE image (the reference indexes
+    ``scores[0]``, :938): simple_nms; the ``pad`` border rows/cols become -1 (:942-945); pixels
+    ``> detection_threshold`` in raster order (:948-955); if more than ``max_num_kps``, the best by
+    score (``torch.topk``, sorted; tie order canonicalised here as raster asc) (:923-927, 958-967);
+    keypoints as float (x, y) pixels (:970); descriptors via ``sample_descriptors`` (:972-975).
+    -> keypoints [n,2], keypoint_scores [n], descriptors [n,C], raster [n]."""
+    sc = simple_nms(np.asarray(scores, dtype=np.float32).reshape(scores.shape[-2:]), nms_radius).copy()
+    h, w = sc.shape
+    if pad > 0:
+        sc[:pad] = -1
+        sc[:, :pad] = -1
+        sc[-pad:] = -1
+        sc[:, -pad:] = -1
+    ys, xs = np.nonzero(sc > np.float32(detection_threshold))
+    val = sc[ys, xs]
+    raster = ys.astype(np.int64) * w + xs
+    if max_num_kps is not None and max_num_kps < val.shape[0]:
+        order = canonical_order(val, raster)[:max_num_kps]
+        ys, xs, val, raster = ys[order], xs[order], val[order], raster[order]
+    kps = np.stack([xs, ys], axis=1).astype(np.float32)
+    desc = sample_lightglue(desc_map, kps, s) if kps.shape[0] else np.zeros((0, np.asarray(desc_map).shape[-3]), np.float32)
+    return kps, val, desc, raster
+
+
+# --------------------------------------------------------------------------------------
 # Stage 3: brute-force mutual-NN matching  (utils/matcher.py:227-234 -> skimage, absent)
 # --------------------------------------------------------------------------------------
 

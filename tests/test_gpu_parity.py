@@ -513,3 +513,47 @@ def test_warp_se3_matches_reference_fixtures_and_oracle(golden):
         assert np.array_equal(ids[i, :a].cpu().numpy().astype(np.int64), wids), i
         assert np.array_equal(ids_out[i, :o].cpu().numpy().astype(np.int64), wout), i
         assert np.allclose(kv[i, :a].cpu().numpy(), wa, rtol=1e-5, atol=1e-6) and np.allclose(kw[i, :a].cpu().numpy(), wb, rtol=1e-5, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ LightGlue-style extract
+
+def test_simple_nms_and_lightglue_extract_match_reference_fixtures(golden):
+    from keypoint_bench_b200.utils import lightglue_extract as lg
+    from oracle.make_golden import LG_CASES
+    from test_oracle_golden import _lg_compare
+    g = golden('ref_lightglue.npz')
+    for tag, kind, h, w, seed, c, s in LG_CASES:
+        sc = synth.score_map(kind, h, w, seed).to(DEV)
+        for r in (0, 2, 5):
+            if f'{tag}__nms{r}' in g.files:
+                got = lg.simple_nms(sc[0], r)
+                assert got.shape == sc[0].shape
+                assert np.array_equal(got[0].cpu().numpy(), g[f'{tag}__nms{r}']), (tag, r)
+        dm = torch.from_numpy(g[f'{tag}__dm']).to(DEV)
+        feats = lg.extract(lambda img: (sc, dm), None, s)
+        assert feats['keypoints'].shape[0] == 1 and feats['descriptors'].shape[2] == c
+        _lg_compare(feats['keypoints'][0].cpu().numpy(), feats['keypoint_scores'][0].cpu().numpy(),
+                    feats['descriptors'][0].cpu().numpy(), g, tag, w)
+
+
+@pytest.mark.parametrize('kind,h,w,r', [('uniform', 480, 640, 5), ('ties', 100, 333, 4), ('alike', 376, 1241, 11),
+                                        ('negative', 70, 90, 3), ('mixed', 65, 129, 16), ('relu', 33, 65, 1)])
+def test_simple_nms_against_oracle(kind, h, w, r):
+    s = torch.cat([synth.score_map(kind, h, w, 300 + r), synth.score_map('uniform', h, w, 301 + r)], 0)
+    got = ops().simple_nms_batched(s.to(DEV), r)
+    assert np.array_equal(got.cpu().numpy()[:, 0], ref_ops.simple_nms(s.numpy()[:, 0], r))
+
+
+def test_lightglue_extract_batched_against_oracle():
+    from keypoint_bench_b200.utils import lightglue_extract as lg
+    maps = torch.cat([synth.score_map(k, 240, 320, 70 + i) for i, k in enumerate(['uniform', 'alike', 'relu'])], 0)
+    gen = torch.Generator().manual_seed(9)
+    dm = torch.randn(3, 48, 30, 40, generator=gen)
+    kps, val, desc, count = lg.extract_batched(maps.to(DEV), dm.to(DEV), 8, max_num_kps=400)
+    for i in range(3):
+        wkp, wval, wdesc, _ = ref_ops.lightglue_extract(maps[i].numpy(), dm[i].numpy(), 8, max_num_kps=400)
+        n = int(count[i])
+        assert n == wkp.shape[0]
+        assert np.array_equal(kps[i, :n].cpu().numpy(), wkp) and np.array_equal(val[i, :n].cpu().numpy(), wval)
+        assert np.allclose(desc[i, :n].cpu().numpy(), wdesc, rtol=1e-5, atol=1e-5)
+        assert not kps[i, n:].any() and not desc[i, n:].any()

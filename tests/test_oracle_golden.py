@@ -161,3 +161,29 @@ def test_warp_se3_restatement_matches_reference(golden):
         a, b, ids, ids_out = ref_ops.warp(g[f'{tag}__kp'], params)
         assert np.array_equal(ids, g[f'{tag}__ids']) and np.array_equal(ids_out, g[f'{tag}__ids_out']), tag
         assert np.allclose(a, g[f'{tag}__valid'], rtol=1e-5, atol=1e-6) and np.allclose(b, g[f'{tag}__proj'], rtol=1e-5, atol=1e-5)
+
+
+def _lg_compare(got_kp, got_val, got_desc, g, tag, w):
+    """torch.topk orders ties arbitrarily (lightglue.py:926): compare keyed by pixel."""
+    rkp, rval, rdesc = g[f'{tag}__kp'], g[f'{tag}__val'], g[f'{tag}__desc']
+    assert got_kp.shape == rkp.shape and got_desc.shape == rdesc.shape, tag
+    o_r = np.argsort(rkp[:, 1].astype(np.int64) * w + rkp[:, 0].astype(np.int64))
+    o_g = np.argsort(got_kp[:, 1].astype(np.int64) * w + got_kp[:, 0].astype(np.int64))
+    assert np.array_equal(rkp[o_r], got_kp[o_g]), tag
+    assert np.array_equal(rval[o_r], got_val[o_g]), tag
+    assert np.allclose(rdesc[o_r], got_desc[o_g], rtol=1e-5, atol=1e-5), tag
+    uniq, cnt = np.unique(rval, return_counts=True)
+    single = np.isin(rval, uniq[cnt == 1])
+    assert np.array_equal(rkp[single], got_kp[np.isin(got_val, uniq[cnt == 1])]), tag     # order, where it is defined
+
+
+def test_lightglue_extract_restatement_matches_reference_fixtures(golden):
+    from oracle.make_golden import LG_CASES
+    g = golden('ref_lightglue.npz')
+    for tag, kind, h, w, seed, c, s in LG_CASES:
+        sc = synth.score_map(kind, h, w, seed).numpy()
+        for r in (0, 2, 5):
+            if f'{tag}__nms{r}' in g.files:
+                assert np.array_equal(ref_ops.simple_nms(sc[0, 0], r), g[f'{tag}__nms{r}']), (tag, r)
+        kp, val, desc, _ = ref_ops.lightglue_extract(sc, g[f'{tag}__dm'], s)
+        _lg_compare(kp, val, desc, g, tag, w)
