@@ -116,6 +116,25 @@ KB_API int kb_simple_nms(const float* score, float* out, int B, int H, int W, in
                   size_t ws_bytes, kb_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Tensor Lucas-Kanade matcher: OpticalFlow.__call__ / optical_flow_tensor
+ *                                                        utils/matcher.py:7-142, 188-203
+ *
+ * Tracks n keypoints of image 0 into image 1.  img0/img1 [B,C,H,W]; pts0_px and
+ * init_px [B,n_max,2] in PIXELS of the full-resolution image (the reference's pts*(W-1,H-1) and its
+ * randomly displaced, clamped start, matcher.py:52-61 -- drawing the random start is the caller's job);
+ * count [B] (NULL = n_max).  Pyramid level j >= 1 is avg_pool2d(img, kernel 2j, stride 2j) of the
+ * original image with coordinates scaled by 2^j; per level `iterations` Gauss-Newton steps on
+ * win_size^2*C-sample patches (bilinear, zero padding) with the per-channel Sobel gradients of image 1;
+ * a step is skipped where det(G) <= 1e-6, and uses the reference's update
+ * delta_b = b_b * sum_i inv(G)[b,i] (matcher.py:139).  out_px [B,n_max,2] in pixels (what
+ * optical_flow_tensor returns).  win_size odd; levels <= 8; C*win_size^2 <= 51200.
+ * ------------------------------------------------------------------------------------------- */
+KB_API size_t kb_lk_workspace_bytes(int B, int C, int H, int W, int levels);
+KB_API int kb_lk_track(const float* img0, const float* img1, int B, int C, int H, int W, const float* pts0_px,
+                const float* init_px, const int* count, int n_max, int win_size, int levels, int iterations,
+                float* out_px, void* ws, size_t ws_bytes, kb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Stage 2 -- descriptor sampling      utils/matcher.py:221-226 and models/lightglue.py:24-41
  *
  * desc [B,C,h,w] (NCHW as the backbones emit it); pts [B,n_max,pts_stride] with (x,y) in the first

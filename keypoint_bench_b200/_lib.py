@@ -29,6 +29,9 @@ PROTOTYPES = {
                           c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     'kb_simple_nms_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
     'kb_simple_nms': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    'kb_lk_workspace_bytes': (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    'kb_lk_track': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                            c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     'kb_detect_workspace_bytes': (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_float]),
     'kb_detect': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_int, c_void_p, c_void_p,
                           c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

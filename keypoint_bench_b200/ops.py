@@ -206,6 +206,36 @@ def sample_batched(desc: torch.Tensor, pts: torch.Tensor, count: torch.Tensor | 
 # Stage 3
 # ------------------------------------------------------------------------------------------------
 
+def lk_track_batched(img0: torch.Tensor, img1: torch.Tensor, pts0_px: torch.Tensor, init_px: torch.Tensor,
+                     count: torch.Tensor | None = None, win_size: int = 3, levels: int = 1, iterations: int = 40):
+    """Pyramidal Gauss-Newton patch tracking of ``OpticalFlow`` (utils/matcher.py:49-142) for B image pairs.
+    img [B,C,H,W]; pts0_px / init_px [B,n,2] in pixels -> tracked points [B,n,2] in pixels."""
+    _require_cuda(img0, 'img0')
+    _require_cuda(img1, 'img1')
+    a, bm = _f32(img0), _f32(img1)
+    if a.dim() != 4 or a.shape != bm.shape:
+        raise ValueError(f'images must be two [B,C,H,W] tensors of one shape, got {tuple(img0.shape)} / {tuple(img1.shape)}')
+    b, c, h, w = a.shape
+    p0, pi = _f32(pts0_px), _f32(init_px)
+    if p0.shape != pi.shape or p0.dim() != 3 or p0.shape[0] != b or p0.shape[2] != 2:
+        raise ValueError('pts0_px / init_px must both be [B,n,2]')
+    n = p0.shape[1]
+    out = _out(b, max(n, 1), 2, dtype=torch.float32, device=a.device)[:, :n]
+    if n == 0:
+        return out
+    nbytes = lib.kb_lk_workspace_bytes(b, c, h, w, int(levels))
+    if nbytes == 0:
+        raise _lib.KbError(f'kb_lk_track: unsupported pyramid ({levels} levels of a {h}x{w} image)')
+    ws = _ws(nbytes, a.device)
+    cnt = _i32(count)
+    with torch.cuda.device(a.device):
+        check(lib.kb_lk_track(a.data_ptr(), bm.data_ptr(), b, c, h, w, p0.data_ptr(), pi.data_ptr(), _ptr(cnt), n,
+                              int(win_size), int(levels), int(iterations), out.data_ptr(), ws.data_ptr(), ws.numel(),
+                              _stream()), 'kb_lk_track')
+    _count(4 * int(levels) - 1)
+    return out
+
+
 def match_batched(d0: torch.Tensor, d1: torch.Tensor, n0: torch.Tensor | None = None, n1: torch.Tensor | None = None,
                   max_distance: float = math.inf, cross_check: bool = True, algo: int = -1, return_ws: bool = False,
                   phases: int = 7, state=None, want_dist: bool = True):

@@ -229,3 +229,22 @@ def se3_scene(h: int, w: int, seed: int, device="cpu") -> dict:
     f32 = lambda t: t.to(torch.float32).to(device)      # noqa: E731
     return {'mode': 'se3', 'width': w, 'height': h, 'pose01': f32(pose), 'bbox0': bbox0.to(device), 'bbox1': bbox1.to(device),
             'depth0': f32(depth0), 'depth1': f32(depth1), 'intrinsics0': f32(k0), 'intrinsics1': f32(k1)}
+
+
+def lk_scene(c: int, h: int, w: int, seed: int, shift=(2.3, -1.7), sigma: float = 3.0, device="cpu"):
+    """Two smooth images for the Lucas-Kanade tracker (utils/matcher.py:7-142): Gaussian-filtered noise scaled to
+    [0,1] (an 'image' the tracker can converge on) and the same field translated by ``shift`` pixels
+    (img1(x, y) = img0(x - dx, y - dy), bilinear).  -> img0, img1 [1,c,h,w]."""
+    g = _gen(seed)
+    x = torch.randn(1, c, h, w, generator=g)
+    k = int(4 * sigma) | 1
+    ax = torch.arange(k, dtype=torch.float32) - k // 2
+    ker = torch.exp(-ax ** 2 / (2 * sigma ** 2))
+    ker = ker / ker.sum()
+    x = torch.nn.functional.conv2d(x, ker.view(1, 1, 1, k).repeat(c, 1, 1, 1), padding=(0, k // 2), groups=c)
+    x = torch.nn.functional.conv2d(x, ker.view(1, 1, k, 1).repeat(c, 1, 1, 1), padding=(k // 2, 0), groups=c)
+    img0 = (x - x.min()) / (x.max() - x.min())
+    ys, xs = torch.meshgrid(torch.arange(h, dtype=torch.float32), torch.arange(w, dtype=torch.float32), indexing='ij')
+    grid = torch.stack([(xs - shift[0]) / (w - 1) * 2 - 1, (ys - shift[1]) / (h - 1) * 2 - 1], dim=-1)[None]
+    img1 = torch.nn.functional.grid_sample(img0, grid, align_corners=True, padding_mode='border')
+    return img0.to(device), img1.to(device)

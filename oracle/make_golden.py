@@ -299,6 +299,44 @@ def gen_lightglue():
     np.savez_compressed(os.path.join(GOLD, 'ref_lightglue.npz'), **out)
 
 
+LK_CASES = [  # tag, C, H, W, win_size, levels, iterations, distance, seed, n
+    ('lk_cfg', 3, 96, 128, 21, 3, 40, 10, 1, 150),        # the shipped YAML settings (config_fund.yaml:72-77)
+    ('lk_default', 3, 64, 80, 3, 1, 40, 3, 2, 100),       # the class defaults (matcher.py:9-16)
+    ('lk_gray', 1, 72, 96, 9, 2, 10, 5, 3, 100),
+    ('lk_onestep', 3, 96, 128, 21, 3, 1, 10, 4, 150),     # a single step per level: no convergence to hide behind
+]
+
+
+def gen_lk(ref):
+    """optical_flow_tensor (utils/matcher.py:188-203) with the random start replayed from the same torch seed."""
+    out = {}
+    for tag, c, h, w, win, levels, iters, dist, seed, n in LK_CASES:
+        img0, img1 = synth.lk_scene(c, h, w, seed)
+        g = torch.Generator().manual_seed(seed + 50)
+        pts = torch.rand(n, 2, generator=g)
+        pts[:4] = torch.tensor([[0.0, 0.0], [1.0, 1.0], [0.02, 0.97], [0.5, 0.001]])      # corners / borders
+        params = {'distance': dist, 'win_size': win, 'levels': levels, 'interation': iters, 'gray': c == 1}
+        torch.manual_seed(seed + 99)
+        t0 = time.time()
+        want = ref.matcher.optical_flow_tensor(pts, pts, img0, img1, params)[0].numpy()
+        dt = time.time() - t0
+        torch.manual_seed(seed + 99)
+        angle = (torch.randn(n) * 6.28).numpy()                                           # matcher.py:55
+        init = ref_ops.lk_init_points(pts.numpy(), h, w, dist, angle)
+        p0 = pts.numpy() * np.array([w - 1, h - 1], np.float32)
+        mine = ref_ops.lk_track(img0[0].numpy(), img1[0].numpy(), p0, init, win, levels, iters)
+        err = np.abs(mine - want).max()
+        assert err < 1e-3, (tag, err)
+        log(f'optical_flow_tensor {tag}: C={c} {h}x{w} win={win} levels={levels} it={iters} n={n} '
+            f'reference_cpu_s={dt:.2f} max |restated - reference| = {err:.2e} px')
+        out[f'{tag}__img0'] = img0.numpy()
+        out[f'{tag}__img1'] = img1.numpy()
+        out[f'{tag}__pts'] = pts.numpy()
+        out[f'{tag}__init'] = init
+        out[f'{tag}__out'] = want
+    np.savez_compressed(os.path.join(GOLD, 'ref_lk.npz'), **out)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
@@ -310,6 +348,7 @@ def main():
     gen_eval(ref)
     gen_se3(ref)
     gen_lightglue()
+    gen_lk(ref)
     with open(os.path.join(ROOT, 'oracle', 'REFCHECK.log'), 'w') as f:
         f.write('\n'.join(LOG) + '\n')
 

@@ -346,6 +346,128 @@ def lightglue_extract(scores: np.ndarray, desc_map: np.ndarray, s: int, detectio
 
 
 # --------------------------------------------------------------------------------------
+# Tensor Lucas-Kanade matcher  (utils/matcher.py:7-142, 188-203)
+# --------------------------------------------------------------------------------------
+
+
+def lk_pyramid(img: np.ndarray, levels: int):
+    """matcher.py:38-47 -- level j >= 1 is ``avg_pool2d(img, kernel=2j, stride=2j)`` of the ORIGINAL
+    image (kernel 2, 4, 6 ... while the coordinates are scaled by 2^j -- the mismatch from level 3 on
+    is the reference's).  img [C,H,W] -> list of [C,Hj,Wj]."""
+    img = np.asarray(img, dtype=np.float32)
+    out = [img]
+    c, h, w = img.shape
+    for j in range(1, levels):
+        k = 2 * j
+        hh, ww = h // k, w // k
+        acc = np.zeros((c, hh, ww), dtype=np.float32)
+        for a in range(k):                      # row-major running sum like the CPU pooling loop
+            for b in range(k):
+                acc += img[:, a:a + hh * k:k, b:b + ww * k:k]
+        out.append(acc / np.float32(k * k))
+    return out
+
+
+def lk_sobel(img: np.ndarray):
+    """matcher.py:22-35, 104-109 -- per-channel 3x3 cross-correlation with [[1,0,-1],[2,0,-2],[1,0,-1]]
+    (dx) and its transpose (dy), zero padding 1.  [C,H,W] -> (dx, dy)."""
+    p = np.pad(np.asarray(img, dtype=np.float32), ((0, 0), (1, 1), (1, 1)))
+    tl, tc, tr = p[:, :-2, :-2], p[:, :-2, 1:-1], p[:, :-2, 2:]
+    ml, mr = p[:, 1:-1, :-2], p[:, 1:-1, 2:]
+    bl, bc, br = p[:, 2:, :-2], p[:, 2:, 1:-1], p[:, 2:, 2:]
+    two = np.float32(2)
+    dx = (tl - tr) + two * (ml - mr) + (bl - br)
+    dy = (tl + two * tc + tr) - (bl + two * bc + br)
+    return dx.astype(np.float32), dy.astype(np.float32)
+
+
+def lk_patch_sample(img: np.ndarray, pts_px: np.ndarray, win: int) -> np.ndarray:
+    """``grid_sample(unfold(img, win, padding=win//2).view(1,-1,H,W), pts/(W-1,H-1)*2-1, align_corners=True)``
+    (matcher.py:113-128, 134) without materialising the unfold: entry (c,u,v) of the unfolded map at pixel
+    (y,x) is img[c, y+u-p, x+v-p] (0 outside), and the bilinear tap adds the four integer corners that lie
+    INSIDE the map, so a corner outside contributes nothing even when its shifted pixel is inside.
+    img [C,H,W], pts [n,2] pixels -> [n, C*win*win] (channel order c, u, v)."""
+    c, h, w = img.shape
+    pad = win // 2
+    pts = np.asarray(pts_px, dtype=np.float32)
+    g = pts / np.array([w - 1, h - 1], dtype=np.float32) * np.float32(2) - np.float32(1)
+    ix = ((g[:, 0] + np.float32(1)) / np.float32(2)) * np.float32(w - 1)
+    iy = ((g[:, 1] + np.float32(1)) / np.float32(2)) * np.float32(h - 1)
+    x0, y0 = np.floor(ix), np.floor(iy)
+    x1, y1 = x0 + 1, y0 + 1
+    wts = ((x1 - ix) * (y1 - iy), (ix - x0) * (y1 - iy), (x1 - ix) * (iy - y0), (ix - x0) * (iy - y0))
+    corners = ((x0, y0), (x1, y0), (x0, y1), (x1, y1))
+    padded = np.pad(img, ((0, 0), (pad, pad), (pad, pad)))
+    n = pts.shape[0]
+    out = np.zeros((n, c, win, win), dtype=np.float32)
+    du = np.arange(win)
+    for (xs, ys), wt in zip(corners, wts):
+        ok = (xs >= 0) & (xs <= w - 1) & (ys >= 0) & (ys <= h - 1) & np.isfinite(xs) & np.isfinite(ys)
+        xi = np.where(ok, xs, 0).astype(np.int64)
+        yi = np.where(ok, ys, 0).astype(np.int64)
+        rows = (yi[:, None] + du[None, :])                       # padded row of (u): y + u - pad + pad
+        cols = (xi[:, None] + du[None, :])
+        tap = padded[:, rows[:, :, None], cols[:, None, :]]       # [C, n, win, win]
+        tap = np.transpose(tap, (1, 0, 2, 3))
+        out += np.where(ok[:, None, None, None], tap * wt.astype(np.float32)[:, None, None, None], np.float32(0))
+    return out.reshape(n, c * win * win)
+
+
+def lk_level(img1: np.ndarray, img2: np.ndarray, pts1: np.ndarray, pts2: np.ndarray, win: int, iterations: int):
+    """matcher.py:94-142 -- ``iterations`` Gauss-Newton steps on one pyramid level.  The update is the
+    reference's ``einsum('bik,bk->bk', G_inverse, b)`` (:139): component b of the right-hand side times the
+    ROW SUM of the inverse (not a matrix-vector product) -- part of the contract.  Points whose 2x2 normal
+    matrix has det <= 1e-6 do not move (:137).  Returns the new points [n,2] float32."""
+    dx2, dy2 = lk_sobel(img2)
+    ref_patch = lk_patch_sample(img1, pts1, win)
+    p = np.array(pts2, dtype=np.float32, copy=True)
+    for _ in range(iterations):
+        d_i = ref_patch - lk_patch_sample(img2, p, win)
+        jx = lk_patch_sample(dx2, p, win)
+        jy = lk_patch_sample(dy2, p, win)
+        gxx = (jx * jx).sum(1, dtype=np.float32)
+        gxy = (jx * jy).sum(1, dtype=np.float32)
+        gyy = (jy * jy).sum(1, dtype=np.float32)
+        bx = (d_i * jx).sum(1, dtype=np.float32)
+        by = (d_i * jy).sum(1, dtype=np.float32)
+        det = gxx.astype(np.float64) * gyy - gxy.astype(np.float64) * gxy
+        ok = det.astype(np.float32) > np.float32(1e-6)
+        safe = np.where(ok, det, 1.0)
+        i00, i01 = (gyy / safe).astype(np.float32), (-gxy / safe).astype(np.float32)
+        i11 = (gxx / safe).astype(np.float32)
+        step = np.stack([i00 * bx + i01 * bx, i01 * by + i11 * by], axis=1).astype(np.float32)
+        p = np.where(ok[:, None], p - step, p).astype(np.float32)
+    return p
+
+
+def lk_init_points(pts1_norm: np.ndarray, h: int, w: int, distance: float, angle: np.ndarray) -> np.ndarray:
+    """matcher.py:52-61 -- start points: ``pts1*(W-1,H-1) + (cos, sin)(angle)*distance`` clamped to
+    x in [10, W-10], y in [10, H-10]; ``angle`` is the reference's ``randn(n)*6.28`` draw."""
+    p = np.asarray(pts1_norm, dtype=np.float32)[:, :2] * np.array([w - 1, h - 1], dtype=np.float32)
+    a = np.asarray(angle, dtype=np.float32)
+    p = p + np.stack([np.cos(a), np.sin(a)], axis=1).astype(np.float32) * np.float32(distance)
+    p[:, 0] = np.clip(p[:, 0], 10, w - 10)
+    p[:, 1] = np.clip(p[:, 1], 10, h - 10)
+    return p.astype(np.float32)
+
+
+def lk_track(img0: np.ndarray, img1: np.ndarray, pts0_px: np.ndarray, init_px: np.ndarray, win: int, levels: int,
+             iterations: int) -> np.ndarray:
+    """``OpticalFlow.__call__`` (matcher.py:49-92) after the random start has been drawn: coarse-to-fine over
+    the pyramid, coordinates divided by 2^level going down and multiplied back coming up.  img [C,H,W],
+    points in PIXELS of the full-resolution image -> tracked points [n,2] in pixels (what the reference
+    returns: ``optical_flow_tensor`` does not re-normalise, :201-203)."""
+    pyr0, pyr1 = lk_pyramid(img0, levels), lk_pyramid(img1, levels)
+    p0 = np.asarray(pts0_px, dtype=np.float32)
+    cur = np.asarray(init_px, dtype=np.float32)
+    for i in range(levels):
+        lvl = levels - i - 1
+        sc = np.float32(2 ** lvl)
+        cur = lk_level(pyr0[lvl], pyr1[lvl], p0 / sc, cur / sc, win, iterations) * sc
+    return cur
+
+
+# --------------------------------------------------------------------------------------
 # Stage 3: brute-force mutual-NN matching  (utils/matcher.py:227-234 -> skimage, absent)
 # --------------------------------------------------------------------------------------
 

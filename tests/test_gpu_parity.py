@@ -557,3 +557,53 @@ def test_lightglue_extract_batched_against_oracle():
         assert np.array_equal(kps[i, :n].cpu().numpy(), wkp) and np.array_equal(val[i, :n].cpu().numpy(), wval)
         assert np.allclose(desc[i, :n].cpu().numpy(), wdesc, rtol=1e-5, atol=1e-5)
         assert not kps[i, n:].any() and not desc[i, n:].any()
+
+
+# ------------------------------------------------------------------------------------------------ Lucas-Kanade tracker
+
+def test_lk_tracker_matches_reference_fixtures(golden):
+    """optical_flow_tensor (utils/matcher.py:188-203) on the fixtures minted from the reference, the random start
+    replayed; 1e-3 px on every point (float32 Gauss-Newton iteration; measured ~1e-5)."""
+    from keypoint_bench_b200.utils.matcher import OpticalFlow
+    from oracle.make_golden import LK_CASES
+    g = golden('ref_lk.npz')
+    for tag, c, h, w, win, levels, iters, dist, seed, n in LK_CASES:
+        params = {'distance': dist, 'win_size': win, 'levels': levels, 'interation': iters, 'gray': c == 1}
+        img0, img1 = torch.from_numpy(g[f'{tag}__img0']).to(DEV), torch.from_numpy(g[f'{tag}__img1']).to(DEV)
+        pts = torch.from_numpy(g[f'{tag}__pts']).to(DEV)
+        start = torch.from_numpy(g[f'{tag}__init'])[None].to(DEV)
+        out, err = OpticalFlow(params)(img0, img1, pts, pts, start=start)
+        assert out.shape == (1, n, 2) and err.shape == (1, n)
+        d = np.abs(out[0].cpu().numpy() - g[f'{tag}__out']).max()
+        assert d < 1e-3, (tag, d)
+
+
+def test_optical_flow_tensor_dropin_and_batched_against_oracle():
+    from keypoint_bench_b200.utils.matcher import optical_flow_tensor, optical_flow_cv
+    params = {'distance': 4, 'win_size': 11, 'levels': 2, 'interation': 8, 'gray': False}
+    scenes = [synth.lk_scene(3, 120, 160, 20 + i, shift=(1.5 + i, -2.0)) for i in range(2)]
+    img0 = torch.cat([s[0] for s in scenes], 0)
+    img1 = torch.cat([s[1] for s in scenes], 0)
+    gen = torch.Generator().manual_seed(4)
+    pts = torch.rand(2, 90, 2, generator=gen)
+    scale = torch.tensor([159.0, 119.0])
+    init = pts * scale + torch.randn(2, 90, 2, generator=gen) * 2
+    cnt = torch.tensor([90, 41], dtype=torch.int32)
+    out = ops().lk_track_batched(img0.to(DEV), img1.to(DEV), (pts * scale).to(DEV), init.to(DEV), cnt.to(DEV), 11, 2, 8)
+    for b in range(2):
+        k = int(cnt[b])
+        want = ref_ops.lk_track(img0[b].numpy(), img1[b].numpy(), (pts[b, :k] * scale).numpy(), init[b, :k].numpy(), 11, 2, 8)
+        assert np.abs(out[b, :k].cpu().numpy() - want).max() < 1e-3, b
+        assert not out[b, k:].any()
+    # the drop-in draws its own random start (matcher.py:55): most points must land on the true shift
+    torch.manual_seed(0)
+    params = {'distance': 3, 'win_size': 21, 'levels': 3, 'interation': 40, 'gray': False}
+    got = optical_flow_tensor(pts[0, :, :2].to(DEV), pts[0, :, :2].to(DEV), img0[0:1].to(DEV), img1[0:1].to(DEV), params)
+    assert got.shape == (1, 90, 2)
+    inner = ((pts[0] > 0.25) & (pts[0] < 0.75)).all(dim=1)
+    err = (got[0].cpu() - (pts[0] * scale + torch.tensor([1.5, -2.0]))).norm(dim=1)[inner]
+    assert (err < 0.5).float().mean() > 0.5
+    with pytest.raises(NotImplementedError):
+        optical_flow_cv(None, None, None, None)
+    with pytest.raises(RuntimeError):
+        optical_flow_tensor(pts[0].to(DEV), pts[0].to(DEV), img0[0:1, :1].to(DEV), img1[0:1, :1].to(DEV), params)

@@ -187,3 +187,17 @@ def test_lightglue_extract_restatement_matches_reference_fixtures(golden):
                 assert np.array_equal(ref_ops.simple_nms(sc[0, 0], r), g[f'{tag}__nms{r}']), (tag, r)
         kp, val, desc, _ = ref_ops.lightglue_extract(sc, g[f'{tag}__dm'], s)
         _lg_compare(kp, val, desc, g, tag, w)
+
+
+def test_lk_restatement_matches_reference_fixtures(golden):
+    """Tolerance: 1e-3 px on every point (measured 1.5e-5 at minting time, oracle/REFCHECK.log); the tracker is a
+    float32 fixed-point iteration, so summation order moves the last bits."""
+    from oracle.make_golden import LK_CASES
+    g = golden('ref_lk.npz')
+    for tag, c, h, w, win, levels, iters, dist, seed, n in LK_CASES:
+        if iters * levels > 40:
+            continue                                  # the 3x40-iteration case takes ~1 min in numpy; the GPU test covers it
+        img0, img1 = g[f'{tag}__img0'], g[f'{tag}__img1']
+        p0 = g[f'{tag}__pts'] * np.array([w - 1, h - 1], np.float32)
+        got = ref_ops.lk_track(img0[0], img1[0], p0, g[f'{tag}__init'], win, levels, iters)
+        assert np.abs(got - g[f'{tag}__out']).max() < 1e-3, tag
