@@ -44,6 +44,8 @@ def parse_args():
     ap.add_argument('--kind', default='uniform', help='synthetic score-map kind (uniform | alike)')
     ap.add_argument('--cpu-pairs', type=int, default=2, help='pairs timed on the host for cpu_baseline (0 = skip)')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--in-flight', type=int, default=2,
+                    help='steps kept in flight (one CUDA graph + stream + batch per slot); 1 = strictly serial steps')
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel from Python instead of replaying a CUDA graph')
     return ap.parse_args()
 
@@ -302,94 +304,149 @@ def main():
         stage_ms['sample'] = time_stage(lambda: ops.sample_batched(batch.desc, kv, nv))
         stage_ms['match'] = time_stage(lambda: ops.match_batched(dd[:P], dd[P:], nv[:P], nv[P:], cfg.max_distance,
                                                                  cfg.cross_check, algo=algo, want_dist=False))
-    # steady state: the launch sequence of one step replayed as a CUDA graph (same kernels, same buffers)
-    graphed = None
+    # steady state: the launch sequence of one step replayed as a CUDA graph (same kernels, same buffers);
+    # `--in-flight` slots, each with its own batch, graph and stream, so consecutive steps overlap
+    depth = 1 if args.no_graph else max(1, args.in_flight)
+    batches = [batch] + [make_batch(cfg, cfg_index, P, (rank + world * s) * P, device, args.kind)[0]
+                         for s in range(1, depth)]
+    graphed = flight = None
     if not args.no_graph:
         try:
-            graphed = pipeline.GraphedStep(step)
+            flight = pipeline.StepsInFlight([(lambda b=b: step(None, b)) for b in batches])
+            graphed = flight.slots[0]
         except Exception as e:      # noqa: BLE001 -- fall back to eager launches, say so in the JSON line
             config['cuda_graph_error'] = repr(e)[:200]
-            graphed = None
+            graphed = flight = None
+            depth = 1
             torch.cuda.synchronize()
-    config['launch'] = 'cuda graph replay of the step' if graphed is not None else 'eager launches from Python'
+    config['launch'] = (f'cuda graph replay of the step, {depth} step(s) in flight on {depth} stream(s)'
+                        if graphed is not None else 'eager launches from Python')
+    config['steps_in_flight'] = depth
     run = graphed if graphed is not None else step
-    for _ in range(2):
-        run()
-    torch.cuda.synchronize()
-    parallel.barrier()
-    torch.cuda.synchronize()
-    acc = None
-    ev0 = torch.cuda.Event(enable_timing=True)
-    ev1 = torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(args.steps):
-        res, a = run()
-        acc = a.clone() if acc is None else acc + a
-    acc = parallel.reduce_counts(acc)               # the run's single collective
-    ev1.record()
-    torch.cuda.synchronize()
-    parallel.barrier()
-    torch.cuda.synchronize()
-    n_launch = launches_per_step * args.steps
-    ms = ev0.elapsed_time(ev1)
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=device)
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-        ms = float(t.item())
+
+    def timed_steps(n_steps, in_flight):
+        """n_steps steps between two events on the launch stream; returns (ms, accumulated counters)."""
+        torch.cuda.synchronize()
+        parallel.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        accs = [None] * depth
+        e0.record()
+        if in_flight and flight is not None and depth > 1:
+            def after(k, out):
+                accs[k] = out[1].clone() if accs[k] is None else accs[k] + out[1]
+            flight.fork()
+            for i in range(n_steps):
+                flight.launch(i, after=after)
+            flight.join()
+        else:
+            for _ in range(n_steps):
+                _, a = run()
+                accs[0] = a.clone() if accs[0] is None else accs[0] + a
+        tot = None
+        for a in accs:
+            if a is not None:
+                a.record_stream(torch.cuda.current_stream())
+                tot = a if tot is None else tot + a
+        tot = parallel.reduce_counts(tot)             # the run's single collective
+        e1.record()
+        torch.cuda.synchronize()
+        parallel.barrier()
+        torch.cuda.synchronize()
+        t = e0.elapsed_time(e1)
+        if world > 1:
+            tt = torch.tensor([t], dtype=torch.float64, device=device)
+            torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
+            t = float(tt.item())
+        return t, tot
+
+    timed_steps(2 * depth, True)                      # graph / stream warm-up
+    serial_ms = None
+    if depth > 1:
+        serial_ms, _ = timed_steps(args.steps, False)  # the same steps strictly one after another, for reference
+    ms, acc = timed_steps(args.steps, True)
     value = world * P * args.steps / (ms / 1000.0)
+    n_launch = launches_per_step * args.steps
+    res, _ = run()                                     # slot 0 = `batch`: the outputs checked against the CPU port below
+    torch.cuda.synchronize()
 
     # ---- end to end through the public API with HOST buffers -----------------------------------
     e2e = None
     if not args.no_e2e:
-        host_score = batch.score.cpu().pin_memory()
-        host_desc = batch.desc.cpu().pin_memory() if batch.desc is not None else None
-        dev_score = torch.empty_like(batch.score)
-        dev_desc = torch.empty_like(batch.desc) if batch.desc is not None else None
-        hb = pipeline.PairBatch(dev_score, dev_desc, batch.h33, batch.wh, batch.resize)
+        # every slot: pinned host inputs -> device copy -> the step's graph -> device -> pinned host results, all on the
+        # slot's stream; the host waits for a slot's previous results before it relaunches that slot (the caller
+        # consumes the result of every step), so with two slots one step's copies overlap the other's kernels
         top = cfg.top_k
-        out_pairs = torch.empty((P, top, 2), dtype=torch.int32).pin_memory()
-        out_n = torch.empty((P,), dtype=torch.int32).pin_memory()
-        out_stats = torch.empty((P, 4), dtype=torch.float64).pin_memory()
-
-        e2e_run = None
-        if graphed is not None:
+        in_bytes = batch.score.numel() * 4 + (batch.desc.numel() * 4 if batch.desc is not None else 0)
+        slots = []
+        for k, bk in enumerate(batches):
+            share = k > 0 and in_bytes > (2 << 30)     # do not pin a second multi-GB host copy: reuse slot 0's
+            sl = {'host_score': slots[0]['host_score'] if share else bk.score.cpu().pin_memory(),
+                  'host_desc': None if bk.desc is None else (slots[0]['host_desc'] if share else bk.desc.cpu().pin_memory()),
+                  'dev_score': torch.empty_like(bk.score),
+                  'dev_desc': torch.empty_like(bk.desc) if bk.desc is not None else None,
+                  'out_pairs': torch.empty((P, top, 2), dtype=torch.int32).pin_memory(),
+                  'out_n': torch.empty((P,), dtype=torch.int32).pin_memory(),
+                  'out_stats': torch.empty((P, 4), dtype=torch.float64).pin_memory(),
+                  'done': torch.cuda.Event()}
+            sl['batch'] = pipeline.PairBatch(sl['dev_score'], sl['dev_desc'], bk.h33, bk.wh, bk.resize)
+            slots.append(sl)
+        e2e_flight = None
+        if flight is not None:
             try:
-                e2e_run = pipeline.GraphedStep(lambda: step(None, hb))
+                e2e_flight = pipeline.StepsInFlight([(lambda b=sl['batch']: step(None, b)) for sl in slots])
             except Exception:       # noqa: BLE001
-                e2e_run = None
+                e2e_flight = None
                 torch.cuda.synchronize()
-        if e2e_run is None:
-            e2e_run = lambda: step(None, hb)        # noqa: E731
 
-        def e2e_step():
-            dev_score.copy_(host_score, non_blocking=True)
-            if dev_desc is not None:
-                dev_desc.copy_(host_desc, non_blocking=True)
-            r, _ = e2e_run()
+        def copy_in(k):
+            sl = slots[k]
+            sl['dev_score'].copy_(sl['host_score'], non_blocking=True)
+            if sl['dev_desc'] is not None:
+                sl['dev_desc'].copy_(sl['host_desc'], non_blocking=True)
+
+        def copy_out(k, out):
+            sl, r = slots[k], out[0]
             if task_rep:
-                out_stats.copy_(r['stats'], non_blocking=True)
+                sl['out_stats'].copy_(r['stats'], non_blocking=True)
             else:
-                out_pairs.copy_(r['matches'], non_blocking=True)
-                out_n.copy_(r['n_matches'], non_blocking=True)
-            torch.cuda.synchronize()                 # the caller consumes the result every step
+                sl['out_pairs'].copy_(r['matches'], non_blocking=True)
+                sl['out_n'].copy_(r['n_matches'], non_blocking=True)
+            sl['done'].record()
+
+        def e2e_steps_run(n_steps):
+            if e2e_flight is not None:
+                e2e_flight.fork()
+                for i in range(n_steps):
+                    if i >= depth:
+                        slots[i % depth]['done'].synchronize()      # results of this slot's previous step are consumed
+                    e2e_flight.launch(i, before=copy_in, after=copy_out)
+                e2e_flight.join()
+                torch.cuda.synchronize()
+            else:
+                for _ in range(n_steps):
+                    copy_in(0)
+                    copy_out(0, step(None, slots[0]['batch']))
+                    torch.cuda.synchronize()
 
         e2e_steps = max(3, min(args.steps, 10))
-        e2e_step()
+        e2e_steps_run(depth)
         parallel.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            e2e_step()
+        e2e_steps_run(e2e_steps)
         dt = time.perf_counter() - t0
         if world > 1:
             t = torch.tensor([dt], dtype=torch.float64, device=device)
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
             dt = float(t.item())
-        h2d = host_score.numel() * 4 + (host_desc.numel() * 4 if host_desc is not None else 0)
-        d2h = out_stats.numel() * 8 if task_rep else out_pairs.numel() * 4 + out_n.numel() * 4
+        h2d = in_bytes
+        d2h = slots[0]['out_stats'].numel() * 8 if task_rep else (slots[0]['out_pairs'].numel() * 4 +
+                                                                 slots[0]['out_n'].numel() * 4)
         e2e = {'value': world * P * e2e_steps / dt, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-               'steps': e2e_steps, 'note': 'pinned host -> device copy of score+descriptor maps, hot path, '
-                                           'device -> host copy of match index pairs and counts, every step'}
+               'steps': e2e_steps, 'steps_in_flight': depth if e2e_flight is not None else 1,
+               'note': 'pinned host -> device copy of score+descriptor maps, hot path, device -> host copy of match '
+                       'index pairs and counts, every step; the host waits for a slot\'s results before reusing the slot'}
     clocks = sampler.stop()
 
     if rank != 0:
@@ -472,6 +529,8 @@ def main():
             'vs_baseline': None, 'dtype': 'f32+f64', 'data': 'synthetic', 'config': config, 'clocks': clocks,
             'e2e': e2e, 'gpu_launches': n_launch, 'roofline': roof, 'cpu_baseline': cpu,
             'counts': {'sum_matches_or_rep': float(acc[0]), 'pairs': float(acc[1])}}
+    if serial_ms is not None:       # the same K steps strictly one after another (what the per-kernel shares refer to)
+        line['serial'] = {'ms_per_step': serial_ms / args.steps, 'value': world * P * args.steps / (serial_ms / 1000.0)}
     print(json.dumps(line))
     parallel.shutdown()
     return 0
