@@ -29,7 +29,7 @@ namespace kbtc {
 constexpr int BM = 128, BN = 256, BK = 64;       // BN = 256: one tcgen05.mma covers 128x256x16 (the issue rate of
                                                  // a single thread, ~70 cycles, cannot feed N = 128 instructions)
 constexpr int TILE_BYTES = BM * BK * 2;          // 16 KB, one 128B-swizzled K-major tile
-constexpr int MAX_SLOTS = 6;                     // ring depth is chosen on the host from the free shared memory
+constexpr int MAX_SLOTS = 8;                     // ring depth is chosen on the host from the free shared memory
 constexpr int EPI_SLICES = 4;                    // column slices of a tile, one epilogue warp per (lane quadrant, slice)
 constexpr int EPI_WARPS = 4 * EPI_SLICES;        // 16 epilogue warps: four per SM sub-partition hide each other's latencies
 constexpr int NT = 128 + 32 * EPI_WARPS;         // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps 4-19 epilogue
@@ -73,16 +73,62 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         else if (now - t0 > 4000000000LL) __trap();
     }
 }
+// mbar_wait that adds the cycles spent waiting to `acc` when profiling is on
+__device__ __forceinline__ void mbar_wait_prof(uint32_t bar, uint32_t parity, bool on, long long& acc) {
+    if (!on) { mbar_wait(bar, parity); return; }
+    const long long t0 = clock64();
+    mbar_wait(bar, parity);
+    acc += clock64() - t0;
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
         : "memory");
 }
+// CTA-pair (cta_group::2) variants.  The leader CTA (cluster rank 0) issues the MMAs for both CTAs, so the loads of
+// the partner complete their bytes on the LEADER's barrier (address mapped into the cluster window with mapa).
+__device__ __forceinline__ uint32_t leader_addr(uint32_t local) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(0));
+    return r;
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t leader_bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(leader_bar)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// the same arrival delivered to the barrier at this offset in both CTAs of the pair
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((unsigned short)3) : "memory");
+}
+// M = 256 across the pair: rows 0-127 from the leader's query tile, 128-255 from the partner's; each CTA supplies
+// 128 of the 256 database rows; each CTA's TMEM receives the accumulators of its own 128 query rows.
+__device__ __forceinline__ void tc_mma_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
 }
 __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
     asm volatile(
@@ -123,6 +169,7 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
 }
 // kind::f16: D=f32 (bit 4), A=B=bf16 (bits 7, 10), both K-major, N>>3 at bit 17, M>>4 at bit 24
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+constexpr uint32_t IDESC_PAIR = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
 
 // ------------------------------------------------------------------------------------------------
 // operand preparation
@@ -233,7 +280,9 @@ struct MainParams {
     Top2* res0;              // [B*n_max]
     Top2* res1;              // [B*m_max]
     int B, n_max, m_max, cs0, cs1, KB, tiles0, tiles1, n_dirs, n_slots;
+    int cl;                  // CTAs per cluster (1 or 2): a pair works on two adjacent query tiles and shares the database stream
     int align_slack;         // bytes the kernel may spend on aligning its tiles to 1024
+    long long* prof;         // timing experiments only (KB_TC_DEBUG & 4): per CTA 8 cycle counters, see scripts/tc_pipeline_profile.py
     int dbg;                 // timing experiments only (KB_TC_DEBUG): 1 = epilogue skips the fold, 2 = no MMAs issued
 };
 
@@ -241,22 +290,28 @@ struct Item {
     int dir, b, q_row0, n_q, n_db, q_base, db_base;
 };
 
-__device__ __forceinline__ bool decode_item(const MainParams& p, int item, Item& it) {
-    const int per_dir0 = p.B * p.tiles0;
+// Work items are (direction, batch entry, group of p.cl adjacent query tiles); CTA `crank` of the cluster takes tile
+// group * cl + crank.  The return value is uniform over the cluster: a CTA whose own tile lies beyond the query count
+// still runs the item (its rows are never stored) because its partner needs its half of every database block.
+template <int CL>
+__device__ __forceinline__ bool decode_item(const MainParams& p, int item, int crank, Item& it) {
+    const int t0 = (p.tiles0 + CL - 1) / CL, t1 = (p.tiles1 + CL - 1) / CL;
+    const int per_dir0 = p.B * t0;
     int dir = 0, rem = item;
     if (item >= per_dir0) { dir = 1; rem = item - per_dir0; }
-    const int tiles = dir ? p.tiles1 : p.tiles0;
-    const int b = rem / tiles, tile = rem - b * tiles;
+    const int tiles = dir ? t1 : t0;
+    const int b = rem / tiles, group = rem - b * tiles;
     const int n = p.n0 ? p.n0[b] : p.n_max, m = p.n1 ? p.n1[b] : p.m_max;
     it.dir = dir; it.b = b;
-    it.q_row0 = tile * BM;
+    it.q_row0 = (group * CL + crank) * BM;
     it.n_q = dir ? m : n;
     it.n_db = dir ? n : m;
     it.q_base = dir ? b * p.m_max : b * p.n_max;
     it.db_base = dir ? b * p.n_max : b * p.m_max;
-    return it.q_row0 < it.n_q && it.n_db > 0;
+    return group * CL * BM < it.n_q && it.n_db > 0;
 }
 
+template <int CL>
 __global__ void __launch_bounds__(NT, 1) nn_top2_kernel(const __grid_constant__ CUtensorMap map0,
                                                         const __grid_constant__ CUtensorMap map1, MainParams p) {
     extern __shared__ __align__(1024) unsigned char smem_dyn[];
@@ -266,7 +321,9 @@ __global__ void __launch_bounds__(NT, 1) nn_top2_kernel(const __grid_constant__ 
     const uint32_t a_tiles = base;                                  // 2*KB tiles: hi blocks then lo blocks
     const uint32_t b_slots = base + (uint32_t)(2 * KB) * TILE_BYTES;
     const int NSLOT = p.n_slots;
-    const uint32_t bars = b_slots + NSLOT * SLOT_BYTES;
+    // CTA pair: every CTA keeps only ITS 128 of the 256 database rows of a block, so a slot is one 16 KB box
+    constexpr uint32_t SLOTB = CL == 2 ? TILE_BYTES : SLOT_BYTES;
+    const uint32_t bars = b_slots + NSLOT * SLOTB;
     if (base - raw > (uint32_t)p.align_slack) __trap();             // the host sized the allocation for this slack
     // barrier map (8 bytes each)
     // one (full, free) barrier pair per 64-wide K block of the query tile, so that the next item's query
@@ -275,28 +332,39 @@ __global__ void __launch_bounds__(NT, 1) nn_top2_kernel(const __grid_constant__ 
     const uint32_t bar_b_full = bars + 64, bar_b_empty = bars + 64 + 8 * MAX_SLOTS;
     const uint32_t bar_t_full = bars + 64 + 16 * MAX_SLOTS, bar_t_empty = bar_t_full + 16;
     const uint32_t tmem_slot = bar_t_empty + 16;
-    float* cbuf = reinterpret_cast<float*>(smem_dyn + (tmem_slot + 16 - raw));     // [2][BN]
+    float* cbuf = reinterpret_cast<float*>(smem_dyn + (tmem_slot + 16 - raw));     // [2][BN], see the epilogue
     volatile uint32_t* tmem_slot_ptr =
         reinterpret_cast<volatile uint32_t*>(smem_dyn + (tmem_slot - raw));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
     if (threadIdx.x == 0) {
         for (int kb = 0; kb < 4; ++kb) { mbar_init(bar_a_full + 8 * kb, 1); mbar_init(bar_a_free + 8 * kb, 1); }
         for (int s = 0; s < NSLOT; ++s) { mbar_init(bar_b_full + 8 * s, 1); mbar_init(bar_b_empty + 8 * s, 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(bar_t_full + 8 * s, 1); mbar_init(bar_t_empty + 8 * s, EPI_WARPS); }
+        // the leader's accumulator-empty barrier collects the epilogue warps of both CTAs of a pair
+        for (int s = 0; s < 2; ++s) { mbar_init(bar_t_full + 8 * s, 1); mbar_init(bar_t_empty + 8 * s, CL * EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (CL == 2) {                    // one warp of each CTA of the pair
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();                 // the partner's barriers exist before anything is signalled on them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
-    const int n_items = p.n_dirs == 2 ? p.B * (p.tiles0 + p.tiles1) : p.B * p.tiles0;
+    const int g0 = (p.tiles0 + CL - 1) / CL, g1 = (p.tiles1 + CL - 1) / CL;
+    const int n_items = p.n_dirs == 2 ? p.B * (g0 + g1) : p.B * g0;
+    const int item0 = blockIdx.x / CL, item_step = gridDim.x / CL;
 
     // The producer and the MMA issuer run their loops with the WHOLE warp (uniform control flow keeps
     // addresses, descriptors and phases in uniform registers); only the issuing instructions themselves
@@ -305,19 +373,30 @@ __global__ void __launch_bounds__(NT, 1) nn_top2_kernel(const __grid_constant__ 
     if (warp == 0) {
         // ================================ TMA producer ==========================================
         const bool issuer = lane == 0;
+        const bool prof = (p.dbg & 4) != 0;
+        long long w_afree = 0, w_bempty = 0;
+        const long long t_start = clock64();
         uint32_t a_phase = 0, slot = 0, b_phase = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        for (int item = item0; item < n_items; item += item_step) {
             Item it;
-            if (!decode_item(p, item, it)) continue;
+            if (!decode_item<CL>(p, item, crank, it)) continue;
             const CUtensorMap* qmap = it.dir ? &map1 : &map0;
             const CUtensorMap* dmap = it.dir ? &map0 : &map1;
             for (int kb = 0; kb < KB; ++kb) {
-                mbar_wait(bar_a_free + 8 * kb, a_phase ^ 1);        // the previous item is done with this K block
+                mbar_wait_prof(bar_a_free + 8 * kb, a_phase ^ 1, prof, w_afree);   // the previous item is done with this K block
                 if (issuer) {
-                    mbar_expect_tx(bar_a_full + 8 * kb, 2 * TILE_BYTES);
-                    tma_load_2d(a_tiles + kb * TILE_BYTES, qmap, kb * BK, it.q_base + it.q_row0, bar_a_full + 8 * kb);
-                    tma_load_2d(a_tiles + (KB + kb) * TILE_BYTES, qmap, (KB + kb) * BK, it.q_base + it.q_row0,
-                                bar_a_full + 8 * kb);
+                    if constexpr (CL == 2) {
+                        // both CTAs' query tiles are operands of the leader's MMAs: all four boxes land on its barrier
+                        const uint32_t lb = leader_addr(bar_a_full + 8 * kb);
+                        if (crank == 0) mbar_expect_tx(bar_a_full + 8 * kb, 4 * TILE_BYTES);
+                        tma_load_2d_pair(a_tiles + kb * TILE_BYTES, qmap, kb * BK, it.q_base + it.q_row0, lb);
+                        tma_load_2d_pair(a_tiles + (KB + kb) * TILE_BYTES, qmap, (KB + kb) * BK, it.q_base + it.q_row0, lb);
+                    } else {
+                        mbar_expect_tx(bar_a_full + 8 * kb, 2 * TILE_BYTES);
+                        tma_load_2d(a_tiles + kb * TILE_BYTES, qmap, kb * BK, it.q_base + it.q_row0, bar_a_full + 8 * kb);
+                        tma_load_2d(a_tiles + (KB + kb) * TILE_BYTES, qmap, (KB + kb) * BK, it.q_base + it.q_row0,
+                                    bar_a_full + 8 * kb);
+                    }
                 }
             }
             a_phase ^= 1;
@@ -327,13 +406,20 @@ __global__ void __launch_bounds__(NT, 1) nn_top2_kernel(const __grid_constant__ 
                 for (int kb = 0; kb < KB; ++kb) {
 #pragma unroll
                     for (int part = 0; part < 2; ++part) {          // hi block then lo block
-                        mbar_wait(bar_b_empty + 8 * slot, b_phase ^ 1);
+                        mbar_wait_prof(bar_b_empty + 8 * slot, b_phase ^ 1, prof, w_bempty);
                         if (issuer) {
-                            mbar_expect_tx(bar_b_full + 8 * slot, SLOT_BYTES);
-                            tma_load_2d(b_slots + slot * SLOT_BYTES, dmap, (part * KB + kb) * BK, row,
-                                        bar_b_full + 8 * slot);
-                            tma_load_2d(b_slots + slot * SLOT_BYTES + TILE_BYTES, dmap, (part * KB + kb) * BK, row + BM,
-                                        bar_b_full + 8 * slot);
+                            if constexpr (CL == 2) {
+                                // this CTA fetches its 128-row half of the block; both halves complete on the leader
+                                if (crank == 0) mbar_expect_tx(bar_b_full + 8 * slot, 2 * TILE_BYTES);
+                                tma_load_2d_pair(b_slots + slot * SLOTB, dmap, (part * KB + kb) * BK, row + crank * BM,
+                                                 leader_addr(bar_b_full + 8 * slot));
+                            } else {
+                                mbar_expect_tx(bar_b_full + 8 * slot, SLOT_BYTES);
+                                tma_load_2d(b_slots + slot * SLOT_BYTES, dmap, (part * KB + kb) * BK, row,
+                                            bar_b_full + 8 * slot);
+                                tma_load_2d(b_slots + slot * SLOT_BYTES + TILE_BYTES, dmap, (part * KB + kb) * BK, row + BM,
+                                            bar_b_full + 8 * slot);
+                            }
                         }
                         if (++slot == (uint32_t)NSLOT) { slot = 0; b_phase ^= 1; }
                     }
@@ -341,66 +427,84 @@ __global__ void __launch_bounds__(NT, 1) nn_top2_kernel(const __grid_constant__ 
             }
             __syncwarp();
         }
-    } else if (warp == 1) {
-        // ================================ MMA issuer ============================================
+        if (prof && issuer) {
+            long long* o = p.prof + (size_t)blockIdx.x * 8;
+            o[0] = clock64() - t_start; o[1] = w_afree; o[2] = w_bempty;
+        }
+    } else if (warp == 1 && crank == 0) {
+        // ================================ MMA issuer (the leader CTA of a pair issues for both) ==
         const bool issuer = lane == 0;
+        constexpr uint32_t ID = CL == 2 ? IDESC_PAIR : IDESC;
+        auto mma = [](uint32_t d, uint64_t a, uint64_t b, uint32_t acc) {
+            if constexpr (CL == 2) tc_mma_pair(d, a, b, ID, acc); else tc_mma(d, a, b, ID, acc);
+        };
+        auto commit = [](uint32_t bar) {
+            if constexpr (CL == 2) tc_commit_pair(bar); else tc_commit(bar);
+        };
+        const bool prof = (p.dbg & 4) != 0;
+        long long w_tempty = 0, w_afull = 0, w_bfull = 0;
+        const long long t_start = clock64();
         uint32_t a_phase = 0, slot = 0, b_phase = 0, acc_buf = 0, t_phase = 0;      // t_phase: one bit per buffer
         const uint64_t desc0 = umma_desc(0);                        // everything but the start address
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        for (int item = item0; item < n_items; item += item_step) {
             Item it;
-            if (!decode_item(p, item, it)) continue;
+            if (!decode_item<CL>(p, item, crank, it)) continue;
             const int n_ct = (it.n_db + BN - 1) / BN;
             for (int ct = 0; ct < n_ct; ++ct) {
-                mbar_wait(bar_t_empty + 8 * acc_buf, ((t_phase >> acc_buf) & 1u) ^ 1u);   // epilogue drained this buffer
+                mbar_wait_prof(bar_t_empty + 8 * acc_buf, ((t_phase >> acc_buf) & 1u) ^ 1u, prof, w_tempty);   // epilogue drained this buffer
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc_buf * BN;
                 for (int kb = 0; kb < KB; ++kb) {
                     if (ct == 0) {                                  // this item's query block has landed
-                        mbar_wait(bar_a_full + 8 * kb, a_phase);
+                        mbar_wait_prof(bar_a_full + 8 * kb, a_phase, prof, w_afull);
                         tc_fence_after();
                     }
                     const uint64_t a_hi = desc0 | (uint64_t)((a_tiles + kb * TILE_BYTES) >> 4);
                     const uint64_t a_lo = desc0 | (uint64_t)((a_tiles + (KB + kb) * TILE_BYTES) >> 4);
                     // ---- database hi block: hi.hi and lo.hi
-                    mbar_wait(bar_b_full + 8 * slot, b_phase);
+                    mbar_wait_prof(bar_b_full + 8 * slot, b_phase, prof, w_bfull);
                     tc_fence_after();
-                    uint64_t bt = desc0 | (uint64_t)((b_slots + slot * SLOT_BYTES) >> 4);
+                    uint64_t bt = desc0 | (uint64_t)((b_slots + slot * SLOTB) >> 4);
                     if (issuer && !(p.dbg & 2)) {
-                        tc_mma(d_tmem, a_hi, bt, IDESC, kb > 0 ? 1u : 0u);        // 32 bytes (16 bf16) per K step: +2
-                        tc_mma(d_tmem, a_hi + 2, bt + 2, IDESC, 1u);
-                        tc_mma(d_tmem, a_hi + 4, bt + 4, IDESC, 1u);
-                        tc_mma(d_tmem, a_hi + 6, bt + 6, IDESC, 1u);
-                        tc_mma(d_tmem, a_lo, bt, IDESC, 1u);
-                        tc_mma(d_tmem, a_lo + 2, bt + 2, IDESC, 1u);
-                        tc_mma(d_tmem, a_lo + 4, bt + 4, IDESC, 1u);
-                        tc_mma(d_tmem, a_lo + 6, bt + 6, IDESC, 1u);
+                        mma(d_tmem, a_hi, bt, kb > 0 ? 1u : 0u);                  // 32 bytes (16 bf16) per K step: +2
+                        mma(d_tmem, a_hi + 2, bt + 2, 1u);
+                        mma(d_tmem, a_hi + 4, bt + 4, 1u);
+                        mma(d_tmem, a_hi + 6, bt + 6, 1u);
+                        mma(d_tmem, a_lo, bt, 1u);
+                        mma(d_tmem, a_lo + 2, bt + 2, 1u);
+                        mma(d_tmem, a_lo + 4, bt + 4, 1u);
+                        mma(d_tmem, a_lo + 6, bt + 6, 1u);
                     }
-                    if (issuer) tc_commit(bar_b_empty + 8 * slot);
+                    if (issuer) commit(bar_b_empty + 8 * slot);
                     __syncwarp();
                     if (++slot == (uint32_t)NSLOT) { slot = 0; b_phase ^= 1; }
                     // ---- database lo block: hi.lo
-                    mbar_wait(bar_b_full + 8 * slot, b_phase);
+                    mbar_wait_prof(bar_b_full + 8 * slot, b_phase, prof, w_bfull);
                     tc_fence_after();
-                    bt = desc0 | (uint64_t)((b_slots + slot * SLOT_BYTES) >> 4);
+                    bt = desc0 | (uint64_t)((b_slots + slot * SLOTB) >> 4);
                     if (issuer && !(p.dbg & 2)) {
-                        tc_mma(d_tmem, a_hi, bt, IDESC, 1u);
-                        tc_mma(d_tmem, a_hi + 2, bt + 2, IDESC, 1u);
-                        tc_mma(d_tmem, a_hi + 4, bt + 4, IDESC, 1u);
-                        tc_mma(d_tmem, a_hi + 6, bt + 6, IDESC, 1u);
+                        mma(d_tmem, a_hi, bt, 1u);
+                        mma(d_tmem, a_hi + 2, bt + 2, 1u);
+                        mma(d_tmem, a_hi + 4, bt + 4, 1u);
+                        mma(d_tmem, a_hi + 6, bt + 6, 1u);
                     }
                     if (issuer) {
-                        tc_commit(bar_b_empty + 8 * slot);
-                        if (ct == n_ct - 1) tc_commit(bar_a_free + 8 * kb);      // query block kb may be overwritten
+                        commit(bar_b_empty + 8 * slot);
+                        if (ct == n_ct - 1) commit(bar_a_free + 8 * kb);         // query block kb may be overwritten
                     }
                     __syncwarp();
                     if (++slot == (uint32_t)NSLOT) { slot = 0; b_phase ^= 1; }
                 }
-                if (issuer) tc_commit(bar_t_full + 8 * acc_buf);    // accumulator ready for the epilogue
+                if (issuer) commit(bar_t_full + 8 * acc_buf);       // accumulator ready for the epilogue
                 __syncwarp();
                 t_phase ^= 1u << acc_buf;
                 acc_buf ^= 1;
             }
             a_phase ^= 1;
+        }
+        if (prof && issuer) {
+            long long* o = p.prof + (size_t)blockIdx.x * 8;
+            o[3] = clock64() - t_start; o[4] = w_tempty; o[5] = w_afull; o[6] = w_bfull;
         }
     } else if (warp >= 4) {
         // ================================ epilogue ==============================================
@@ -411,10 +515,27 @@ __global__ void __launch_bounds__(NT, 1) nn_top2_kernel(const __grid_constant__ 
         const int cidx = ew * 32 + lane;                            // c entry this thread stages (first 8 warps)
         constexpr int SW = BN / EPI_SLICES;                         // 64 columns per warp and tile
         uint32_t acc_buf = 0, t_phase = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const bool prof = (p.dbg & 4) != 0;
+        long long w_tfull = 0;
+        // -|y|^2/2 of a column tile is staged in one half of a 2 x 256-float shared buffer: the values of the NEXT
+        // tile (of this item or of the next one) are fetched while the current tile is folded and published with one
+        // named barrier per tile, so neither the load latency nor a second barrier sits on the per-tile path.
+        auto c_of = [&](const Item& q) { return (q.dir ? p.c0 : p.c1) + (size_t)q.b * (q.dir ? p.cs0 : p.cs1); };
+        auto next_valid = [&](int from, Item& q) {
+            for (int k = from; k < n_items; k += item_step)
+                if (decode_item<CL>(p, k, crank, q)) return true;
+            return false;
+        };
+        int cpar = 0;
+        {
+            Item first;
+            if (next_valid(item0, first) && cidx < BN) cbuf[cidx] = __ldg(c_of(first) + cidx);
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+        }
+        for (int item = item0; item < n_items; item += item_step) {
             Item it;
-            if (!decode_item(p, item, it)) continue;
-            const float* cvec = (it.dir ? p.c0 : p.c1) + (size_t)it.b * (it.dir ? p.cs0 : p.cs1);
+            if (!decode_item<CL>(p, item, crank, it)) continue;
+            const float* cvec = c_of(it);
             // running top-3 scores and top-2 indices of this row over this warp's column slice; the slices
             // are merged by the resolver.  (Which of two exactly tied scores ranks first is irrelevant
             // here: near-ties are settled exactly in the resolver.)
@@ -424,9 +545,9 @@ __global__ void __launch_bounds__(NT, 1) nn_top2_kernel(const __grid_constant__ 
             // TMEM -> register bandwidth (~56 B/clk/SM measured) is what bounds this epilogue, so every warp
             // keeps a tcgen05.ld in flight while it folds the previous 16 columns (two 16-register buffers;
             // the first chunk of the next tile is requested before the last chunk of this one is folded).
-            // -|y|^2/2 of a tile is staged through a 256-float shared buffer between two named barriers.
             auto fold = [&](const uint32_t (&v)[16], int ct, int col0) {
-                const float4* c4 = reinterpret_cast<const float4*>(cbuf + col0);
+                if (p.dbg & 1) { b1 = fmaxf(b1, __uint_as_float(v[0] ^ v[7] ^ v[15])); return; }   // timing experiment: no fold
+                const float4* c4 = reinterpret_cast<const float4*>(cbuf + cpar * BN + col0);
                 const int j0 = ct * BN + col0;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -453,47 +574,55 @@ __global__ void __launch_bounds__(NT, 1) nn_top2_kernel(const __grid_constant__ 
                     }
                 }
             };
-            auto stage_c = [&](int ct) {                                // all 16 warps call this
-                const float cv = cidx < BN ? __ldg(cvec + ct * BN + cidx) : 0.0f;
-                asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");   // everyone is done with the old values
-                if (cidx < BN) cbuf[cidx] = cv;
-                asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
-            };
             const int col_base = slice * SW;
-            uint32_t ra[16], rb[16];
+            uint32_t ra[16] = {}, rb[16] = {};
+            const bool noload = (p.dbg & 8) != 0;      // timing experiment: the epilogue leaves TMEM alone
             // prologue: first tile
-            mbar_wait(bar_t_full + 8 * acc_buf, (t_phase >> acc_buf) & 1u);
+            mbar_wait_prof(bar_t_full + 8 * acc_buf, (t_phase >> acc_buf) & 1u, prof, w_tfull);
             t_phase ^= 1u << acc_buf;
             tc_fence_after();
             uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc_buf * BN + col_base;
-            tmem_ld16(taddr, ra);
-            stage_c(0);
+            if (!noload) tmem_ld16(taddr, ra);
             tmem_ld_wait();
             for (int ct = 0; ct < n_ct; ++ct) {
-                tmem_ld16(taddr + 16, rb);
+                // the tile after this one (uniform over the 16 warps): its c values travel while this tile is folded
+                const float* nc = nullptr;
+                if (ct + 1 < n_ct) nc = cvec + (ct + 1) * BN;
+                else { Item nx; if (next_valid(item + item_step, nx)) nc = c_of(nx); }
+                const float cvn = (nc != nullptr && cidx < BN) ? __ldg(nc + cidx) : 0.0f;
+                if (!noload) tmem_ld16(taddr + 16, rb);
                 fold(ra, ct, col_base);
                 tmem_ld_wait();
-                tmem_ld16(taddr + 32, ra);
+                if (!noload) tmem_ld16(taddr + 32, ra);
                 fold(rb, ct, col_base + 16);
                 tmem_ld_wait();
-                tmem_ld16(taddr + 48, rb);
+                if (!noload) tmem_ld16(taddr + 48, rb);
                 fold(ra, ct, col_base + 32);
                 tmem_ld_wait();
                 // the slice has left TMEM: hand the accumulator back to the MMA issuer
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_t_empty + 8 * acc_buf);
+                if (lane == 0) {
+                    if constexpr (CL == 2) mbar_arrive_cluster(leader_addr(bar_t_empty + 8 * acc_buf));
+                    else mbar_arrive(bar_t_empty + 8 * acc_buf);
+                }
                 acc_buf ^= 1;
                 fold(rb, ct, col_base + 48);
-                if (ct + 1 < n_ct) {
-                    mbar_wait(bar_t_full + 8 * acc_buf, (t_phase >> acc_buf) & 1u);
+                const bool more = ct + 1 < n_ct;
+                if (more) {
+                    mbar_wait_prof(bar_t_full + 8 * acc_buf, (t_phase >> acc_buf) & 1u, prof, w_tfull);
                     t_phase ^= 1u << acc_buf;
                     tc_fence_after();
                     taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc_buf * BN + col_base;
-                    tmem_ld16(taddr, ra);
-                    stage_c(ct + 1);
-                    tmem_ld_wait();
+                    if (!noload) tmem_ld16(taddr, ra);
                 }
+                if (nc != nullptr) {
+                    // every warp has passed the previous barrier, i.e. finished reading the other half one tile ago
+                    if (cidx < BN) cbuf[(cpar ^ 1) * BN + cidx] = cvn;
+                    asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+                    cpar ^= 1;
+                }
+                if (more) tmem_ld_wait();
             }
             const int qi = it.q_row0 + row_in_tile;
             if (qi < it.n_q) {
@@ -503,12 +632,17 @@ __global__ void __launch_bounds__(NT, 1) nn_top2_kernel(const __grid_constant__ 
                 (it.dir ? p.res1 : p.res0)[((size_t)it.q_base + qi) * EPI_SLICES + slice] = o;
             }
         }
+        if (prof && ew == 0 && lane == 0) p.prof[(size_t)blockIdx.x * 8 + 7] = w_tfull;
     }
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();                 // no CTA leaves while its partner can still write to it
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        if constexpr (CL == 2)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
 }
 
@@ -958,6 +1092,7 @@ static TcLayout tc_layout(int B, int n_max, int m_max, int D) {
     add((size_t)B * (n_max + m_max) * 8 * 16);  // rescan partial minima
     add((size_t)B * (n_max + m_max) * 4);       // rescan tickets
     add((size_t)B * n_max * 4);                 // tensor-core score of the direction-0 winners
+    add(8 * 512 * 8);                           // pipeline wait counters (KB_TC_DEBUG & 4)
     L.bytes = n + 1024;
     return L;
 }
@@ -975,6 +1110,7 @@ struct TcBuffers {
     void* parts;
     int* tickets;
     float* tsel;
+    long long* prof;
     bool ok;
 };
 
@@ -1000,6 +1136,7 @@ static TcBuffers tc_carve(void* ws, size_t ws_bytes, int B, int n_max, int m_max
     t.parts = arena.take<char>((size_t)B * (n_max + m_max) * 8 * 16);
     t.tickets = arena.take<int>((size_t)B * (n_max + m_max));
     t.tsel = arena.take<float>((size_t)B * n_max);
+    t.prof = arena.take<long long>(8 * 512);
     t.ok = arena.ok();
     return t;
 }
@@ -1012,7 +1149,7 @@ extern "C" KB_API int kb_match_tc_debug_offsets(int B, int n_max, int m_max, int
     char* base = (char*)4096;                       // any non-null, 256-aligned base
     TcBuffers t = tc_carve(base, (size_t)-1, B, n_max, m_max, L);
     off[0] = (char*)t.res0 - base; off[1] = (char*)t.res1 - base; off[2] = (char*)t.n_exact - base;
-    off[3] = (char*)t.norm2_0 - base; off[4] = (char*)t.norm2_1 - base;
+    off[3] = (char*)t.norm2_0 - base; off[4] = (char*)t.norm2_1 - base; off[5] = (char*)t.prof - base;
     return KB_OK;
 }
 
@@ -1076,25 +1213,48 @@ int kb_match_tc_run(const float* d0, const float* d1, const int* n0, const int* 
     mp.n0 = n0; mp.n1 = n1; mp.c0 = c0; mp.c1 = c1; mp.res0 = res0; mp.res1 = res1;
     mp.B = B; mp.n_max = n_max; mp.m_max = m_max; mp.cs0 = L.cs0; mp.cs1 = L.cs1; mp.KB = L.KB;
     mp.tiles0 = L.tiles0; mp.tiles1 = L.tiles1; mp.n_dirs = cross_check ? 2 : 1;
-    // after the tiles: barriers (256 bytes) and the 256-float c buffer; the tiles must start on a
+    // after the tiles: barriers (256 bytes) and the 2 x 256-float c buffer; the tiles must start on a
     // 1024-byte boundary (128B swizzle) -- dynamic shared memory normally does, `slack` covers the rest
-    const size_t fixed = 256 + BN * 4;
+    const size_t fixed = 256 + 2 * BN * 4;
     const size_t budget = 227 * 1024;
-    int n_slots = (int)((budget - fixed - (size_t)2 * L.KB * TILE_BYTES) / SLOT_BYTES);
+    // CTA pairs (KB_TC_CLUSTER=2: thread-block clusters of 2, tcgen05 cta_group::2 MMAs with M = 256): the pair
+    // multiplies two adjacent query tiles against one database stream of which every CTA holds half, so the operand
+    // bytes per CTA halve and the ring is twice as deep.  Measured on B200 it is neither faster nor slower than the
+    // 1-CTA kernel (172 vs 170-178 us on cfg2): the kernel's time goes to the tensor pipe sharing TMEM with the
+    // epilogue's tcgen05.ld and to the epilogue itself, not to operand delivery (scripts/tc_pipeline_profile.py), so
+    // the 1-CTA kernel stays the default and the pair kernel is kept selectable and tested.
+    int cl = 1;
+    { const char* e = getenv("KB_TC_CLUSTER"); if (e && atoi(e) == 2 && (L.tiles0 > 1 || L.tiles1 > 1)) cl = 2; }
+    mp.cl = cl;
+    const size_t slot_bytes = cl == 2 ? TILE_BYTES : SLOT_BYTES;
+    int n_slots = (int)((budget - fixed - (size_t)2 * L.KB * TILE_BYTES) / slot_bytes);
     if (n_slots > MAX_SLOTS) n_slots = MAX_SLOTS;
     if (n_slots < 2) return KB_ERR_UNSUPPORTED;
-    const size_t used = (size_t)2 * L.KB * TILE_BYTES + (size_t)n_slots * SLOT_BYTES + fixed;
+    const size_t used = (size_t)2 * L.KB * TILE_BYTES + (size_t)n_slots * slot_bytes + fixed;
     size_t slack = budget - used;
     if (slack > 1024) slack = 1024;
     mp.n_slots = n_slots;
     mp.align_slack = (int)slack;
     const size_t smem = used + slack;
     { const char* e = getenv("KB_TC_DEBUG"); mp.dbg = e ? atoi(e) : 0; }
-    KB_CUDA_TRY(cudaFuncSetAttribute(nn_top2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int n_items = mp.n_dirs == 2 ? B * (L.tiles0 + L.tiles1) : B * L.tiles0;
-    const int grid = n_items < sms ? n_items : sms;
-    if (phases & 2) {
-        nn_top2_kernel<<<grid, NT, smem, st>>>(map0, map1, mp);
+    mp.prof = tb.prof;
+    KB_CUDA_TRY(cudaFuncSetAttribute(nn_top2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    KB_CUDA_TRY(cudaFuncSetAttribute(nn_top2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int g0 = (L.tiles0 + cl - 1) / cl, g1 = (L.tiles1 + cl - 1) / cl;
+    const int n_items = mp.n_dirs == 2 ? B * (g0 + g1) : B * g0;
+    const int max_groups = sms / cl;
+    const int grid = (n_items < max_groups ? n_items : max_groups) * cl;
+    if ((phases & 2) && cl == 1) {
+        nn_top2_kernel<1><<<grid, NT, smem, st>>>(map0, map1, mp);
+        KB_LAUNCH_CHECK();
+    } else if (phases & 2) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = cl; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr; cfg.numAttrs = 1;
+        KB_CUDA_TRY(cudaLaunchKernelEx(&cfg, nn_top2_kernel<2>, map0, map1, mp));
         KB_LAUNCH_CHECK();
     }
     if (!(phases & 4)) return KB_OK;

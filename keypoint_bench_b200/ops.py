@@ -276,7 +276,7 @@ def match_batched(d0: torch.Tensor, d1: torch.Tensor, n0: torch.Tensor | None = 
 def match_tc_debug(ws: torch.Tensor, b: int, n: int, m: int, dd: int) -> dict:
     """Views into an algo=1 workspace (tests only): per-row top-2 records, exact-rescan count, norms."""
     import ctypes
-    off = (ctypes.c_size_t * 5)()
+    off = (ctypes.c_size_t * 6)()
     check(lib.kb_match_tc_debug_offsets(b, n, m, dd, ctypes.cast(off, ctypes.c_void_p)), 'kb_match_tc_debug_offsets')
     def rec(o, rows, slices=4):
         # per row: `slices` records of 32 bytes (float best, second, third, pad; int argbest, argsecond, pad, pad),

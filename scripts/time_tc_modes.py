@@ -9,7 +9,7 @@ for B, n, m, D in shapes:
     a = torch.nn.functional.normalize(torch.randn(B, n, D, generator=g), dim=2).cuda()
     b = torch.nn.functional.normalize(torch.randn(B, m, D, generator=g), dim=2).cuda()
     b[:, :n // 2] = a[:, :n // 2] + 0.05 * torch.randn(B, n // 2, D, generator=g).cuda()
-    for mode in (0, 2):
+    for mode in (0, 1, 2):
         os.environ['KB_TC_DEBUG'] = str(mode)
         for _ in range(2):
             ops.match_batched(a, b, None, None, 5.0, True, algo=1)

@@ -228,6 +228,37 @@ def test_matcher_without_distances_gives_same_pairs(algo, dim, scale):
                                          b[0].numpy(), maxd, cc)
 
 
+def test_matcher_cta_pair_kernel_gives_same_pairs(monkeypatch):
+    """KB_TC_CLUSTER=2 selects the cta_group::2 variant of the tensor-core search (clusters of two CTAs, M = 256
+    MMAs issued by the leader, TMA loads completing on the leader's barriers): same pairs, same top-3 records."""
+    gen = torch.Generator().manual_seed(77)
+    cases = [(3, 1000, 1000, 256), (2, 700, 1300, 64), (1, 129, 300, 128), (2, 2048, 2048, 128)]
+    for b, n, m, dim in cases:
+        a = torch.nn.functional.normalize(torch.randn(b, n, dim, generator=gen), dim=2)
+        d = torch.nn.functional.normalize(torch.randn(b, m, dim, generator=gen), dim=2)
+        k = min(n, m) // 2
+        d[:, :k] = a[:, :k] + 0.05 * torch.randn(b, k, dim, generator=gen)
+        n0 = torch.tensor([n - 37 * i for i in range(b)], dtype=torch.int32)
+        n1 = torch.tensor([m - 91 * i for i in range(b)], dtype=torch.int32)
+        out = {}
+        for mode in ('1', '2'):
+            monkeypatch.setenv('KB_TC_CLUSTER', mode)
+            p, _, c, ws = ops().match_batched(a.to(DEV), d.to(DEV), n0.to(DEV), n1.to(DEV), 0.9, True, algo=1,
+                                              return_ws=True)
+            best = ops().match_tc_debug(ws, b, n, m, dim)['res0'][0][:int(n0[0])]
+            out[mode] = (p.clone(), c.clone(), best.clone())
+        monkeypatch.delenv('KB_TC_CLUSTER')
+        assert torch.equal(out['1'][1], out['2'][1]), (b, n, m, dim)
+        assert torch.allclose(out['1'][2], out['2'][2], rtol=1e-6, atol=1e-6)        # the per-row best scores themselves
+        for i in range(b):
+            kk = int(out['1'][1][i])
+            assert torch.equal(out['1'][0][i, :kk], out['2'][0][i, :kk]), (b, n, m, dim, i)
+        want = ref_ops.match_descriptors(a[0, :n0[0]].numpy(), d[0, :n1[0]].numpy(), max_distance=0.9, cross_check=True)
+        _exact_pairs_or_near_tie(out['2'][0][0, :int(out['2'][1][0])].cpu().numpy().astype(np.int64), a[0, :n0[0]].numpy(),
+                                 d[0, :n1[0]].numpy(), 0.9, True)
+        assert want.shape[0] > 0
+
+
 @pytest.mark.parametrize('algo', [0, 1])
 def test_matcher_ragged_batch_and_ties(algo):
     gen = torch.Generator().manual_seed(11)
