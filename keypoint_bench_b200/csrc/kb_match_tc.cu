@@ -333,6 +333,9 @@ __global__ void __launch_bounds__(NT, 1) nn_top2_kernel(const __grid_constant__ 
     const uint32_t bar_t_full = bars + 64 + 16 * MAX_SLOTS, bar_t_empty = bar_t_full + 16;
     const uint32_t tmem_slot = bar_t_empty + 16;
     float* cbuf = reinterpret_cast<float*>(smem_dyn + (tmem_slot + 16 - raw));     // [2][BN], see the epilogue
+    // thr[row]: a lower bound on the row's third-best score over ALL column slices (the largest third-best any
+    // slice has reported so far), shared by the four epilogue warps that own the row -- see the epilogue
+    volatile float* thr = cbuf + 2 * BN;
     volatile uint32_t* tmem_slot_ptr =
         reinterpret_cast<volatile uint32_t*>(smem_dyn + (tmem_slot - raw));
 
@@ -542,6 +545,15 @@ __global__ void __launch_bounds__(NT, 1) nn_top2_kernel(const __grid_constant__ 
             float b1 = -CUDART_INF_F, b2 = -CUDART_INF_F, b3 = -CUDART_INF_F;
             int i1 = 0, i2 = 0;
             const int n_ct = (it.n_db + BN - 1) / BN;
+            // Each warp sees only a quarter of the columns, so on its own its third-best -- the threshold below
+            // which columns are skipped -- rises four times more slowly than the row's.  After every tile a warp
+            // publishes its third-best if it beats the shared bound and adopts the bound before the next tile: a
+            // score below ANY slice's third-best cannot be among the row's best three, and the min/max/select
+            // sequence of an insertion (ALU pipe, half rate) is what this epilogue spends its time on.  The bound is
+            // reset by slice 0 while the others are in the item's first tile (which they fold without it); plain
+            // racing stores are fine, every value ever stored is a valid bound.
+            if (slice == 0) thr[row_in_tile] = -CUDART_INF_F;
+            float th = -CUDART_INF_F;
             // TMEM -> register bandwidth (~56 B/clk/SM measured) is what bounds this epilogue, so every warp
             // keeps a tcgen05.ld in flight while it folds the previous 16 columns (two 16-register buffers;
             // the first chunk of the next tile is requested before the last chunk of this one is folded).
@@ -590,6 +602,7 @@ __global__ void __launch_bounds__(NT, 1) nn_top2_kernel(const __grid_constant__ 
                 if (ct + 1 < n_ct) nc = cvec + (ct + 1) * BN;
                 else { Item nx; if (next_valid(item + item_step, nx)) nc = c_of(nx); }
                 const float cvn = (nc != nullptr && cidx < BN) ? __ldg(nc + cidx) : 0.0f;
+                if (ct > 0) { th = thr[row_in_tile]; b3 = fmaxf(b3, th); }
                 if (!noload) tmem_ld16(taddr + 16, rb);
                 fold(ra, ct, col_base);
                 tmem_ld_wait();
@@ -616,6 +629,7 @@ __global__ void __launch_bounds__(NT, 1) nn_top2_kernel(const __grid_constant__ 
                     taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc_buf * BN + col_base;
                     if (!noload) tmem_ld16(taddr, ra);
                 }
+                if (more && b3 > th) thr[row_in_tile] = b3;
                 if (nc != nullptr) {
                     // every warp has passed the previous barrier, i.e. finished reading the other half one tile ago
                     if (cidx < BN) cbuf[(cpar ^ 1) * BN + cidx] = cvn;
@@ -627,7 +641,7 @@ __global__ void __launch_bounds__(NT, 1) nn_top2_kernel(const __grid_constant__ 
             const int qi = it.q_row0 + row_in_tile;
             if (qi < it.n_q) {
                 Top2 o;
-                o.best = b1; o.second = b2; o.third = b3; o.pad0 = 0.0f;
+                o.best = b1; o.second = b2; o.third = fminf(b3, b2); o.pad0 = 0.0f;     // b3 may hold the adopted bound
                 o.idx = i1; o.idx2 = i2; o.pad1 = 0; o.pad2 = 0;
                 (it.dir ? p.res1 : p.res0)[((size_t)it.q_base + qi) * EPI_SLICES + slice] = o;
             }
@@ -1213,9 +1227,9 @@ int kb_match_tc_run(const float* d0, const float* d1, const int* n0, const int* 
     mp.n0 = n0; mp.n1 = n1; mp.c0 = c0; mp.c1 = c1; mp.res0 = res0; mp.res1 = res1;
     mp.B = B; mp.n_max = n_max; mp.m_max = m_max; mp.cs0 = L.cs0; mp.cs1 = L.cs1; mp.KB = L.KB;
     mp.tiles0 = L.tiles0; mp.tiles1 = L.tiles1; mp.n_dirs = cross_check ? 2 : 1;
-    // after the tiles: barriers (256 bytes) and the 2 x 256-float c buffer; the tiles must start on a
+    // after the tiles: barriers (256 bytes), the 2 x 256-float c buffer and the 128-float shared bound; the tiles must start on a
     // 1024-byte boundary (128B swizzle) -- dynamic shared memory normally does, `slack` covers the rest
-    const size_t fixed = 256 + 2 * BN * 4;
+    const size_t fixed = 256 + 2 * BN * 4 + BM * 4;
     const size_t budget = 227 * 1024;
     // CTA pairs (KB_TC_CLUSTER=2: thread-block clusters of 2, tcgen05 cta_group::2 MMAs with M = 256): the pair
     // multiplies two adjacent query tiles against one database stream of which every CTA holds half, so the operand
