@@ -6,18 +6,24 @@
 //   prep_kernel     float32 descriptors -> split-bf16 operand rows [hi(D) | lo(D)] (x = hi + lo up to
 //                   2^-18 |x|), c_j = -|y_j|^2/2, row norms.  Three bf16 MMAs (hi.hi + hi.lo + lo.hi)
 //                   reproduce x.y to ~2^-16 relative: float32-grade, at bf16 tensor throughput.
-//   nn_top2_kernel  persistent, warp-specialised: one TMA producer lane, one MMA-issuing lane
-//                   (tcgen05.mma cta_group::1 kind::f16, M=128 N=128 K=16, accumulators double-buffered
-//                   in TMEM), four epilogue warps (tcgen05.ld 32x32b.x32) that fold every 128x128 tile
-//                   into a per-row running (best, second best, argbest).  The [n,m] matrix never
-//                   leaves the SM.  The query tile's operand rows stay resident in shared memory while
-//                   the database tiles stream through a 6-slot TMA ring (128B-swizzled K-major tiles).
-//                   Both directions (rows->cols, cols->rows for the cross-check) are work items of
-//                   the same launch.
-//   resolve_kernel  one warp per query: if best-second exceeds the a-priori error bound of the split
-//                   product the argmax is certified and only its float64 distance is evaluated;
-//                   otherwise the row is rescanned exactly in float64 (first of ties, as np.argmin).
-//   pairs_kernel    mutual check, strict < max_distance gate, ordered compaction (per pair).
+//   nn_top2_kernel  persistent, warp-specialised, 640 threads: warp 0 TMA producer, warp 1 MMA issuer (both run
+//                   their loops warp-uniformly and predicate only the issue on lane 0), warp 2 TMEM allocation,
+//                   16 epilogue warps (4 TMEM lane quadrants x 4 column slices).  tcgen05.mma kind::f16,
+//                   M=128 N=256 K=16, two 256-column accumulators in TMEM (all 512 columns), so the epilogue of
+//                   one column tile overlaps the MMAs of the next.  The query tile's operand rows stay resident
+//                   in shared memory while the database blocks (256 rows x 64 k, 128B-swizzled K-major) stream
+//                   through a TMA ring sized from the free shared memory.  The epilogue folds every 128x256 tile
+//                   into per-row running (best, second, third, argbest, argsecond) with software-pipelined
+//                   tcgen05.ld.32x32b.x16; the [n,m] matrix never leaves the SM.  Both directions (rows->cols,
+//                   cols->rows for the cross-check) are work items of the same launch.  nn_top2_kernel<2> is the
+//                   CTA-pair variant (cluster of 2, cta_group::2, M=256), selectable with KB_TC_CLUSTER=2.
+//   resolve_kernel  merges the column slices; best-second above twice the a-priori error bound of the split
+//                   product certifies the argmax; best-third above it leaves two candidates that are compared
+//                   exactly in float64; anything else is queued for rescan_kernel, an exact float64 scan of the
+//                   row (first of ties, as np.argmin).
+//   gate_kernel     mutual check + strict < max_distance: decided from the certified tensor-core score when the
+//                   caller wants pairs only, float64 distance inside the error band or when distances are returned.
+//   pairs_kernel    ordered compaction (per pair).
 #include <cuda.h>
 #include <cstdlib>
 #include <cuda_bf16.h>
