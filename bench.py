@@ -283,14 +283,17 @@ def main():
     torch.cuda.synchronize()
 
     def time_stage(fn, reps=5):
-        fn()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(reps):
+        # like the pipeline (pipeline.extract_match), outputs are not zero-filled: the fill kernels of a
+        # 131 MB descriptor buffer would otherwise be charged to the sampling stage
+        with ops.no_zero_fill():
             fn()
-        e1.record()
-        torch.cuda.synchronize()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
         return e0.elapsed_time(e1) / reps
 
     stage_ms = {'detect': time_stage(lambda: ops.detect_batched(batch.score, cfg.extractor_params)),

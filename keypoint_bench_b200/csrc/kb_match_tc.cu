@@ -1125,6 +1125,7 @@ struct TcBuffers {
     int *nn0, *nn1;
     double* d2_0;
     int* n_exact;
+    size_t zero_bytes;          // from maxn0 to the end of the tickets
     int2* list;
     int* keep_j;
     void* parts;
@@ -1145,16 +1146,18 @@ static TcBuffers tc_carve(void* ws, size_t ws_bytes, int B, int n_max, int m_max
     t.norm2_1 = arena.take<float>((size_t)B * m_max);
     t.maxn0 = arena.take<unsigned int>(B);
     t.maxn1 = arena.take<unsigned int>(B);
+    // maxn0, maxn1, n_exact and the rescan tickets are zeroed per call: kept adjacent for one memset
+    t.n_exact = arena.take<int>(2);
+    t.tickets = arena.take<int>((size_t)B * (n_max + m_max));
+    t.zero_bytes = (size_t)((char*)(t.tickets + (size_t)B * (n_max + m_max)) - (char*)t.maxn0);
     t.res0 = arena.take<kbtc::Top2>((size_t)B * n_max * kbtc::EPI_SLICES);
     t.res1 = arena.take<kbtc::Top2>((size_t)B * m_max * kbtc::EPI_SLICES);
     t.nn0 = arena.take<int>((size_t)B * n_max);
     t.nn1 = arena.take<int>((size_t)B * m_max);
     t.d2_0 = arena.take<double>((size_t)B * n_max);
-    t.n_exact = arena.take<int>(2);
     t.list = arena.take<int2>((size_t)B * (n_max + m_max));
     t.keep_j = arena.take<int>((size_t)B * n_max);
     t.parts = arena.take<char>((size_t)B * (n_max + m_max) * 8 * 16);
-    t.tickets = arena.take<int>((size_t)B * (n_max + m_max));
     t.tsel = arena.take<float>((size_t)B * n_max);
     t.prof = arena.take<long long>(8 * 512);
     t.ok = arena.ok();
@@ -1195,11 +1198,18 @@ int kb_match_tc_run(const float* d0, const float* d1, const int* n0, const int* 
     int *nn0 = tb.nn0, *nn1 = tb.nn1, *n_exact = tb.n_exact;
     double* d2_0 = tb.d2_0;
 
-    if (phases & 1) {
-        KB_CUDA_TRY(cudaMemsetAsync(maxn0, 0, (size_t)B * 4, st));
-        KB_CUDA_TRY(cudaMemsetAsync(maxn1, 0, (size_t)B * 4, st));
+    if (phases == 7) {
+        KB_CUDA_TRY(cudaMemsetAsync(maxn0, 0, tb.zero_bytes, st));      // maxn0, maxn1, n_exact, tickets in one node
+    } else {
+        if (phases & 1) {
+            KB_CUDA_TRY(cudaMemsetAsync(maxn0, 0, (size_t)B * 4, st));
+            KB_CUDA_TRY(cudaMemsetAsync(maxn1, 0, (size_t)B * 4, st));
+        }
+        if (phases & 4) {
+            KB_CUDA_TRY(cudaMemsetAsync(n_exact, 0, 8, st));
+            KB_CUDA_TRY(cudaMemsetAsync(tb.tickets, 0, (size_t)B * (n_max + m_max) * 4, st));
+        }
     }
-    if (phases & 4) KB_CUDA_TRY(cudaMemsetAsync(n_exact, 0, 8, st));
     int dev = 0, sms = 0;
     KB_CUDA_TRY(cudaGetDevice(&dev));
     KB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -1285,7 +1295,6 @@ int kb_match_tc_run(const float* d0, const float* d1, const int* n0, const int* 
     rp.nn0 = nn0; rp.nn1 = nn1; rp.n_exact = n_exact; rp.n_pair = n_exact + 1;
     rp.list = tb.list; rp.list_cap = B * (n_max + m_max);
     rp.parts = (RescanPart*)tb.parts; rp.tickets = tb.tickets; rp.tsel = tb.tsel;
-    KB_CUDA_TRY(cudaMemsetAsync(tb.tickets, 0, (size_t)B * (n_max + m_max) * 4, st));
     rp.B = B; rp.n_max = n_max; rp.m_max = m_max; rp.D = D; rp.n_dirs = mp.n_dirs;
     const int qmax = n_max > m_max ? n_max : m_max;
     resolve_kernel<<<dim3((qmax + 255) / 256, B, mp.n_dirs), 256, 0, st>>>(rp);

@@ -162,8 +162,8 @@ def detect_batched(score: torch.Tensor, params: dict | None = None, phases: int 
     else:
         xyp = _out(b, top_k, 3, dtype=torch.float32, device=s.device)
         raster = _out(b, top_k, dtype=torch.int32, device=s.device)
-        count = torch.zeros(b, dtype=torch.int32, device=s.device)
-        path = torch.zeros(b, dtype=torch.int32, device=s.device)
+        count = _out(b, dtype=torch.int32, device=s.device)         # assigned for every map by the kernels
+        path = _out(b, dtype=torch.int32, device=s.device)
         ws = _ws(lib.kb_detect_workspace_bytes(b, h, w, int(nms_dist), int(top_k), float(threshold)), s.device)
         if state is not None:
             state.extend([xyp, raster, count, path, ws])
@@ -254,10 +254,10 @@ def match_batched(d0: torch.Tensor, d1: torch.Tensor, n0: torch.Tensor | None = 
     else:
         pairs = _out(b, max(n, 1), 2, dtype=torch.int32, device=a.device)
         dist = _out(b, max(n, 1), dtype=torch.float64, device=a.device) if want_dist else None
-        count = torch.zeros(b, dtype=torch.int32, device=a.device)
+        count = _out(b, dtype=torch.int32, device=a.device)         # assigned for every pair by the compaction kernel
         ws = None
     if n == 0 or m == 0:
-        return pairs[:, :n], (dist[:, :n] if dist is not None else None), count
+        return pairs[:, :n], (dist[:, :n] if dist is not None else None), torch.zeros_like(count)
     c0, c1 = _i32(n0), _i32(n1)
     if ws is None:
         ws = _ws(lib.kb_match_workspace_bytes(b, n, m, dd, int(algo)), a.device)
@@ -309,9 +309,9 @@ def warp_batched(pts: torch.Tensor, count: torch.Tensor | None, h33: torch.Tenso
     kw = _out(b, max(n, 1), 2, dtype=torch.float32, device=p.device)
     ids = _out(b, max(n, 1), dtype=torch.int32, device=p.device)
     ids_out = _out(b, max(n, 1), dtype=torch.int32, device=p.device)
-    nv = torch.zeros(b, dtype=torch.int32, device=p.device)
     if n == 0:
-        return kv[:, :0], kw[:, :0], ids[:, :0], ids_out[:, :0], nv
+        return kv[:, :0], kw[:, :0], ids[:, :0], ids_out[:, :0], torch.zeros(b, dtype=torch.int32, device=p.device)
+    nv = _out(b, dtype=torch.int32, device=p.device)                # assigned for every map by the kernel
     cnt = _i32(count)
     with torch.cuda.device(p.device):
         check(lib.kb_warp_homography(p.data_ptr(), p.shape[2], _ptr(cnt), b, n, hm.data_ptr(), whf.data_ptr(),
