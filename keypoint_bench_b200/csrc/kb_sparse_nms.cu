@@ -241,15 +241,15 @@ __global__ void __launch_bounds__(DNT) round1_kernel(SparseParams p) {
         constexpr int NK = (W * W + 31) / 32;
         // lane-constant part of the exact check: offsets of this lane's window entries and whether they come
         // earlier in raster order (bit k of `early`); entries past the window are parked on the centre
-        int woff[NK];
-        unsigned early = 0u;
+        int woff[NK];                                               // in floats, relative to the centre
+        constexpr int CENTRE = R * W + R;                            // window entries before the centre come earlier
+        constexpr int KMIX = CENTRE / 32;                            // the only k whose 32 entries straddle the centre
+        const bool mix_early = lane + 32 * KMIX < CENTRE;
 #pragma unroll
         for (int k = 0; k < NK; ++k) {
             const int idx = lane + 32 * k;
             const int dy = idx / W - R, dx = idx - (idx / W) * W - R;
-            const bool in = idx < W * W;
-            woff[k] = in ? dy * T::SP + dx : 0;
-            if (in && (dy < 0 || (dy == 0 && dx < 0))) early |= 1u << k;
+            woff[k] = idx < W * W ? dy * T::SP + dx : 0;
         }
         for (int base = 0; base < NB; base += DNT) {
             const int blk = base + threadIdx.x;
@@ -274,19 +274,25 @@ __global__ void __launch_bounds__(DNT) round1_kernel(SparseParams p) {
                 }
             }
             unsigned pend = __ballot_sync(0xffffffffu, surv);
+            const int cofs = sy * T::SP + sx;
             while (pend) {
                 const int src = __ffs(pend) - 1;
                 pend &= pend - 1;
-                const int cy = __shfl_sync(0xffffffffu, sy, src), cx = __shfl_sync(0xffffffffu, sx, src);
+                const int co = __shfl_sync(0xffffffffu, cofs, src);
                 const float cc = __shfl_sync(0xffffffffu, c, src);
+                // entries earlier in raster order must be < cc, later ones <= cc.  cc > tau >= 0, so "v >= cc" is
+                // "v > the float just below cc": one strict comparison per entry against a per-k threshold
+                const float cc_lo = __uint_as_float(__float_as_uint(cc) - 1u);
                 bool bad = false;
-                const float* centre = S + cy * T::SP + cx;
+                const float* centre = S + co;
 #pragma unroll
                 for (int k = 0; k < NK; ++k) {
                     const float v = centre[woff[k]];
-                    bad |= ((early >> k) & 1u) ? (v >= cc) : (v > cc);         // the centre itself: v > cc is false
+                    const float thr = k < KMIX ? cc_lo : (k > KMIX ? cc : (mix_early ? cc_lo : cc));
+                    bad |= v > thr;                                             // the centre itself: v > cc is false
                 }
                 if (!__any_sync(0xffffffffu, bad) && lane == 0) {
+                    const int cy = co / T::SP, cx = co - cy * T::SP;
                     const int my = cy - R, mx = cx - R;                         // region coordinates
                     atomicOr(&MB[my * T::MWW + (mx >> 5)], 1u << (mx & 31));
                 }
