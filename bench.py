@@ -44,7 +44,7 @@ def parse_args():
     ap.add_argument('--kind', default='uniform', help='synthetic score-map kind (uniform | alike)')
     ap.add_argument('--cpu-pairs', type=int, default=2, help='pairs timed on the host for cpu_baseline (0 = skip)')
     ap.add_argument('--no-e2e', action='store_true')
-    ap.add_argument('--in-flight', type=int, default=2,
+    ap.add_argument('--in-flight', type=int, default=3,
                     help='steps kept in flight (one CUDA graph + stream + batch per slot); 1 = strictly serial steps')
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel from Python instead of replaying a CUDA graph')
     return ap.parse_args()

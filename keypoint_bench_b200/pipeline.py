@@ -135,8 +135,8 @@ class StepsInFlight:
     """Keeps ``len(fns)`` steps in flight: one captured CUDA graph per slot, each replayed on its own stream over
     its own input batch and output buffers.  A step is a chain of dependent kernels of which several are
     latency-bound (one CTA per map in the sparse NMS resolve, the matcher's resolve / rescan / gate tails), so a
-    second step's bandwidth- and tensor-bound kernels fill the SMs those leave idle (+11 % pairs/s on cfg2,
-    +17 % on cfg1, measured).  ``launch(i)`` replays slot ``i % depth`` and returns that slot's outputs, valid
+    other steps' bandwidth- and tensor-bound kernels fill the SMs those leave idle (cfg2: +10 % pairs/s with two
+    slots, +14 % with three, measured).  ``launch(i)`` replays slot ``i % depth`` and returns that slot's outputs, valid
     until the slot is launched again; work queued with ``on_slot`` runs on the slot's stream after it."""
 
     def __init__(self, fns):
