@@ -155,8 +155,10 @@ KB_API int kb_sample_desc(const float* desc, int B, int C, int h, int w, const f
  * d0 the first-of-ties Euclidean nearest column j (distances evaluated in float64 from the float32
  * inputs); with cross_check the pair survives only if i is also the first-of-ties nearest row of j;
  * pairs with distance >= max_distance are dropped (strict <; pass INFINITY to disable).  Output
- * sorted by i ascending: pairs [B,n_max,2] int32, dist [B,n_max] float64 (may be NULL),
- * count [B].  `algo` 0 = float64 SIMT evaluation of every distance; 1 = tcgen05 tensor-core
+ * sorted by i ascending: pairs [B,n_max,2] int32, dist [B,n_max] float64 (may be NULL: the reference's
+ * brute_force_matcher keeps only the index pairs, and the tensor-core path then decides the max_distance gate
+ * from its certified score, evaluating float64 distances only inside the error band), count [B] (assigned for
+ * every b).  `algo` 0 = float64 SIMT evaluation of every distance; 1 = tcgen05 tensor-core
  * candidate search (split-bf16 Gram in TMEM) with float64 certification of the winners (D <= 256);
  * -1 = automatic (1 when supported, else 0).  Both produce the same pairs.
  * ------------------------------------------------------------------------------------------- */
@@ -174,7 +176,11 @@ KB_API int kb_match_mnn_phases(const float* d0, const float* d1, const int* n0, 
  * off[0] records of direction 0: per row FOUR records (one per column slice of the epilogue) of 32 B
  * (float best, second, third, pad; int argbest, argsecond, pad, pad), off[1] same for direction 1, off[2] int32[2] = rows that needed the exact float64 rescan,
  * rows settled by the two-candidate exact check,
- * off[3]/off[4] float32 squared row norms of d0/d1. */
+ * off[3]/off[4] float32 squared row norms of d0/d1, off[5] int64[512][8] pipeline wait counters of the search
+ * kernel (filled when the environment has KB_TC_DEBUG=4, scripts/tc_pipeline_profile.py).  `off` has SIX entries.
+ * Environment switches read by the tensor-core path (experiments; results do not change): KB_TC_CLUSTER=2 selects
+ * the CTA-pair (cta_group::2) search kernel, KB_TC_DEBUG is a bit mask of timing experiments (results are WRONG
+ * with bits 1, 2 or 8 set). */
 KB_API int kb_match_tc_debug_offsets(int B, int n_max, int m_max, int D, size_t* off);
 
 /* ---------------------------------------------------------------------------------------------
