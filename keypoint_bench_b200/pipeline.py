@@ -67,6 +67,34 @@ def _extract_match(batch, cfg, algo, covisible_only, timer) -> dict:
     return out
 
 
+@dataclass
+class FrameBatch:
+    """Device-resident inputs of a frame stream (KITTI-like sequences, tasks/visual_odometer.py,
+    tasks/FundamentalMatrix.py): F + 1 consecutive frames give F pairs (t-1, t)."""
+    score: torch.Tensor          # [F+1,1,H,W]
+    desc: torch.Tensor           # [F+1,C,h,w]
+
+    @property
+    def pairs(self) -> int:
+        return self.score.shape[0] - 1
+
+
+def extract_match_stream(frames: FrameBatch, cfg: PathConfig, algo: int = -1) -> dict:
+    """Stream form of the path: every frame is detected and sampled ONCE and matched against its predecessor.
+    The reference's per-pair step (models/model_interface.py:217-228 keeps the previous frame's maps and calls
+    ``detection`` on both maps of every pair) does the previous frame's extraction a second time; the results per
+    pair are identical because extraction depends on the frame alone.  The stream tasks match ALL keypoints
+    (no covisibility warp: tasks/FundamentalMatrix.py:53-57, tasks/visual_odometer.py:44-60).
+    Returns kpts [F+1,top_k,3], n_kpts [F+1], desc [F+1,top_k,C], matches [F,top_k,2] (pair f = frames f, f+1),
+    n_matches [F].  A rank's chunk carries a one-frame halo (parallel.shard_stream)."""
+    with ops.no_zero_fill():
+        xyp, count, raster, path = ops.detect_batched(frames.score, cfg.extractor_params)
+        d = ops.sample_batched(frames.desc, xyp, count)
+        pairs, _, n_m = ops.match_batched(d[:-1], d[1:], count[:-1], count[1:], cfg.max_distance, cfg.cross_check,
+                                          algo=algo, want_dist=False)
+    return {'kpts': xyp, 'n_kpts': count, 'raster': raster, 'path': path, 'desc': d, 'matches': pairs, 'n_matches': n_m}
+
+
 def repeatability_counts(batch: PairBatch, cfg: PathConfig, th: float = 3.0, timer=None) -> dict:
     """detect x2 -> warp x2 -> val_key_points counting for every pair (tasks/repeatability.py:95-122).
     stats[P,4] float64 = (gt_num, sum of errors<=th, n mutual pairs, 0); num_feat[P] = min(n0,n1)."""

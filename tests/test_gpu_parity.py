@@ -675,3 +675,39 @@ def test_optical_flow_tensor_dropin_and_batched_against_oracle():
         optical_flow_cv(None, None, None, None)
     with pytest.raises(RuntimeError):
         optical_flow_tensor(pts[0].to(DEV), pts[0].to(DEV), img0[0:1, :1].to(DEV), img1[0:1, :1].to(DEV), params)
+
+
+# ------------------------------------------------------------------------------------------------ frame streams
+
+def test_stream_pipeline_equals_pairwise_pipeline_and_oracle():
+    """extract_match_stream (every frame extracted once) gives, pair by pair, what the pairwise pipeline gives on
+    (frame t-1, frame t) without the covisibility warp -- and what the oracle's brute_force_matcher gives."""
+    import dataclasses
+    from keypoint_bench_b200 import pipeline
+    cfg = dataclasses.replace(synth.CONFIGS['cfg5'], height=120, width=200, top_k=300)
+    f = 5
+    gen = torch.Generator().manual_seed(21)
+    score = torch.rand(f + 1, 1, cfg.height, cfg.width, generator=gen)
+    desc = 2.67 * torch.nn.functional.normalize(torch.randn(f + 1, cfg.desc_dim, cfg.height, cfg.width, generator=gen), dim=1)
+    for t in range(1, f + 1):                                   # consecutive frames share content: shift by 2 px + noise
+        score[t, :, :, 2:] = score[t - 1, :, :, :-2]
+        desc[t, :, :, 2:] = desc[t - 1, :, :, :-2] + 0.05 * torch.randn(cfg.desc_dim, cfg.height, cfg.width - 2, generator=gen)
+    frames = pipeline.FrameBatch(score.to(DEV), desc.to(DEV))
+    got = pipeline.extract_match_stream(frames, cfg)
+    assert got['matches'].shape[0] == f
+    # pairwise pipeline on the same frames: first f frames as image 0, last f as image 1
+    eye = torch.eye(3).reshape(1, 9).repeat(2 * f, 1).to(DEV)
+    wh = torch.tensor([[float(cfg.width), float(cfg.height)]]).repeat(2 * f, 1).to(DEV)
+    pb = pipeline.PairBatch(torch.cat([score[:-1], score[1:]]).to(DEV), torch.cat([desc[:-1], desc[1:]]).to(DEV), eye, wh)
+    want = pipeline.extract_match(pb, cfg, covisible_only=False)
+    for i in range(f):
+        k = int(got['n_matches'][i])
+        assert k == int(want['n_matches'][i]) and k > 20
+        assert torch.equal(got['matches'][i, :k], want['matches'][i, :k]), i
+        assert int(got['n_kpts'][i]) == int(want['n_kpts'][i])
+    # oracle on the first pair
+    n0, n1 = int(got['n_kpts'][0]), int(got['n_kpts'][1])
+    k0, k1 = got['kpts'][0, :n0].cpu().numpy(), got['kpts'][1, :n1].cpu().numpy()
+    _, _, pairs = ref_ops.brute_force_matcher(k0, k1, desc[0:1].numpy(), desc[1:2].numpy(), cfg.matcher_params)
+    k = int(got['n_matches'][0])
+    assert np.array_equal(got['matches'][0, :k].cpu().numpy().astype(np.int64), pairs)
