@@ -3,6 +3,7 @@
 // MHA corner error (tasks/MHA.py:51-72).  Inputs are a few KB per pair, so these kernels are
 // latency-bound; they exist to keep a whole batch of pairs on the device with no host round trip.
 #include <math_constants.h>
+#include <cstdlib>
 #include "kb_common.cuh"
 
 namespace {
@@ -107,13 +108,16 @@ __global__ void __launch_bounds__(RT) rep_minima_kernel(RepParams p) {
     const int b = blockIdx.y;
     if (p.only_flagged && !p.only_flagged[b]) return;
     const int A = p.na ? p.na[b] : p.a_max, Bn = p.nb ? p.nb[b] : p.b_max;
-    const int i0 = blockIdx.x * RB;
-    if (i0 >= A || Bn <= 0) return;
+    if (Bn <= 0) return;
     const int nd = A < Bn ? A : Bn;
     const float2* k0c = reinterpret_cast<const float2*>(p.k0c) + (size_t)b * p.a_max;
     const float2* k01c = reinterpret_cast<const float2*>(p.k01c) + (size_t)b * p.a_max;
     const float2* k1c = reinterpret_cast<const float2*>(p.k1c) + (size_t)b * p.b_max;
     const float2* k10c = reinterpret_cast<const float2*>(p.k10c) + (size_t)b * p.b_max;
+    __shared__ float s_red[RB][RT / 32];
+    __shared__ float s_max[RT / 32];
+    // the grid is small (these kernels only run for maps the pruned path rejected): every block walks row blocks
+    for (int i0 = blockIdx.x * RB; i0 < A; i0 += gridDim.x * RB) {
     float2 a[RB], a1[RB];
     float rmin[RB];
 #pragma unroll
@@ -138,8 +142,6 @@ __global__ void __launch_bounds__(RT) rep_minima_kernel(RepParams p) {
         }
         atomicMin(&p.colmin[(size_t)b * p.b_max + j], __float_as_uint(cmin));
     }
-    __shared__ float s_red[RB][RT / 32];
-    __shared__ float s_max[RT / 32];
 #pragma unroll
     for (int r = 0; r < RB; ++r) {
         float v = rmin[r];
@@ -160,14 +162,15 @@ __global__ void __launch_bounds__(RT) rep_minima_kernel(RepParams p) {
         for (int w = 1; w < RT / 32; ++w) v = fmaxf(v, s_max[w]);
         atomicMax(&p.gmax[b], __float_as_uint(v));
     }
+    __syncthreads();
+    }
 }
 
 __global__ void __launch_bounds__(RT) rep_mutual_kernel(RepParams p) {
     const int b = blockIdx.y;
     if (p.only_flagged && !p.only_flagged[b]) return;
     const int A = p.na ? p.na[b] : p.a_max, Bn = p.nb ? p.nb[b] : p.b_max;
-    const int i0 = blockIdx.x * RB;
-    if (i0 >= A || Bn <= 0) return;
+    if (Bn <= 0) return;
     const int nd = A < Bn ? A : Bn;
     const float2* k0c = reinterpret_cast<const float2*>(p.k0c) + (size_t)b * p.a_max;
     const float2* k01c = reinterpret_cast<const float2*>(p.k01c) + (size_t)b * p.a_max;
@@ -175,6 +178,9 @@ __global__ void __launch_bounds__(RT) rep_mutual_kernel(RepParams p) {
     const float2* k10c = reinterpret_cast<const float2*>(p.k10c) + (size_t)b * p.b_max;
     // value = -dist_mutual; v = value - value.min() = (-d) - (-dmax)      (repeatability.py:18, 36)
     const float vmin = -__uint_as_float(p.gmax[b]);
+    int gt = 0, np = 0;
+    double sum = 0.0;
+    for (int i0 = blockIdx.x * RB; i0 < A; i0 += gridDim.x * RB) {       // small grid: every block walks row blocks
     float2 a[RB], a1[RB];
     float rq[RB];
 #pragma unroll
@@ -184,8 +190,6 @@ __global__ void __launch_bounds__(RT) rep_mutual_kernel(RepParams p) {
         a1[r] = k01c[i];
         rq[r] = __fsub_rn(-__uint_as_float(p.rowmin[(size_t)b * p.a_max + i]), vmin);   // row max of v
     }
-    int gt = 0, np = 0;
-    double sum = 0.0;
     for (int j = threadIdx.x; j < Bn; j += RT) {
         const float2 bq = k1c[j], b0 = k10c[j];
         const float cq = __fsub_rn(-__uint_as_float(p.colmin[(size_t)b * p.b_max + j]), vmin);   // col max of v
@@ -201,6 +205,7 @@ __global__ void __launch_bounds__(RT) rep_mutual_kernel(RepParams p) {
                 }
             }
         }
+    }
     }
     // block reduction then one atomic per block
     __shared__ int s_gt[RT / 32], s_np[RT / 32];
@@ -411,6 +416,228 @@ __global__ void __launch_bounds__(PT) rep_mutual_pruned_kernel(RepParams p, cons
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Sorted sweeps (the default when both sides have <= SRT_MAX points): the other side's points are sorted by the
+// y coordinate of their FIRST pair of coordinates once per map, and a row (column) only visits the entries around
+// its own y, outwards in both directions, until |dy| alone excludes them:
+//     dist_mutual >= |a - b0| / 2 >= |dy| / 2,
+// so with the other side sorted by y the walk stops as soon as dy^2 / 4 exceeds the squared running minimum --
+// everything farther is farther in y.  A repeatable point finds its partner within the first few entries and stops
+// after two or three steps; the old sweep above evaluates the bound for every entry.  Evaluated entries use exactly
+// the arithmetic of dist_mutual(); skipped entries are provably larger than the minimum (same 1.0001 guard as
+// above), so minima, counts and sums are identical.  The masked diagonal entry (d = 99999 whatever its geometry)
+// is taken out of the walk and added back explicitly.
+// ------------------------------------------------------------------------------------------------
+constexpr int SRT_MAX = 4096;     // points per side the sorted path handles (shared-memory staging)
+constexpr int SW_NT = 256;        // threads per block of the sweeps: 32 rows x 8 lanes
+constexpr int SW_ROWS = SW_NT / PL;
+
+struct SortedSide {
+    float4* pts;      // [B, n_max] (o1.x, o1.y, o2.x, o2.y) sorted by o1.y ascending
+    int* idx;         // [B, n_max] original index of every sorted entry
+};
+
+// side 0: the B points (k10c, k1c) sorted by k10c.y; side 1: the A points (k0c, k01c) sorted by k0c.y
+__global__ void __launch_bounds__(1024) rep_sort_kernel(RepParams p, const int* need_bf, SortedSide s0, SortedSide s1) {
+    extern __shared__ unsigned long long srt_keys[];
+    const int b = blockIdx.x, side = blockIdx.y;
+    if (need_bf[b]) return;
+    const int A = p.na ? p.na[b] : p.a_max, Bn = p.nb ? p.nb[b] : p.b_max;
+    const int n = side ? A : Bn, n_max = side ? p.a_max : p.b_max;
+    const float2* o1 = reinterpret_cast<const float2*>(side ? p.k0c : p.k10c) + (size_t)b * n_max;
+    const float2* o2 = reinterpret_cast<const float2*>(side ? p.k01c : p.k1c) + (size_t)b * n_max;
+    int np2 = 1;
+    while (np2 < n) np2 <<= 1;
+    for (int i = threadIdx.x; i < np2; i += 1024)
+        srt_keys[i] = i < n ? (((unsigned long long)kb::float_order_key(o1[i].y) << 32) | (unsigned)i) : ~0ull;
+    __syncthreads();
+    for (int k = 2; k <= np2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < np2; i += 1024) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const unsigned long long x = srt_keys[i], y = srt_keys[l];
+                    const bool asc = ((i & k) == 0);
+                    if (asc ? (x > y) : (x < y)) { srt_keys[i] = y; srt_keys[l] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    float4* op = (side ? s1.pts : s0.pts) + (size_t)b * n_max;
+    int* oi = (side ? s1.idx : s0.idx) + (size_t)b * n_max;
+    for (int i = threadIdx.x; i < n; i += 1024) {
+        const int src = (int)(srt_keys[i] & 0xffffffffu);
+        const float2 a = o1[src], c = o2[src];
+        op[i] = make_float4(a.x, a.y, c.x, c.y);
+        oi[i] = src;
+    }
+}
+
+// the walk shared by the three sorted kernels: lanes 0-3 of a row go up from its y, lanes 4-7 go down
+struct Walk {
+    int k, step, n;
+    __device__ __forceinline__ void init(int pos, int sub, int n_) {
+        n = n_;
+        if (sub < PL / 2) { k = pos + sub; step = PL / 2; } else { k = pos - 1 - (sub - PL / 2); step = -(PL / 2); }
+    }
+    __device__ __forceinline__ bool in_range() const { return k >= 0 && k < n; }
+    __device__ __forceinline__ void stop() { k = -1; step = -1; }
+};
+
+__device__ __forceinline__ int lower_bound_y(const float4* pts, int n, float y) {
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (pts[mid].y < y) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+template <int SIDE>
+__global__ void __launch_bounds__(SW_NT) rep_min_sorted_kernel(RepParams p, const int* need_bf, SortedSide so) {
+    extern __shared__ __align__(16) unsigned char sw_smem[];
+    const int b = blockIdx.y;
+    if (need_bf[b]) return;
+    const int A = p.na ? p.na[b] : p.a_max, Bn = p.nb ? p.nb[b] : p.b_max;
+    const int n_own = SIDE ? Bn : A, n_oth = SIDE ? A : Bn, oth_max = SIDE ? p.a_max : p.b_max;
+    if (blockIdx.x * SW_ROWS >= n_own) return;
+    const int nd = A < Bn ? A : Bn;
+    float4* s_pts = reinterpret_cast<float4*>(sw_smem);
+    int* s_idx = reinterpret_cast<int*>(s_pts + n_oth);
+    for (int t = threadIdx.x; t < n_oth; t += SW_NT) {
+        s_pts[t] = so.pts[(size_t)b * oth_max + t];
+        s_idx[t] = so.idx[(size_t)b * oth_max + t];
+    }
+    __syncthreads();
+    const int own = blockIdx.x * SW_ROWS + threadIdx.x / PL, sub = threadIdx.x % PL;
+    const bool live = own < n_own;
+    const float2* own1 = reinterpret_cast<const float2*>(SIDE ? p.k10c : p.k0c) + (size_t)b * (SIDE ? p.b_max : p.a_max);
+    const float2* own2 = reinterpret_cast<const float2*>(SIDE ? p.k1c : p.k01c) + (size_t)b * (SIDE ? p.b_max : p.a_max);
+    const float2 P = live ? own1[own] : make_float2(0.f, 0.f), Q = live ? own2[own] : make_float2(0.f, 0.f);
+    // the masked diagonal entry counts as 99999 wherever it lies; it is skipped in the walk
+    const bool has_diag = live && own < nd;
+    float best = has_diag ? 99999.0f : CUDART_INF_F;
+    float thr = has_diag ? 99999.0f * 99999.0f * 1.0001f : CUDART_INF_F;
+    Walk w;
+    w.init(live ? lower_bound_y(s_pts, n_oth, P.y) : 0, sub, live ? n_oth : 0);
+    while (true) {
+        bool active = w.in_range();
+        if (active) {
+            const float4 o = s_pts[w.k];
+            const float dy = __fsub_rn(P.y, o.y);
+            if (__fmul_rn(dy, dy) * 0.25f > thr) {
+                w.stop();                                   // everything farther in this direction is farther in y
+                active = false;
+            } else {
+                const float dx = __fsub_rn(P.x, o.x);
+                const float s1 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+                if (!(s1 * 0.25f > thr) && !(has_diag && s_idx[w.k] == own)) {
+                    const float ex = __fsub_rn(o.z, Q.x), ey = __fsub_rn(o.w, Q.y);
+                    const float s2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+                    if (!(s2 * 0.25f > thr)) {
+                        const float d = __fmul_rn(__fadd_rn(__fsqrt_rn(s1), __fsqrt_rn(s2)), 0.5f);     // repeatability.py:69-71
+                        best = fminf(best, d);
+                    }
+                }
+                w.k += w.step;
+            }
+        }
+        // the PL lanes of a row share their running minimum after every step
+#pragma unroll
+        for (int m = PL / 2; m > 0; m >>= 1) best = fminf(best, __shfl_xor_sync(0xffffffffu, best, m));
+        thr = best * best * 1.0001f;
+        if (!__any_sync(0xffffffffu, active)) break;
+    }
+    if (live && sub == 0) {
+        if (SIDE == 0) {
+            p.rowmin[(size_t)b * p.a_max + own] = __float_as_uint(best);
+            if (p.errors) p.errors[(size_t)b * p.a_max + own] = __fmul_rn(best, p.scale10);      // :78,85
+        } else {
+            p.colmin[(size_t)b * p.b_max + own] = __float_as_uint(best);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(SW_NT) rep_mutual_sorted_kernel(RepParams p, const int* need_bf, SortedSide so) {
+    extern __shared__ __align__(16) unsigned char sw_smem[];
+    __shared__ int s_gt[SW_NT / 32], s_np[SW_NT / 32];
+    __shared__ double s_sum[SW_NT / 32];
+    const int b = blockIdx.y;
+    if (need_bf[b]) return;
+    const int A = p.na ? p.na[b] : p.a_max, Bn = p.nb ? p.nb[b] : p.b_max;
+    if (blockIdx.x * SW_ROWS >= A) return;
+    const int nd = A < Bn ? A : Bn;
+    float4* s_pts = reinterpret_cast<float4*>(sw_smem);
+    int* s_idx = reinterpret_cast<int*>(s_pts + Bn);
+    for (int t = threadIdx.x; t < Bn; t += SW_NT) {
+        s_pts[t] = so.pts[(size_t)b * p.b_max + t];
+        s_idx[t] = so.idx[(size_t)b * p.b_max + t];
+    }
+    __syncthreads();
+    const int i = blockIdx.x * SW_ROWS + threadIdx.x / PL, sub = threadIdx.x % PL;
+    const bool live = i < A;
+    const float2* k0c = reinterpret_cast<const float2*>(p.k0c) + (size_t)b * p.a_max;
+    const float2* k01c = reinterpret_cast<const float2*>(p.k01c) + (size_t)b * p.a_max;
+    const unsigned int* colmin = p.colmin + (size_t)b * p.b_max;
+    const float vmin = -__uint_as_float(p.gmax[b]);          // = -99999: value.min() of repeatability.py:18
+    const float2 a = live ? k0c[i] : make_float2(0.f, 0.f), a1 = live ? k01c[i] : make_float2(0.f, 0.f);
+    const float rmin = live ? __uint_as_float(p.rowmin[(size_t)b * p.a_max + i]) : 0.0f;
+    const float rq = __fsub_rn(-rmin, vmin);                 // row maximum of v = (-d) - min(-d)
+    // v has a resolution of one ulp of 99999 (2^-7): every d that rounds onto rq lies within 2 ulps of the
+    // row minimum; everything farther is skipped
+    const float lim = rmin + 0.0172f;
+    const float thr = lim * lim * 1.0001f;
+    const bool has_diag = live && i < nd;
+    int gt = 0, np = 0;
+    double sum = 0.0;
+    auto tally = [&](float d, int j) {
+        const float v = __fsub_rn(-d, vmin);
+        if (v == rq) {
+            const float cq = __fsub_rn(-__uint_as_float(colmin[j]), vmin);               // column maximum of v
+            if (v == cq) {                                                               // repeatability.py:25-28
+                const float ds = __fmul_rn(d, p.scale01);                                // :76-80
+                ++np;
+                if (ds <= p.th) { ++gt; sum += (double)ds; }                             // :82-83
+            }
+        }
+    };
+    if (has_diag && sub == 0) tally(99999.0f, i);            // the masked diagonal entry (repeatability.py:72-73)
+    Walk w;
+    w.init(live ? lower_bound_y(s_pts, Bn, a.y) : 0, sub, live ? Bn : 0);
+    while (w.in_range()) {
+        const float4 o = s_pts[w.k];
+        const float dy = __fsub_rn(a.y, o.y);
+        if (__fmul_rn(dy, dy) * 0.25f > thr) break;
+        const float dx = __fsub_rn(a.x, o.x);
+        const float s1 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+        const int j = s_idx[w.k];
+        if (!(s1 * 0.25f > thr) && !(has_diag && j == i)) {
+            const float ex = __fsub_rn(o.z, a1.x), ey = __fsub_rn(o.w, a1.y);
+            const float s2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+            if (!(s2 * 0.25f > thr)) tally(__fmul_rn(__fadd_rn(__fsqrt_rn(s1), __fsqrt_rn(s2)), 0.5f), j);
+        }
+        w.k += w.step;
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+        gt += __shfl_xor_sync(0xffffffffu, gt, d);
+        np += __shfl_xor_sync(0xffffffffu, np, d);
+        sum += __shfl_xor_sync(0xffffffffu, sum, d);
+    }
+    if ((threadIdx.x & 31) == 0) { s_gt[threadIdx.x >> 5] = gt; s_np[threadIdx.x >> 5] = np; s_sum[threadIdx.x >> 5] = sum; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int g = 0, q = 0;
+        double sm = 0.0;
+        for (int wq = 0; wq < SW_NT / 32; ++wq) { g += s_gt[wq]; q += s_np[wq]; sm += s_sum[wq]; }
+        if (q) {
+            atomicAdd(&p.stats[b * 4 + 0], (double)g);
+            atomicAdd(&p.stats[b * 4 + 1], sm);
+            atomicAdd(&p.stats[b * 4 + 2], (double)q);
+        }
+    }
+}
+
 // second variant of the mutual sweep that also lists the pairs (unordered)
 __global__ void __launch_bounds__(RT) rep_pairs_kernel(RepParams p, int* pair_count) {
     const int b = blockIdx.y;
@@ -606,7 +833,9 @@ extern "C" int kb_warp_homography(const float* pts, int pts_stride, const int* c
 extern "C" size_t kb_repeat_workspace_bytes(int B, int a_max, int b_max) {
     if (B <= 0 || a_max <= 0 || b_max <= 0) return 0;
     return kb_align_up((size_t)B * a_max * 4, 256) + kb_align_up((size_t)B * b_max * 4, 256) +
-           kb_align_up((size_t)B * 4, 256) * 3 + 1024;
+           kb_align_up((size_t)B * 4, 256) * 3 + 1024 +
+           kb_align_up((size_t)B * a_max * 16, 256) + kb_align_up((size_t)B * b_max * 16, 256) +     // sorted points
+           kb_align_up((size_t)B * a_max * 4, 256) + kb_align_up((size_t)B * b_max * 4, 256);        // their indices
 }
 
 extern "C" int kb_repeat_counts(const float* k0c, const float* k01c, const int* na, const float* k1c,
@@ -624,6 +853,9 @@ extern "C" int kb_repeat_counts(const float* k0c, const float* k01c, const int* 
     p.gmax = arena.take<unsigned int>(B);
     int* pair_count = arena.take<int>(B);
     int* need_bf = arena.take<int>(B);
+    SortedSide s_b, s_a;                    // the B points sorted by k10c.y, the A points sorted by k0c.y
+    s_b.pts = arena.take<float4>((size_t)B * b_max); s_b.idx = arena.take<int>((size_t)B * b_max);
+    s_a.pts = arena.take<float4>((size_t)B * a_max); s_a.idx = arena.take<int>((size_t)B * a_max);
     if (!arena.ok()) return KB_ERR_WORKSPACE;
     p.only_flagged = nullptr;
     p.k0c = k0c; p.k01c = k01c; p.k1c = k1c; p.k10c = k10c; p.na = na; p.nb = nb; p.stats = stats;
@@ -636,20 +868,41 @@ extern "C" int kb_repeat_counts(const float* k0c, const float* k01c, const int* 
     // pruned sweeps for every map whose distances are provably below the 99999 diagonal mask ...
     rep_bound_kernel<<<B, 256, 0, st>>>(p, need_bf);
     KB_LAUNCH_CHECK();
-    rep_min_pruned_kernel<0><<<dim3((a_max + PR - 1) / PR, B), PT, 0, st>>>(p, need_bf);
-    KB_LAUNCH_CHECK();
-    rep_min_pruned_kernel<1><<<dim3((b_max + PR - 1) / PR, B), PT, 0, st>>>(p, need_bf);
-    KB_LAUNCH_CHECK();
-    rep_mutual_pruned_kernel<<<dim3((a_max + PR - 1) / PR, B), PT, 0, st>>>(p, need_bf);
-    KB_LAUNCH_CHECK();
+    static const bool no_sort = getenv("KB_REP_NO_SORT") != nullptr;          // A/B timing only
+    if (a_max <= SRT_MAX && b_max <= SRT_MAX && !no_sort) {
+        int np2 = 1;
+        while (np2 < (a_max > b_max ? a_max : b_max)) np2 <<= 1;
+        rep_sort_kernel<<<dim3(B, 2), 1024, (size_t)np2 * 8, st>>>(p, need_bf, s_b, s_a);
+        KB_LAUNCH_CHECK();
+        const size_t sm_b = (size_t)b_max * 20, sm_a = (size_t)a_max * 20;
+        KB_CUDA_TRY(cudaFuncSetAttribute(rep_min_sorted_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_b));
+        KB_CUDA_TRY(cudaFuncSetAttribute(rep_min_sorted_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_a));
+        KB_CUDA_TRY(cudaFuncSetAttribute(rep_mutual_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_b));
+        rep_min_sorted_kernel<0><<<dim3((a_max + SW_ROWS - 1) / SW_ROWS, B), SW_NT, sm_b, st>>>(p, need_bf, s_b);
+        KB_LAUNCH_CHECK();
+        rep_min_sorted_kernel<1><<<dim3((b_max + SW_ROWS - 1) / SW_ROWS, B), SW_NT, sm_a, st>>>(p, need_bf, s_a);
+        KB_LAUNCH_CHECK();
+        rep_mutual_sorted_kernel<<<dim3((a_max + SW_ROWS - 1) / SW_ROWS, B), SW_NT, sm_b, st>>>(p, need_bf, s_b);
+        KB_LAUNCH_CHECK();
+    } else {
+        rep_min_pruned_kernel<0><<<dim3((a_max + PR - 1) / PR, B), PT, 0, st>>>(p, need_bf);
+        KB_LAUNCH_CHECK();
+        rep_min_pruned_kernel<1><<<dim3((b_max + PR - 1) / PR, B), PT, 0, st>>>(p, need_bf);
+        KB_LAUNCH_CHECK();
+        rep_mutual_pruned_kernel<<<dim3((a_max + PR - 1) / PR, B), PT, 0, st>>>(p, need_bf);
+        KB_LAUNCH_CHECK();
+    }
     // ... the exhaustive sweeps for the rest (they return at once for all other maps)
     dim3 grid((a_max + RB - 1) / RB, B);
+    // exhaustive kernels: a handful of blocks per map (they loop over the row blocks); in the common case every
+    // block returns at once, and 16 k empty blocks cost more than the sorted sweeps
+    dim3 grid_x(grid.x < 8 ? grid.x : 8, B);
     p.only_flagged = need_bf;
-    rep_minima_kernel<<<grid, RT, 0, st>>>(p);
+    rep_minima_kernel<<<grid_x, RT, 0, st>>>(p);
     KB_LAUNCH_CHECK();
     RepParams q = p;
     q.pairs = nullptr;
-    rep_mutual_kernel<<<grid, RT, 0, st>>>(q);
+    rep_mutual_kernel<<<grid_x, RT, 0, st>>>(q);
     KB_LAUNCH_CHECK();
     p.only_flagged = nullptr;
     if (pairs) {

@@ -361,11 +361,12 @@ def repeat_batched(k0c, k01c, na, k1c, k10c, nb, scale01: float, scale10: float,
         _require_cuda(t, nm)
     a0, a1, b0, b1 = _f32(k0c), _f32(k01c), _f32(k1c), _f32(k10c)
     b, a_max, b_max = a0.shape[0], a0.shape[1], b0.shape[1]
-    stats = torch.zeros(b, 4, dtype=torch.float64, device=a0.device)
-    errors = torch.zeros(b, a_max, dtype=torch.float32, device=a0.device) if want_errors else None
     pairs = torch.full((b, pair_cap, 2), -1, dtype=torch.int32, device=a0.device) if pair_cap > 0 else None
     if a_max == 0 or b_max == 0:
-        return stats, errors, pairs
+        return (torch.zeros(b, 4, dtype=torch.float64, device=a0.device),
+                torch.zeros(b, a_max, dtype=torch.float32, device=a0.device) if want_errors else None, pairs)
+    stats = _out(b, 4, dtype=torch.float64, device=a0.device)           # both are cleared by the library's init kernel
+    errors = _out(b, a_max, dtype=torch.float32, device=a0.device) if want_errors else None
     ca, cb = _i32(na), _i32(nb)
     ws = _ws(lib.kb_repeat_workspace_bytes(b, a_max, b_max), a0.device)
     with torch.cuda.device(a0.device):
@@ -373,7 +374,7 @@ def repeat_batched(k0c, k01c, na, k1c, k10c, nb, scale01: float, scale10: float,
                                    a_max, b_max, float(scale01), float(scale10), float(th), stats.data_ptr(),
                                    _ptr(errors), _ptr(pairs), int(pair_cap), ws.data_ptr(), ws.numel(), _stream()),
               'kb_repeat_counts')
-    _count(7 + (1 if pair_cap > 0 else 0))     # init, bound, 2 pruned minima, pruned mutual, 2 exhaustive (early exit)
+    _count(8 + (1 if pair_cap > 0 else 0))     # init, bound, sort, 2 sorted minima, sorted mutual, 2 exhaustive (early exit)
     return stats, errors, pairs
 
 

@@ -100,14 +100,15 @@ def repeatability_counts(batch: PairBatch, cfg: PathConfig, th: float = 3.0, tim
     stats[P,4] float64 = (gt_num, sum of errors<=th, n mutual pairs, 0); num_feat[P] = min(n0,n1)."""
     P = batch.pairs
     t = timer or (lambda name: None)
-    t('detect')
-    xyp, count, raster, path = ops.detect_batched(batch.score, cfg.extractor_params)
-    t('warp')
-    kv, kw, ids, ids_out, nv = ops.warp_batched(xyp, count, batch.h33, batch.wh)
-    t('repeat')
-    stats, errors, _ = ops.repeat_batched(kv[:P], kw[:P], nv[:P], kv[P:], kw[P:], nv[P:], float(batch.resize),
-                                          float(batch.resize), th, want_errors=True)
-    t(None)
+    with ops.no_zero_fill():                                  # rows beyond the per-map counts are unspecified
+        t('detect')
+        xyp, count, raster, path = ops.detect_batched(batch.score, cfg.extractor_params)
+        t('warp')
+        kv, kw, ids, ids_out, nv = ops.warp_batched(xyp, count, batch.h33, batch.wh)
+        t('repeat')
+        stats, errors, _ = ops.repeat_batched(kv[:P], kw[:P], nv[:P], kv[P:], kw[P:], nv[P:], float(batch.resize),
+                                              float(batch.resize), th, want_errors=True)
+        t(None)
     num_feat = torch.minimum(count[:P], count[P:])
     empty = (nv[:P] == 0) | (nv[P:] == 0)                     # repeatability.py:61-67 -> zeros
     return {'stats': stats, 'errors': errors, 'num_feat': torch.where(empty, torch.zeros_like(num_feat), num_feat),

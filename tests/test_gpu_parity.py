@@ -711,3 +711,45 @@ def test_stream_pipeline_equals_pairwise_pipeline_and_oracle():
     _, _, pairs = ref_ops.brute_force_matcher(k0, k1, desc[0:1].numpy(), desc[1:2].numpy(), cfg.matcher_params)
     k = int(got['n_matches'][0])
     assert np.array_equal(got['matches'][0, :k].cpu().numpy().astype(np.int64), pairs)
+
+
+@pytest.mark.parametrize('seed', range(10))
+def test_repeat_counts_randomised_sorted_and_exhaustive_paths(seed):
+    """kb_repeat_counts against the oracle's dist_mutual / mutual_argmin arithmetic (tasks/repeatability.py:69-85) on
+    random point sets: clustered partners, ragged counts, one-point sides, and coordinates scaled past the 99999
+    diagonal mask (which sends the map to the exhaustive kernels instead of the sorted sweeps)."""
+    rng = np.random.default_rng(7000 + seed)
+    b = 3
+    a_max, b_max = int(rng.integers(1, 400)), int(rng.integers(1, 400))
+    scale = [1.0, 1.0, 5.0e4][seed % 3]                       # 5e4: distances beat the 99999 mask -> exhaustive path
+    na = rng.integers(1, a_max + 1, size=b)
+    nb = rng.integers(1, b_max + 1, size=b)
+    k0c = rng.random((b, a_max, 2), dtype=np.float32) * scale
+    k1c = rng.random((b, b_max, 2), dtype=np.float32) * scale
+    k01c = (k0c + rng.normal(0, 0.002, k0c.shape).astype(np.float32) * scale).astype(np.float32)   # A points seen in image 1
+    k10c = (k1c + rng.normal(0, 0.002, k1c.shape).astype(np.float32) * scale).astype(np.float32)
+    m = min(a_max, b_max) // 2
+    k1c[:, :m] = k01c[:, :m]                                   # true partners: B point j sits where A point j lands
+    k10c[:, :m] = k0c[:, :m]
+    if m > 3:                                                  # shuffle partners away from the masked diagonal
+        perm = rng.permutation(m)
+        k1c[:, :m] = k1c[:, perm]
+        k10c[:, :m] = k10c[:, perm]
+    th, s01, s10 = 3.0, 512.0, 512.0
+    t = lambda x: torch.from_numpy(x).to(DEV)      # noqa: E731
+    stats, errors, _ = ops().repeat_batched(t(k0c), t(k01c), t(na.astype(np.int32)), t(k1c), t(k10c),
+                                            t(nb.astype(np.int32)), s01, s10, th, want_errors=True)
+    stats, errors = stats.cpu().numpy(), errors.cpu().numpy()
+    for i in range(b):
+        A, Bn = int(na[i]), int(nb[i])
+        d01 = ref_ops.keypoint_distance(k0c[i, :A], k10c[i, :Bn])
+        d10 = ref_ops.keypoint_distance(k1c[i, :Bn], k01c[i, :A])
+        dm = ((d01 + d10.T) / np.float32(2)).astype(np.float32)
+        for q in range(min(A, Bn)):
+            dm[q, q] = np.float32(99999)
+        rows, cols = ref_ops.mutual_argmin(dm)
+        dist = (dm[rows, cols] * np.float32(s01)).astype(np.float32)
+        assert stats[i, 2] == rows.shape[0], (seed, i, scale)
+        assert stats[i, 0] == int((dist <= th).sum()), (seed, i, scale)
+        assert np.isclose(stats[i, 1], dist[dist <= th].astype(np.float64).sum(), rtol=1e-12, atol=1e-9)
+        assert np.array_equal(errors[i, :A], (dm.min(axis=1) * np.float32(s10)).astype(np.float32)), (seed, i, scale)
