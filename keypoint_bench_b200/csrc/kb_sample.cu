@@ -208,6 +208,26 @@ __global__ void __launch_bounds__(PL_NT, 2) sample_planes_kernel(SampleParams p)
     }
 }
 
+// L2 normalisation of the sampled rows in place (lightglue.py:38-40: x / max(||x||_2, 1e-12)), one warp per row, with
+// the summation order of sample_kernel's fused norm (lanes stride over the channels, xor-shuffle tree), so that the
+// plane-staged sampler + this kernel give the same bits as the gather kernel with normalize = 1.
+__global__ void __launch_bounds__(256) normalize_rows_kernel(float* out, const int* count, int n_max, int C) {
+    const int b = blockIdx.y;
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const int n = count ? count[b] : n_max;
+    if (row >= n) return;
+    float* o = out + ((size_t)b * n_max + row) * C;
+    float ss = 0.0f;
+    for (int c0 = 0; c0 < C; c0 += 32) {
+        const int c = c0 + lane;
+        const float v = c < C ? o[c] : 0.0f;
+        ss += v * v;
+    }
+    for (int d = 16; d > 0; d >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, d);
+    const float denom = fmaxf(sqrtf(ss), 1e-12f);
+    for (int c = lane; c < C; c += 32) o[c] = o[c] / denom;
+}
+
 }  // namespace
 
 extern "C" int kb_sample_desc(const float* desc, int B, int C, int h, int w, const float* pts, int pts_stride,
@@ -223,12 +243,17 @@ extern "C" int kb_sample_desc(const float* desc, int B, int C, int h, int w, con
     p.normalize = normalize; p.coord_mode = coord_mode; p.s = s;
     // low-resolution, densely sampled maps: stage whole planes (see sample_planes_kernel)
     const size_t plane_bytes = (size_t)h * w * 4;
-    if (!normalize && plane_bytes * PL_C + (size_t)n_max * 8 <= 110 * 1024 && (size_t)n_max * 16 > (size_t)h * w) {
+    if (plane_bytes * PL_C + (size_t)n_max * 8 <= 110 * 1024 && (size_t)n_max * 16 > (size_t)h * w) {
         const size_t smem = plane_bytes * PL_C + (size_t)n_max * 8;
         KB_CUDA_TRY(cudaFuncSetAttribute(sample_planes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 grid((C + PL_C - 1) / PL_C, B);
+        p.normalize = 0;                      // the staged kernel writes raw samples; rows are normalised afterwards
         sample_planes_kernel<<<grid, PL_NT, smem, (cudaStream_t)stream>>>(p);
         KB_LAUNCH_CHECK();
+        if (normalize) {
+            normalize_rows_kernel<<<dim3((n_max + 7) / 8, B), 256, 0, (cudaStream_t)stream>>>(out, count, n_max, C);
+            KB_LAUNCH_CHECK();
+        }
         return KB_OK;
     }
     dim3 grid((n_max * 32 + NT - 1) / NT, B);

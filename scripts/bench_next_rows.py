@@ -46,8 +46,12 @@ def main():
     desc = torch.randn(args.maps, 256, 60, 80, generator=g, device=dev)
     ms_nms = timed(lambda: ops.simple_nms_batched(score, 5))
     ms_all = timed(lambda: lg.extract_batched(score, desc, 8))
+    from keypoint_bench_b200 import pipeline
+    graphed = pipeline.GraphedStep(lambda: lg.extract_batched(score, desc, 8))      # the same launches as one CUDA graph
+    ms_graph = timed(graphed)
     row = {'row': 'lightglue extract (simple_nms r=5 + top-1000 + normalised sampling)', 'maps': args.maps,
-           'ms': ms_all, 'maps_per_s': args.maps / ms_all * 1e3, 'simple_nms_ms': ms_nms,
+           'ms': ms_all, 'maps_per_s': args.maps / ms_all * 1e3, 'ms_cuda_graph': ms_graph,
+           'maps_per_s_cuda_graph': args.maps / ms_graph * 1e3, 'simple_nms_ms': ms_nms,
            'simple_nms_GBps_algorithmic': args.maps * 480 * 640 * 8 / ms_nms / 1e6}
     if args.cpu:
         from oracle import ref_ops
