@@ -8,7 +8,8 @@ import sys
 
 PER_STEP = {'tau_kernel': 1, 'round1_kernel': 1, 'sparse_kernel': 1, 'nms_rounds_kernel': 1, 'select_kernel': 1,
             'warp_homography_kernel': 1, 'sample_planes_kernel': 1, 'sample_kernel': 1, 'prep_kernel': 1,
-            'nn_top2_kernel': 1, 'resolve_kernel': 1, 'rescan_kernel': 1, 'gate_kernel': 1, 'pairs_kernel': 1}
+            'nn_top2_kernel': 1, 'resolve_kernel': 1, 'rescan_kernel': 1, 'gate_kernel': 1, 'pairs_kernel': 1,
+            'rep_min_sorted_kernel': 2, 'rep_min_pruned_kernel': 2}
 
 
 def main(path):
