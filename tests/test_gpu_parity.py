@@ -753,3 +753,28 @@ def test_repeat_counts_randomised_sorted_and_exhaustive_paths(seed):
         assert stats[i, 0] == int((dist <= th).sum()), (seed, i, scale)
         assert np.isclose(stats[i, 1], dist[dist <= th].astype(np.float64).sum(), rtol=1e-12, atol=1e-9)
         assert np.array_equal(errors[i, :A], (dm.min(axis=1) * np.float32(s10)).astype(np.float32)), (seed, i, scale)
+
+
+def test_repeat_counts_sorted_and_tile_walking_kernels_agree(monkeypatch):
+    """The y-sorted sweeps (default up to 4096 points per side) and the tile-walking pruned kernels (KB_REP_NO_SORT, also
+    the path for larger sets) must give identical statistics and per-row minima."""
+    rng = np.random.default_rng(99)
+    b, a_max, b_max = 4, 1500, 1300
+    k0c = rng.random((b, a_max, 2), dtype=np.float32)
+    k1c = rng.random((b, b_max, 2), dtype=np.float32)
+    k01c = (k0c + rng.normal(0, 0.001, k0c.shape)).astype(np.float32)
+    k10c = (k1c + rng.normal(0, 0.001, k1c.shape)).astype(np.float32)
+    k1c[:, 100:900] = k01c[:, 200:1000]
+    k10c[:, 100:900] = k0c[:, 200:1000]
+    na = torch.tensor([1500, 1200, 7, 1], dtype=torch.int32)
+    nb = torch.tensor([1300, 1300, 900, 5], dtype=torch.int32)
+    t = lambda x: torch.from_numpy(x).to(DEV)      # noqa: E731
+    args = (t(k0c), t(k01c), na.to(DEV), t(k1c), t(k10c), nb.to(DEV), 512.0, 512.0, 3.0)
+    s_sorted, e_sorted, _ = ops().repeat_batched(*args, want_errors=True)
+    monkeypatch.setenv('KB_REP_NO_SORT', '1')
+    s_tiles, e_tiles, _ = ops().repeat_batched(*args, want_errors=True)
+    monkeypatch.delenv('KB_REP_NO_SORT')
+    assert torch.equal(s_sorted, s_tiles)
+    assert float(s_sorted[0, 0]) > 500
+    for i in range(b):
+        assert torch.equal(e_sorted[i, :int(na[i])], e_tiles[i, :int(na[i])]), i
