@@ -504,6 +504,7 @@ __global__ void __launch_bounds__(SP_NT, 1) sparse_kernel(SparseParams p) {
     volatile uint8_t* state = reinterpret_cast<volatile uint8_t*>(items + SMEM_CAP);   // [SMEM_CAP]
     __shared__ int s_scan[33];
     __shared__ int s_part[SP_NT / 32];
+    __shared__ int s_cut[3];
 
     const int b = blockIdx.x;
     const int H = p.H, W = p.W, r = p.r;
@@ -544,12 +545,24 @@ __global__ void __launch_bounds__(SP_NT, 1) sparse_kernel(SparseParams p) {
                     const int idx = i * SP_NT + threadIdx.x;
                     k32[i] = (i < per && idx < nM) ? (uint32_t)(LM[idx] >> 32) : 0u;
                 }
+                // one block-wide barrier per bit instead of one per bit and key: every warp adds its count to a shared
+                // counter (three rotating counters: the one for bit+2 is cleared after the barrier of bit, a full
+                // barrier before it is used)
+                if (threadIdx.x < 3) s_cut[threadIdx.x] = 0;
+                __syncthreads();
+                int rot = 0;
                 for (int bit = 31; bit >= 12; --bit) {
                     const uint32_t t = tkey | (1u << bit);
-                    int c = 0;
+                    int local = 0;
 #pragma unroll
                     for (int i = 0; i < PER; ++i)
-                        if (i < per) c += __syncthreads_count(k32[i] >= t);
+                        if (i < per) local += k32[i] >= t ? 1 : 0;
+                    local = __reduce_add_sync(0xffffffffu, local);
+                    if ((threadIdx.x & 31) == 0 && local) atomicAdd(&s_cut[rot], local);
+                    __syncthreads();
+                    const int c = s_cut[rot];
+                    if (threadIdx.x == 0) s_cut[(rot + 2) % 3] = 0;
+                    rot = (rot + 1) % 3;
                     if ((long long)c >= ksel) tkey = t;
                 }
             }
