@@ -4,12 +4,21 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
     python bench.py --impl reference --steps K --warmup W    # the reference's CPU algorithm (oracle port)
 
-A "step" is one pass of the hot path over one batch of synthetic image pairs per GPU:
-detection x2 -> covisibility warp x2 -> descriptor sampling x2 -> mutual-NN matching
-(tasks/MHA.py:29-39 up to, not including, the host-side cv2 RANSAC).  N>1 = one process per GPU
-under torchrun; pairs are independent so every rank processes its own batch (weak scaling) and the
-only collective is the all-reduce of the count vector at the end of the timed region.
-Rank 0 prints ONE JSON line.
+A "step" is one pass of the hot path over one batch of synthetic image pairs per GPU, as the task the config names
+runs it in the reference (keypoint_bench_b200.pipeline.run_task):
+
+    cfg1  repeatability   detect x2 -> warp x2 -> val_key_points counting            (tasks/repeatability.py:95-122)
+    cfg2  MHA (headline)  detect x2 -> warp x2 -> sample + match the covisible keypoints (tasks/MHA.py:29-39,
+                          up to, not including, the host-side cv2 RANSAC)
+    cfg3 / cfg4  match    detect x2 -> sample + match ALL keypoints                  (tasks/AUC.py:115-120)
+    cfg5  stream          F+1 frames: every frame extracted once, matched with its predecessor
+                          (models/model_interface.py:217-228 + tasks/FundamentalMatrix.py:53-57)
+
+N>1 = one process per GPU under torchrun; pairs are independent so every rank processes its own batch (weak scaling;
+cfg5: contiguous frame chunks with a one-frame halo) and the only collective is the all-reduce of the count vector at
+the end of the timed region.  The default run times the headline config (cfg2) in full -- device-timed value, e2e with
+host buffers, roofline of the dominant kernel, CPU baseline -- and then every other config briefly (`configs` key),
+because the driver's command line cannot pass --config.  Rank 0 prints ONE JSON line.
 """
 from __future__ import annotations
 
@@ -30,6 +39,8 @@ if ROOT not in sys.path:
 
 METRIC = 'image pairs/sec (extract+match)'
 UNIT = 'pairs/s'
+HEADLINE = 'cfg2'
+STREAM_SEED = 5150
 
 
 def parse_args():
@@ -38,61 +49,17 @@ def parse_args():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--config', default='cfg2', help='cfg1..cfg5 (BASELINE.json configs); cfg2 is the headline')
+    ap.add_argument('--config', default=HEADLINE, help='cfg1..cfg5 (BASELINE.json configs); cfg2 is the headline')
     ap.add_argument('--pairs', type=int, default=0, help='pairs per GPU per step (0 = config default)')
     ap.add_argument('--algo', type=int, default=-1, help='matcher: 0 = float64 SIMT, 1 = tcgen05; -1 = best available')
     ap.add_argument('--kind', default='uniform', help='synthetic score-map kind (uniform | alike)')
     ap.add_argument('--cpu-pairs', type=int, default=2, help='pairs timed on the host for cpu_baseline (0 = skip)')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-others', action='store_true', help='skip the brief runs of the other four configs')
     ap.add_argument('--in-flight', type=int, default=3,
                     help='steps kept in flight (one CUDA graph + stream + batch per slot); 1 = strictly serial steps')
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel from Python instead of replaying a CUDA graph')
     return ap.parse_args()
-
-
-# ------------------------------------------------------------------------------------------------
-# synthetic batch (device)
-# ------------------------------------------------------------------------------------------------
-
-def make_batch(cfg, cfg_index, n_pairs, first_pair, device, kind='uniform'):
-    """P pairs resident on `device`, generated per SURVEY 8(d): score A, score B = nearest-warp of A,
-    unit-norm descriptor map A, map B = bilinear warp of A + 0.05 noise."""
-    from keypoint_bench_b200 import synth
-    from keypoint_bench_b200.pipeline import PairBatch
-    H, W = cfg.height, cfg.width
-    g = torch.Generator(device=device)
-    g.manual_seed(synth.pair_seed(cfg_index, first_pair))
-    hms = torch.stack([synth.homography(synth.pair_seed(cfg_index, first_pair + i) + 7) for i in range(n_pairs)])
-    if kind == 'uniform':
-        s0 = torch.rand(n_pairs, 1, H, W, generator=g, device=device)
-    else:
-        s0 = torch.cat([synth.score_map(kind, H, W, synth.pair_seed(cfg_index, first_pair + i), device)
-                        for i in range(n_pairs)])
-    s1 = torch.empty_like(s0)
-    chunk = 8
-    for i in range(0, n_pairs, chunk):
-        grids = torch.cat([synth._inverse_grid(hms[j], H, W, device) for j in range(i, min(i + chunk, n_pairs))])
-        s1[i:i + chunk] = torch.nn.functional.grid_sample(s0[i:i + chunk], grids, mode='nearest',
-                                                          padding_mode='zeros', align_corners=True)
-    desc = None
-    if cfg.desc_dim:
-        dh, dw = H // cfg.desc_stride, W // cfg.desc_stride
-        d0 = torch.nn.functional.normalize(torch.randn(n_pairs, cfg.desc_dim, dh, dw, generator=g, device=device), dim=1)
-        if not cfg.desc_normalized:
-            d0 = 2.67 * d0
-        d1 = torch.empty_like(d0)
-        for i in range(0, n_pairs, chunk):
-            grids = torch.cat([synth._inverse_grid(synth.rescale_homography(hms[j], cfg.desc_stride), dh, dw, device)
-                               for j in range(i, min(i + chunk, n_pairs))])
-            d1[i:i + chunk] = torch.nn.functional.grid_sample(d0[i:i + chunk], grids, mode='bilinear',
-                                                              padding_mode='zeros', align_corners=True)
-        d1 += 0.05 * torch.randn(d1.shape, generator=g, device=device)
-        desc = torch.cat([d0, d1])
-    h01 = hms.reshape(n_pairs, 9)
-    h10 = torch.linalg.inv(hms.double()).float().reshape(n_pairs, 9)
-    h33 = torch.cat([h01, h10]).to(device)
-    wh = torch.tensor([[float(W), float(H)]], device=device).expand(2 * n_pairs, 2).contiguous()
-    return PairBatch(score=torch.cat([s0, s1]), desc=desc, h33=h33, wh=wh, resize=512), hms
 
 
 class ClockSampler:
@@ -103,7 +70,6 @@ class ClockSampler:
 
     def __init__(self, device_index):
         self.proc = None
-        self.samples = []
         try:
             uuid = str(torch.cuda.get_device_properties(device_index).uuid)
             if not uuid.startswith('GPU-'):
@@ -143,26 +109,6 @@ class ClockSampler:
                 'samples': len(sm), 'reasons': sorted(reasons)}
 
 
-class StageTimer:
-    """CUDA-event timing of the pipeline stages on the launching (current) stream."""
-    def __init__(self):
-        self.events = []      # (name, event)
-        self.cur = None
-
-    def __call__(self, name):
-        ev = torch.cuda.Event(enable_timing=True)
-        ev.record()
-        self.events.append((name, ev))
-
-    def totals(self):
-        tot = {}
-        for (n0, e0), (n1, e1) in zip(self.events[:-1], self.events[1:]):
-            if n0 is None:
-                continue
-            tot[n0] = tot.get(n0, 0.0) + e0.elapsed_time(e1)
-        return tot
-
-
 def peaks():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(path):
@@ -173,149 +119,232 @@ def peaks():
     return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0, 'source': 'fallback'}
 
 
+def bind_to_gpu_cpus(local_rank):
+    """Pin this process to the cores NVML names as local to its GPU BEFORE pinned host buffers are allocated, so the
+    e2e copies read host memory of the GPU's own NUMA node.  Returns the number of cores bound (None if unavailable)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------------------------------------
-# CPU baseline: the reference's algorithm (oracle port) on the host
+# CPU side: the reference's algorithm (oracle port) on the host, one pair as the config's task runs it
 # ------------------------------------------------------------------------------------------------
 
 def cpu_pair(cfg, score0, score1, desc0, desc1, hm):
-    """One pair through the oracle exactly as the reference would run it on CPU: detection with the
-    im2col/argmax/col2im rounds (utils/extracter.py:49-98), warp, grid_sample, float64 cdist matcher."""
+    """One pair through the oracle exactly as the reference would run it on CPU: detection with the im2col / argmax /
+    col2im rounds (utils/extracter.py:49-98), then the task's own continuation."""
     from keypoint_bench_b200 import synth
     from oracle import ref_ops
     H, W = cfg.height, cfg.width
-    w01, w10 = synth.warp_params(hm, H, W)
     k0, _ = ref_ops.detection(score0, cfg.extractor_params, nms='im2col')
     k1, _ = ref_ops.detection(score1, cfg.extractor_params, nms='im2col')
-    k0c, _, ids0, _ = ref_ops.warp(k0, w01)
-    k1c, _, ids1, _ = ref_ops.warp(k1, w10)
-    pairs = None
-    if desc0 is not None and k0c.shape[0] and k1c.shape[0]:
-        _, _, pairs = ref_ops.brute_force_matcher(k0c, k1c, desc0, desc1, cfg.matcher_params)
-    return k0, k1, k0c, k1c, pairs
+    out = {'k0': k0, 'k1': k1}
+    if cfg.task == 'repeatability':
+        w01, w10 = synth.warp_params(hm, H, W)
+        out['rep'] = ref_ops.val_key_points(k0, k1, w01, w10, th=3)
+        return out
+    m0, m1 = k0, k1
+    if cfg.task == 'mha':                                       # tasks/MHA.py:33-34
+        w01, w10 = synth.warp_params(hm, H, W)
+        m0, _, _, _ = ref_ops.warp(k0, w01)
+        m1, _, _, _ = ref_ops.warp(k1, w10)
+    out['m0'], out['m1'] = m0, m1
+    if m0.shape[0] and m1.shape[0]:
+        out['d0'] = ref_ops.sample_brute_force(desc0, m0)
+        out['d1'] = ref_ops.sample_brute_force(desc1, m1)
+        out['pairs'] = ref_ops.match_descriptors(out['d0'], out['d1'], metric='euclidean', max_distance=cfg.max_distance,
+                                                 cross_check=cfg.cross_check)
+    return out
 
 
-def run_cpu(cfg, batch_cpu, hms, n_pairs):
-    torch.set_num_threads(os.cpu_count() or 1)
-    P = batch_cpu['score'].shape[0] // 2
-    t0 = time.perf_counter()
-    results = []
-    for i in range(n_pairs):
-        d0 = batch_cpu['desc'][i:i + 1].numpy() if batch_cpu['desc'] is not None else None
-        d1 = batch_cpu['desc'][P + i:P + i + 1].numpy() if batch_cpu['desc'] is not None else None
-        results.append(cpu_pair(cfg, batch_cpu['score'][i:i + 1], batch_cpu['score'][P + i:P + i + 1], d0, d1, hms[i]))
-    dt = time.perf_counter() - t0
-    return dt, results
-
-
-def main():
-    args = parse_args()
+def cpu_inputs(cfg, cfg_index, n_pairs, batch=None, hms=None):
+    """Host tensors of `n_pairs` pairs: (score0, score1, desc0, desc1, H) per pair.  `batch` (+ `hms`) = the device
+    batch the GPU arm processed: its first pairs are copied to the host so both sides see identical inputs; without
+    it the pairs are generated on the host (the reference arm)."""
     from keypoint_bench_b200 import synth
-    cfg = synth.CONFIGS[args.config]
-    cfg_index = int(args.config[3:])
-    rank = int(os.environ.get('RANK', 0))
-    local_rank = int(os.environ.get('LOCAL_RANK', 0))
-    world = int(os.environ.get('WORLD_SIZE', 1))
-    P = args.pairs or cfg.pairs_per_gpu
-    config = {'workload': cfg.name, 'pairs_per_gpu_per_step': P, 'height': cfg.height, 'width': cfg.width,
-              'desc_dim': cfg.desc_dim, 'desc_stride': cfg.desc_stride, 'nms_dist': cfg.nms_dist, 'top_k': cfg.top_k,
-              'border_dist': cfg.border_dist, 'max_distance': cfg.max_distance, 'cross_check': cfg.cross_check,
-              'score_map': args.kind, 'sharding': f'by-pair x{world}',
-              'timed_stages': 'detect x2, warp x2, sample x2, mutual-NN match (host cv2 RANSAC excluded)',
-              'l2': 'working set per step > 126 MB L2 (no flush needed)'}
+    if cfg.task == 'stream':
+        fr = batch if batch is not None else synth.make_frames(cfg, STREAM_SEED, 0, n_pairs + 1, n_pairs + 1, 'cpu')
+        sc, de = fr.score[:n_pairs + 1].cpu(), fr.desc[:n_pairs + 1].cpu()
+        return [(sc[i:i + 1], sc[i + 1:i + 2], de[i:i + 1].numpy(), de[i + 1:i + 2].numpy(), None) for i in range(n_pairs)]
+    if batch is None:
+        batch, hms = synth.make_batch(cfg, cfg_index, n_pairs, 0, 'cpu')
+    P = batch.pairs
+    idx = list(range(n_pairs)) + list(range(P, P + n_pairs))
+    sc = batch.score[idx].cpu()
+    de = None if batch.desc is None else batch.desc[idx].cpu()
+    n = n_pairs
+    return [(sc[i:i + 1], sc[n + i:n + i + 1], None if de is None else de[i:i + 1].numpy(),
+             None if de is None else de[n + i:n + i + 1].numpy(), hms[i].cpu()) for i in range(n)]
 
-    # -------------------------------------------------------------------------------- reference arm
-    if args.impl == 'reference':
-        if rank != 0:
-            return 0
-        dev = 'cpu'
-        batch, hms = make_batch(cfg, cfg_index, 1, 0, dev, args.kind)
-        bc = {'score': batch.score, 'desc': batch.desc}
-        for _ in range(min(args.warmup, 1)):                     # one warm pair is enough to page in torch
-            run_cpu(cfg, bc, hms, 1)
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            run_cpu(cfg, bc, hms, 1)
-        dt = time.perf_counter() - t0
-        value = args.steps / dt
-        line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
-                'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1000 * dt / args.steps,
-                'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32+f64',
-                'data': 'synthetic', 'config': dict(config, pairs_per_gpu_per_step=1),
-                'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
-                                 'sample': f'{args.steps} steps x 1 pair of {cfg.name} through oracle/ref_ops.py '
-                                           f'(im2col NMS rounds, grid_sample, scipy cdist float64)'},
-                'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-        print(json.dumps(line))
-        return 0
 
-    # -------------------------------------------------------------------------------- our arm
-    if not torch.cuda.is_available():
-        raise SystemExit('bench.py needs a CUDA device (no CPU fallback for the product path)')
-    from keypoint_bench_b200 import ops, parallel, pipeline
-    torch.cuda.set_device(local_rank)
-    device = torch.device('cuda', local_rank)
-    if world > 1:
-        parallel.init('nccl')
+def run_cpu(cfg, inputs):
+    torch.set_num_threads(os.cpu_count() or 1)
+    t0 = time.perf_counter()
+    results = [cpu_pair(cfg, *inp) for inp in inputs]
+    return time.perf_counter() - t0, results
+
+
+def base_config(cfg, P, world, kind):
+    return {'workload': cfg.name, 'task': cfg.task, 'pairs_per_gpu_per_step': P, 'height': cfg.height, 'width': cfg.width,
+            'desc_dim': cfg.desc_dim, 'desc_stride': cfg.desc_stride, 'nms_dist': cfg.nms_dist, 'top_k': cfg.top_k,
+            'border_dist': cfg.border_dist, 'max_distance': cfg.max_distance, 'cross_check': cfg.cross_check,
+            'score_map': kind, 'sharding': (f'contiguous frame chunks + 1-frame halo x{world}' if cfg.task == 'stream'
+                                            else f'by-pair x{world}'),
+            'timed_stages': {'repeatability': 'detect x2, warp x2, val_key_points counting',
+                             'mha': 'detect x2, warp x2, sample x2, mutual-NN match of the covisible keypoints (host cv2 RANSAC excluded)',
+                             'match': 'detect x2, sample x2, mutual-NN match of all keypoints',
+                             'stream': 'detect + sample once per frame, mutual-NN match of consecutive frames'}[cfg.task],
+            'l2': 'working set per step > 126 MB L2 (no flush needed)'}
+
+
+# ------------------------------------------------------------------------------------------------
+# one config on this rank's GPU
+# ------------------------------------------------------------------------------------------------
+
+def time_ms(fn, reps=5):
+    """`reps` back-to-back calls between two CUDA events on the launch (current) stream, after one warm call."""
+    from keypoint_bench_b200 import ops
+    with ops.no_zero_fill():
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def kernel_table(cfg, inputs, res, algo, tc, pk):
+    """Every kernel group of one step timed ALONE (5 back-to-back launches between CUDA events on the launch stream,
+    through the library's measurement hooks), with its algorithmic bytes / flops and roofline fraction.
+    Peaks: measured HBM copy bandwidth; bf16 BURST for the isolated tensor-core kernel."""
+    from keypoint_bench_b200 import ops
+    P = inputs.pairs
+    score, desc = inputs.score, inputs.desc
+    n_img = score.shape[0]
+    stream = cfg.task == 'stream'
+    k = {}
+    st = []
+    ops.detect_batched(score, cfg.extractor_params, state=st)
+    hbm_img = n_img * 4.0 * cfg.height * cfg.width
+    n_out = float(res['n_kpts'].float().sum().item())
+    k['detect.tau (threshold estimate)'] = {'ms': time_ms(lambda: ops.detect_batched(score, cfg.extractor_params, phases=1, state=st)),
+                                            'bound': 'latency'}
+    k['detect.round1 (NMS round 1, the one pass over the score maps)'] = {
+        'ms': time_ms(lambda: ops.detect_batched(score, cfg.extractor_params, phases=2, state=st)), 'bound': 'hbm',
+        'algorithmic_bytes': hbm_img}
+    ops.detect_batched(score, cfg.extractor_params, phases=7, state=st)      # (the lists the repeated round-1 launches grew) restored
+    k['detect.resolve (per-map greedy resolve + top-k sort + fallback stubs)'] = {
+        'ms': time_ms(lambda: ops.detect_batched(score, cfg.extractor_params, phases=4, state=st)), 'bound': 'latency',
+        'algorithmic_bytes': 16.0 * n_out}
+    k['detect (whole stage)'] = {'ms': time_ms(lambda: ops.detect_batched(score, cfg.extractor_params)), 'bound': 'hbm',
+                                 'algorithmic_bytes': hbm_img + 16.0 * n_out, 'stage': True}
+    pts, n_pts = res['kpts'], res['n_kpts']
+    if cfg.task in ('repeatability', 'mha'):
+        k['warp_homography'] = {'ms': time_ms(lambda: ops.warp_batched(res['kpts'], res['n_kpts'], inputs.h33, inputs.wh)),
+                                'bound': 'latency', 'algorithmic_bytes': 8.0 * n_out + 36.0 * n_img}
+        pts, n_pts = res['kcov'], res['n_cov']
+    if cfg.task == 'repeatability':
+        kv, kw, nv = res['kcov'], res['kwarp'], res['n_cov']
+        k['repeat_counts (val_key_points core)'] = {
+            'ms': time_ms(lambda: ops.repeat_batched(kv[:P], kw[:P], nv[:P], kv[P:], kw[P:], nv[P:], 512.0, 512.0, 3.0,
+                                                     want_errors=True)),
+            'bound': 'latency', 'algorithmic_bytes': 16.0 * float(nv.float().sum().item())}
+        return k
+    npts = float(n_pts.float().sum().item())
+    hw = (cfg.height // cfg.desc_stride) * (cfg.width // cfg.desc_stride)
+    k['sample (bilinear descriptor sampling)'] = {
+        'ms': time_ms(lambda: ops.sample_batched(desc, pts, n_pts)), 'bound': 'hbm',
+        'algorithmic_bytes': min(16 * npts * cfg.desc_dim, 4.0 * cfg.desc_dim * hw * n_img) + 4 * npts * cfg.desc_dim + 8 * npts,
+        'sector_bytes': (64.0 * npts * cfg.desc_dim if cfg.desc_stride == 1 else None)}
+    dd = res['desc']
+    a, b = (dd[:-1], dd[1:]) if stream else (dd[:P], dd[P:])
+    na, nb = (n_pts[:-1], n_pts[1:]) if stream else (n_pts[:P], n_pts[P:])
+    flops = float((2.0 * na.double() * nb.double() * cfg.desc_dim).sum().item())        # ONE pass of 2 n m D per pair
+    margs = (a, b, na, nb, cfg.max_distance, cfg.cross_check)
+    if tc:
+        mst = []
+        ops.match_batched(*margs, algo=1, state=mst, want_dist=False)
+        passes = ops.match_issue_factor(bool(cfg.cross_check))
+        k['match.prep (hi/lo bf16 split + norms)'] = {
+            'ms': time_ms(lambda: ops.match_batched(*margs, algo=1, phases=1, state=mst, want_dist=False)), 'bound': 'hbm',
+            'algorithmic_bytes': 0.0}
+        k['match.search (tcgen05 Gram + fused top-3 epilogue)'] = {
+            'ms': time_ms(lambda: ops.match_batched(*margs, algo=1, phases=2, state=mst, want_dist=False)), 'bound': 'tensor',
+            'algorithmic_flops': flops, 'issued_flops': flops * passes,
+            'issued_note': f'{passes}x the one-pass flops are issued to the tensor pipe (directions x split-bf16 passes)'}
+        k['match.tail (certify / rescan / gate / pairs)'] = {
+            'ms': time_ms(lambda: ops.match_batched(*margs, algo=1, phases=4, state=mst, want_dist=False)), 'bound': 'latency',
+            'algorithmic_bytes': 12.0 * float(res['n_matches'].float().sum().item())}
+    k['match (whole stage)'] = {'ms': time_ms(lambda: ops.match_batched(*margs, algo=algo, want_dist=False)),
+                                'bound': 'tensor', 'algorithmic_flops': flops, 'stage': True}
+    return k
+
+
+def finish_table(kernels, pk):
+    for v in kernels.values():
+        if v['bound'] == 'tensor':
+            v['achieved'] = v['algorithmic_flops'] / (v['ms'] / 1e3) / 1e12
+            v['unit'], v['peak'] = 'TFLOP/s', pk['bf16_tflops']           # burst: the kernel is timed alone
+        else:
+            v['achieved'] = v.get('algorithmic_bytes', 0.0) / (v['ms'] / 1e3) / 1e9
+            v['unit'], v['peak'] = 'GB/s', pk['hbm_gbs']
+        v['frac'] = v['achieved'] / v['peak']
+    single = {n: v for n, v in kernels.items() if not v.get('stage')}
+    return max(single, key=lambda n: single[n]['ms'])
+
+
+def run_config(args, name, rank, local_rank, world, device, full):
+    """Times one config on this rank.  full: headline treatment (stage table, e2e, CPU baseline)."""
+    from keypoint_bench_b200 import ops, parallel, pipeline, synth
+    cfg = synth.CONFIGS[name]
+    cfg_index = int(name[3:])
+    P = (args.pairs if full and args.pairs else cfg.pairs_per_gpu)
+    steps = args.steps if full else max(3, min(args.steps, 10))
+    config = base_config(cfg, P, world, args.kind)
     algo = args.algo
-    tc = algo == 1 or (algo < 0 and cfg.desc_dim <= 256)
-    config['matcher'] = 'tcgen05 split-bf16 Gram + float64 certify' if tc else 'float64 SIMT'
+    tc = cfg.desc_dim > 0 and (algo == 1 or (algo < 0 and cfg.desc_dim <= 256))
+    if cfg.desc_dim:
+        config['matcher'] = 'tcgen05 split-bf16 Gram + float64 certify' if tc else 'float64 SIMT'
+    stream = cfg.task == 'stream'
+    depth = 1 if args.no_graph else max(1, args.in_flight)
+    total_frames = world * P + 1                                  # one sequence per step slot, sharded over the ranks
 
-    batch, hms = make_batch(cfg, cfg_index, P, rank * P, device, args.kind)
-    task_rep = cfg.desc_dim == 0
+    hms_of = {}
 
-    def step(timer=None, b=None):
-        b = batch if b is None else b
-        if task_rep:
-            res = pipeline.repeatability_counts(b, cfg, 3.0, timer)
-            return res, pipeline.accumulate_repeatability(res)
-        res = pipeline.extract_match(b, cfg, algo=algo, timer=timer)
-        return res, pipeline.accumulate_matches(res)
+    def make_inputs(slot):
+        if stream:
+            lo, hi = parallel.shard_stream(total_frames, rank, world)
+            return synth.make_frames(cfg, STREAM_SEED + slot, lo, hi - lo, total_frames, device)
+        b, hms_of[slot] = synth.make_batch(cfg, cfg_index, P, (rank + world * slot) * P, device, args.kind)
+        return b
 
-    sampler = ClockSampler(local_rank)
+    inputs = make_inputs(0)
+
+    def step(b=None, timer=None):
+        return pipeline.run_task(inputs if b is None else b, cfg, algo=algo, timer=timer)
+
     for _ in range(max(args.warmup, 3)):
         step()
     torch.cuda.synchronize()
-    # per-stage device times: every stage alone, 5 back-to-back calls between two CUDA events on the launch
-    # stream (the stage's kernels queue up behind each other, so host launch gaps do not count)
     l0 = ops.launches()
     res0, _ = step()
     launches_per_step = ops.launches() - l0
     torch.cuda.synchronize()
 
-    def time_stage(fn, reps=5):
-        # like the pipeline (pipeline.extract_match), outputs are not zero-filled: the fill kernels of a
-        # 131 MB descriptor buffer would otherwise be charged to the sampling stage
-        with ops.no_zero_fill():
-            fn()
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(reps):
-                fn()
-            e1.record()
-            torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / reps
-
-    stage_ms = {'detect': time_stage(lambda: ops.detect_batched(batch.score, cfg.extractor_params)),
-                'warp': time_stage(lambda: ops.warp_batched(res0['kpts'], res0['n_kpts'], batch.h33, batch.wh))}
-    if task_rep:
-        kv, kw, nv = res0['kcov'], res0['kwarp'], res0['n_cov']
-        stage_ms['repeat'] = time_stage(lambda: ops.repeat_batched(kv[:P], kw[:P], nv[:P], kv[P:], kw[P:], nv[P:], 512.0,
-                                                                   512.0, 3.0, want_errors=True))
-    else:
-        kv, nv, dd = res0['kcov'], res0['n_cov'], res0['desc']
-        stage_ms['sample'] = time_stage(lambda: ops.sample_batched(batch.desc, kv, nv))
-        stage_ms['match'] = time_stage(lambda: ops.match_batched(dd[:P], dd[P:], nv[:P], nv[P:], cfg.max_distance,
-                                                                 cfg.cross_check, algo=algo, want_dist=False))
-    # steady state: the launch sequence of one step replayed as a CUDA graph (same kernels, same buffers);
-    # `--in-flight` slots, each with its own batch, graph and stream, so consecutive steps overlap
-    depth = 1 if args.no_graph else max(1, args.in_flight)
-    batches = [batch] + [make_batch(cfg, cfg_index, P, (rank + world * s) * P, device, args.kind)[0]
-                         for s in range(1, depth)]
+    batches = [inputs] + [make_inputs(s) for s in range(1, depth)]
     graphed = flight = None
     if not args.no_graph:
         try:
-            flight = pipeline.StepsInFlight([(lambda b=b: step(None, b)) for b in batches])
+            flight = pipeline.StepsInFlight([(lambda b=b: step(b)) for b in batches])
             graphed = flight.slots[0]
         except Exception as e:      # noqa: BLE001 -- fall back to eager launches, say so in the JSON line
             config['cuda_graph_error'] = repr(e)[:200]
@@ -366,174 +395,261 @@ def main():
     timed_steps(2 * depth, True)                      # graph / stream warm-up
     serial_ms = None
     if depth > 1:
-        serial_ms, _ = timed_steps(args.steps, False)  # the same steps strictly one after another, for reference
-    ms, acc = timed_steps(args.steps, True)
-    value = world * P * args.steps / (ms / 1000.0)
-    n_launch = launches_per_step * args.steps
-    res, _ = run()                                     # slot 0 = `batch`: the outputs checked against the CPU port below
+        serial_ms, _ = timed_steps(steps, False)      # the same steps strictly one after another, for reference
+    ms, acc = timed_steps(steps, True)
+    value = world * P * steps / (ms / 1000.0)
+    res, _ = run()                                    # slot 0: the outputs checked against the CPU port below
     torch.cuda.synchronize()
+    out = {'config': config, 'value': value, 'ms_per_step': ms / steps, 'steps': steps, 'pairs_per_step': world * P,
+           'gpu_launches': launches_per_step * steps,
+           'counts': {'sum_matches_or_rep': float(acc[0]), 'pairs': float(acc[1])}}
+    if serial_ms is not None:
+        out['serial'] = {'ms_per_step': serial_ms / steps, 'value': world * P * steps / (serial_ms / 1000.0)}
 
-    # ---- end to end through the public API with HOST buffers -----------------------------------
-    e2e = None
-    if not args.no_e2e:
-        # every slot: pinned host inputs -> device copy -> the step's graph -> device -> pinned host results, all on the
-        # slot's stream; the host waits for a slot's previous results before it relaunches that slot (the caller
-        # consumes the result of every step), so with two slots one step's copies overlap the other's kernels
-        top = cfg.top_k
-        in_bytes = batch.score.numel() * 4 + (batch.desc.numel() * 4 if batch.desc is not None else 0)
-        slots = []
-        for k, bk in enumerate(batches):
-            share = k > 0 and in_bytes > (2 << 30)     # do not pin a second multi-GB host copy: reuse slot 0's
-            sl = {'host_score': slots[0]['host_score'] if share else bk.score.cpu().pin_memory(),
-                  'host_desc': None if bk.desc is None else (slots[0]['host_desc'] if share else bk.desc.cpu().pin_memory()),
-                  'dev_score': torch.empty_like(bk.score),
-                  'dev_desc': torch.empty_like(bk.desc) if bk.desc is not None else None,
-                  'out_pairs': torch.empty((P, top, 2), dtype=torch.int32).pin_memory(),
-                  'out_n': torch.empty((P,), dtype=torch.int32).pin_memory(),
-                  'out_stats': torch.empty((P, 4), dtype=torch.float64).pin_memory(),
-                  'done': torch.cuda.Event()}
-            sl['batch'] = pipeline.PairBatch(sl['dev_score'], sl['dev_desc'], bk.h33, bk.wh, bk.resize)
-            slots.append(sl)
-        e2e_flight = None
-        if flight is not None:
-            try:
-                e2e_flight = pipeline.StepsInFlight([(lambda b=sl['batch']: step(None, b)) for sl in slots])
-            except Exception:       # noqa: BLE001
-                e2e_flight = None
-                torch.cuda.synchronize()
+    # ---- cfg5 on N ranks: the reduced match count equals a single-rank run over the same frames ----------------
+    if stream:
+        _, acc1 = timed_steps(1, False)               # one step of slot 0 on every rank, reduced: [sum matches, pairs]
+        if rank == 0:
+            # the same sequence on rank 0 alone, cut into chunks that do NOT coincide with the rank shards
+            tot, npairs, n_chunks = 0.0, 0, 2 * world + 1
+            for c in range(n_chunks):
+                lo, hi = parallel.shard_stream(total_frames, c, n_chunks)
+                if hi - lo < 2:
+                    continue
+                fr = synth.make_frames(cfg, STREAM_SEED, lo, hi - lo, total_frames, device)
+                r1, a1 = pipeline.run_task(fr, cfg, algo=algo)
+                tot += float(a1[0]); npairs += int(a1[1])
+                del fr, r1
+            out['stream_check'] = {'frames': total_frames, 'ranks': world, 'reduced_matches': float(acc1[0]),
+                                   'reduced_pairs': float(acc1[1]), 'single_rank_matches': tot, 'single_rank_pairs': npairs,
+                                   'equal': bool(tot == float(acc1[0]) and npairs == int(acc1[1]))}
 
-        def copy_in(k):
-            sl = slots[k]
-            sl['dev_score'].copy_(sl['host_score'], non_blocking=True)
-            if sl['dev_desc'] is not None:
-                sl['dev_desc'].copy_(sl['host_desc'], non_blocking=True)
-
-        def copy_out(k, out):
-            sl, r = slots[k], out[0]
-            if task_rep:
-                sl['out_stats'].copy_(r['stats'], non_blocking=True)
-            else:
-                sl['out_pairs'].copy_(r['matches'], non_blocking=True)
-                sl['out_n'].copy_(r['n_matches'], non_blocking=True)
-            sl['done'].record()
-
-        def e2e_steps_run(n_steps):
-            if e2e_flight is not None:
-                e2e_flight.fork()
-                for i in range(n_steps):
-                    if i >= depth:
-                        slots[i % depth]['done'].synchronize()      # results of this slot's previous step are consumed
-                    e2e_flight.launch(i, before=copy_in, after=copy_out)
-                e2e_flight.join()
-                torch.cuda.synchronize()
-            else:
-                for _ in range(n_steps):
-                    copy_in(0)
-                    copy_out(0, step(None, slots[0]['batch']))
-                    torch.cuda.synchronize()
-
-        e2e_steps = max(3, min(args.steps, 10))
-        e2e_steps_run(depth)
-        parallel.barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        e2e_steps_run(e2e_steps)
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device=device)
-            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-            dt = float(t.item())
-        h2d = in_bytes
-        d2h = slots[0]['out_stats'].numel() * 8 if task_rep else (slots[0]['out_pairs'].numel() * 4 +
-                                                                 slots[0]['out_n'].numel() * 4)
-        e2e = {'value': world * P * e2e_steps / dt, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-               'steps': e2e_steps, 'steps_in_flight': depth if e2e_flight is not None else 1,
-               'note': 'pinned host -> device copy of score+descriptor maps, hot path, device -> host copy of match '
-                       'index pairs and counts, every step; the host waits for a slot\'s results before reusing the slot'}
-    clocks = sampler.stop()
+    # ---- end to end through the public API with HOST buffers (headline only) -----------------------------------
+    if full and not args.no_e2e and not stream:
+        out['e2e'] = run_e2e(args, cfg, batches, step, flight, depth, P, world, device, cfg.task == 'repeatability')
 
     if rank != 0:
-        parallel.shutdown()
-        return 0
+        return out
 
-    # ---- roofline of the dominant kernel ---------------------------------------------------------
+    # ---- per-kernel table + roofline of the dominant kernel ----------------------------------------------------
     pk = peaks()
-    n_img = 2 * P
-    n_out = float(res['n_kpts'].float().mean().item())
-    # the detect stage is tau + round-1 + resolve: its streaming kernel (round1_kernel) is timed alone
-    st = []
-    ops.detect_batched(batch.score, cfg.extractor_params, state=st)
-    round1_ms = time_stage(lambda: ops.detect_batched(batch.score, cfg.extractor_params, phases=2, state=st))
-    kernels = {'round1_kernel (detect, streaming NMS round 1)': {
-        'ms': round1_ms, 'bound': 'hbm', 'algorithmic_bytes': n_img * 4.0 * cfg.height * cfg.width}}
-    if not task_rep:
-        npts = float(res['n_cov'].float().sum().item())
-        hw = (cfg.height // cfg.desc_stride) * (cfg.width // cfg.desc_stride)
-        kernels['sample kernel'] = {'ms': stage_ms['sample'], 'bound': 'hbm', 'algorithmic_bytes':
-                                    min(16 * npts * cfg.desc_dim, 4.0 * cfg.desc_dim * hw * n_img) + 4 * npts * cfg.desc_dim + 8 * npts}
-        ncov = res['n_cov'].float()
-        flops = float((2.0 * ncov[:P] * ncov[P:] * cfg.desc_dim).sum().item()) * (2 if cfg.cross_check else 1)
-        if tc:      # the tcgen05 search kernel alone (kb_match_mnn_phases), on the buffers of a full call
-            mst = []
-            margs = (res['desc'][:P], res['desc'][P:], res['n_cov'][:P], res['n_cov'][P:], cfg.max_distance, cfg.cross_check)
-            ops.match_batched(*margs, algo=1, state=mst, want_dist=False)
-            top2_ms = time_stage(lambda: ops.match_batched(*margs, algo=1, phases=2, state=mst, want_dist=False))
-            kernels['nn_top2_kernel (match, tcgen05 Gram + fused top-3 epilogue)'] = {
-                'ms': top2_ms, 'bound': 'tensor', 'algorithmic_flops': flops}
-        else:
-            kernels['match stage (float64 SIMT)'] = {'ms': stage_ms['match'], 'bound': 'tensor', 'algorithmic_flops': flops}
-    for k in kernels.values():
-        if k['bound'] == 'hbm':
-            k['achieved'] = k['algorithmic_bytes'] / (k['ms'] / 1e3) / 1e9
-            k['unit'], k['peak'] = 'GB/s', pk['hbm_gbs']
-        else:
-            k['achieved'] = k['algorithmic_flops'] / (k['ms'] / 1e3) / 1e12
-            k['unit'], k['peak'] = 'TFLOP/s', pk['bf16_tflops_sustained']
-        k['frac'] = k['achieved'] / k['peak']
-    dom = max(kernels, key=lambda n: kernels[n]['ms'])
-    # ncu --set full figures captured for this workload (profiles/traffic.json): DRAM bytes per launch, tensor-pipe %
+    kernels = kernel_table(cfg, inputs, res, algo, tc, pk)
+    dom = finish_table(kernels, pk)
     traffic = None
     tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
     if os.path.exists(tpath):
         with open(tpath) as f:
             tj = json.load(f)
-        for name, k in kernels.items():
-            t = tj.get(name.split(' ')[0].replace('sample', 'sample_planes_kernel') if name.startswith('sample') else name.split(' ')[0], {})
-            if t.get('workload') == cfg.name and t.get('maps') == n_img:
-                k['ncu'] = {kk: vv for kk, vv in t.items() if kk not in ('workload', 'maps', 'source')}
-                if name == dom:
+        for kn, kv in kernels.items():
+            t = tj.get(kn.split(' ')[0], {})
+            if t.get('workload') == cfg.name and t.get('maps') == inputs.score.shape[0]:
+                kv['ncu'] = {kk: vv for kk, vv in t.items() if kk not in ('workload', 'maps', 'source')}
+                if kn == dom:
                     traffic = t.get('dram_bytes_per_launch')
     d = kernels[dom]
-    roof = {'kernel': dom, 'bound': d['bound'], 'achieved': d['achieved'], 'peak': d['peak'], 'unit': d['unit'],
-            'frac': d['frac'], 'traffic': traffic, 'stage_ms': stage_ms, 'kernels': kernels,
-            'note': f'algorithmic bytes (or one-pass 2nmD flops per direction) of one launch / CUDA-event time of the kernel '
-                    f'launched alone 5x back to back; peaks {pk["source"]} (HBM copy, bf16 sustained); traffic = dram bytes of '
-                    f'one ncu --set full capture (profiles/)'}
+    out['roofline'] = {
+        'kernel': dom, 'bound': 'tensor' if d['bound'] == 'tensor' else 'hbm', 'achieved': d['achieved'], 'peak': d['peak'],
+        'unit': d['unit'], 'frac': d['frac'], 'traffic': traffic, 'kernels': kernels,
+        'note': f'dominant = the kernel group with the largest CUDA-event time when launched alone 5x back to back (every '
+                f'group of the step is timed); achieved = algorithmic bytes, or ONE pass of 2nmD flops per pair, per launch / '
+                f'that time; peaks {pk["source"]}: HBM copy {pk["hbm_gbs"]:.0f} GB/s, bf16 burst {pk["bf16_tflops"]:.0f} TFLOP/s '
+                f'(isolated kernel); traffic = dram bytes of one ncu --set full capture (profiles/)'}
 
-    # ---- CPU baseline on a bounded sample + parity spot check ------------------------------------
-    cpu = None
-    if world == 1 and args.cpu_pairs > 0:
-        bc = {'score': batch.score.cpu(), 'desc': batch.desc.cpu() if batch.desc is not None else None}
-        dt, results = run_cpu(cfg, bc, hms, args.cpu_pairs)
-        ok = True
-        for i, (k0, k1, k0c, k1c, pairs) in enumerate(results):
-            n0 = int(res['n_kpts'][i])
-            ok &= bool(np.array_equal(np.sort(res['kpts'][i, :n0, 2].cpu().numpy()), np.sort(k0[:, 2])))
-            if pairs is not None:
-                got = res['matches'][i, :int(res['n_matches'][i])].cpu().numpy()
-                ok &= bool(abs(got.shape[0] - pairs.shape[0]) <= 2)
-        cpu = {'value': args.cpu_pairs / dt, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
-               'sample': f'{args.cpu_pairs} pairs of {cfg.name} through oracle/ref_ops.py (the reference\'s im2col NMS '
-                         f'rounds, grid_sample, scipy float64 cdist); scipy cdist is single-threaded',
-               'gpu_matches_oracle_on_sample': ok}
+    # ---- CPU baseline on a bounded sample + exact parity check of that sample ----------------------------------
+    if full and world == 1 and args.cpu_pairs > 0:
+        out['cpu_baseline'] = cpu_baseline(cfg, cfg_index, args.cpu_pairs, res, P, inputs, hms_of.get(0))
+    return out
 
-    line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
-            'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': 'f32+f64', 'data': 'synthetic', 'config': config, 'clocks': clocks,
-            'e2e': e2e, 'gpu_launches': n_launch, 'roofline': roof, 'cpu_baseline': cpu,
-            'counts': {'sum_matches_or_rep': float(acc[0]), 'pairs': float(acc[1])}}
-    if serial_ms is not None:       # the same K steps strictly one after another (what the per-kernel shares refer to)
-        line['serial'] = {'ms_per_step': serial_ms / args.steps, 'value': world * P * args.steps / (serial_ms / 1000.0)}
+
+def cpu_baseline(cfg, cfg_index, n_pairs, res, P, batch, hms):
+    """The oracle port timed on `n_pairs` pairs of the batch the GPU just processed (same seeds), and an EXACT check of
+    the GPU outputs on them: keypoint rows of both images and the match pair sets (modulo north_star's 1e-5 near-tie
+    rule, evaluated on float64 distances)."""
+    from oracle.compare import check_detection_rows, exact_pairs_or_near_tie
+    stream = cfg.task == 'stream'
+    inputs = cpu_inputs(cfg, cfg_index, n_pairs, batch, hms)
+    dt, results = run_cpu(cfg, inputs)
+    ok, why = True, None
+    try:
+        for i, r in enumerate(results):
+            i0, i1 = (i, i + 1) if stream else (i, P + i)
+            for idx, want in ((i0, r['k0']), (i1, r['k1'])):
+                n = int(res['n_kpts'][idx])
+                check_detection_rows(res['kpts'][idx, :n].cpu().numpy(), want)
+            if cfg.task == 'repeatability':
+                st = res['stats'][i].cpu().numpy()
+                assert int(st[0]) == r['rep']['gt_num'] and int(res['num_feat'][i]) == r['rep']['num_feat'], (st, r['rep']['gt_num'])
+            elif 'pairs' in r:
+                got = res['matches'][i, :int(res['n_matches'][i])].cpu().numpy().astype(np.int64)
+                exact_pairs_or_near_tie(got, r['d0'], r['d1'], cfg.max_distance, cfg.cross_check)
+    except AssertionError as e:
+        ok, why = False, repr(e)[:300]
+    cpu = {'value': n_pairs / dt, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
+           'sample': f'{n_pairs} pairs of {cfg.name} through oracle/ref_ops.py (the reference\'s im2col NMS rounds, '
+                     f'grid_sample, scipy float64 cdist); scipy cdist is single-threaded',
+           'gpu_matches_oracle_on_sample': ok,
+           'check': 'exact keypoint rows of both images and exact match pairs (1e-5 near-tie rule) / exact gt_num, num_feat'}
+    if why:
+        cpu['mismatch'] = why
+    return cpu
+
+
+def run_e2e(args, cfg, batches, step, flight, depth, P, world, device, task_rep):
+    """Every slot: pinned host inputs -> device copy -> the step's graph -> device -> pinned host results, all on the
+    slot's stream; the host waits for a slot's previous results before it relaunches that slot (the caller consumes the
+    result of every step), so with several slots one step's copies overlap another's kernels."""
+    from keypoint_bench_b200 import parallel, pipeline
+    top = cfg.top_k
+    batch = batches[0]
+    in_bytes = batch.score.numel() * 4 + (batch.desc.numel() * 4 if batch.desc is not None else 0)
+    share_host = in_bytes > (256 << 20)        # one pinned copy of large inputs serves every slot (the bytes copied are the same)
+    slots = []
+    for k, bk in enumerate(batches):
+        share = k > 0 and share_host
+        sl = {'host_score': slots[0]['host_score'] if share else bk.score.cpu().pin_memory(),
+              'host_desc': None if bk.desc is None else (slots[0]['host_desc'] if share else bk.desc.cpu().pin_memory()),
+              'dev_score': torch.empty_like(bk.score),
+              'dev_desc': torch.empty_like(bk.desc) if bk.desc is not None else None,
+              'out_pairs': torch.empty((P, top, 2), dtype=torch.int32).pin_memory(),
+              'out_n': torch.empty((P,), dtype=torch.int32).pin_memory(),
+              'out_stats': torch.empty((P, 4), dtype=torch.float64).pin_memory(),
+              'done': torch.cuda.Event()}
+        sl['batch'] = pipeline.PairBatch(sl['dev_score'], sl['dev_desc'], bk.h33, bk.wh, bk.resize)
+        slots.append(sl)
+    e2e_flight = None
+    if flight is not None:
+        try:
+            e2e_flight = pipeline.StepsInFlight([(lambda b=sl['batch']: step(b)) for sl in slots])
+        except Exception:       # noqa: BLE001
+            e2e_flight = None
+            torch.cuda.synchronize()
+
+    def copy_in(k):
+        sl = slots[k]
+        sl['dev_score'].copy_(sl['host_score'], non_blocking=True)
+        if sl['dev_desc'] is not None:
+            sl['dev_desc'].copy_(sl['host_desc'], non_blocking=True)
+
+    def copy_out(k, out):
+        sl, r = slots[k], out[0]
+        if task_rep:
+            sl['out_stats'].copy_(r['stats'], non_blocking=True)
+        else:
+            sl['out_pairs'].copy_(r['matches'], non_blocking=True)
+            sl['out_n'].copy_(r['n_matches'], non_blocking=True)
+        sl['done'].record()
+
+    def e2e_steps_run(n_steps):
+        if e2e_flight is not None:
+            e2e_flight.fork()
+            for i in range(n_steps):
+                if i >= depth:
+                    slots[i % depth]['done'].synchronize()      # results of this slot's previous step are consumed
+                e2e_flight.launch(i, before=copy_in, after=copy_out)
+            e2e_flight.join()
+            torch.cuda.synchronize()
+        else:
+            for _ in range(n_steps):
+                copy_in(0)
+                copy_out(0, step(slots[0]['batch']))
+                torch.cuda.synchronize()
+
+    e2e_steps = max(3, min(args.steps, 10))
+    e2e_steps_run(depth)
+    parallel.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e2e_steps_run(e2e_steps)
+    dt_rank = time.perf_counter() - t0
+    dt = dt_rank
+    if world > 1:
+        t = torch.tensor([dt], dtype=torch.float64, device=device)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        dt = float(t.item())
+    d2h = slots[0]['out_stats'].numel() * 8 if task_rep else (slots[0]['out_pairs'].numel() * 4 + slots[0]['out_n'].numel() * 4)
+    return {'value': world * P * e2e_steps / dt, 'unit': UNIT, 'h2d_bytes_per_step': in_bytes, 'd2h_bytes_per_step': d2h,
+            'steps': e2e_steps, 'steps_in_flight': depth if e2e_flight is not None else 1,
+            'h2d_gbs_this_rank': in_bytes * e2e_steps / dt_rank / 1e9,
+            'pinned_host_copies': 1 if share_host else depth,
+            'note': 'pinned host -> device copy of score+descriptor maps, hot path, device -> host copy of match '
+                    'index pairs and counts, every step; the host waits for a slot\'s results before reusing the slot; '
+                    'this number is the H2D link (PCIe), not the kernels'}
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get('RANK', 0))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+
+    # -------------------------------------------------------------------------------- reference arm
+    if args.impl == 'reference':
+        # the reference's own CPU algorithm through the oracle port; nothing of the product (no CUDA library) is loaded
+        if rank != 0:
+            return 0
+        from keypoint_bench_b200 import synth
+        cfg = synth.CONFIGS[args.config]
+        inputs = cpu_inputs(cfg, int(args.config[3:]), 1)
+        for _ in range(min(args.warmup, 1)):                     # one warm pair is enough to page in torch
+            run_cpu(cfg, inputs)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            run_cpu(cfg, inputs)
+        dt = time.perf_counter() - t0
+        value = args.steps / dt
+        line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+                'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1000 * dt / args.steps,
+                'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32+f64',
+                'data': 'synthetic', 'config': dict(base_config(cfg, 1, 1, args.kind), pairs_per_gpu_per_step=1),
+                'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
+                                 'sample': f'{args.steps} steps x 1 pair of {cfg.name} through oracle/ref_ops.py '
+                                           f'(im2col NMS rounds, grid_sample, scipy cdist float64)'},
+                'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+                'product_library_loaded': 'keypoint_bench_b200._lib' in sys.modules}
+        print(json.dumps(line))
+        return 0
+
+    # -------------------------------------------------------------------------------- our arm
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device (no CPU fallback for the product path)')
+    bound = bind_to_gpu_cpus(local_rank)
+    from keypoint_bench_b200 import parallel
+    torch.cuda.set_device(local_rank)
+    device = torch.device('cuda', local_rank)
+    if world > 1:
+        parallel.init('nccl')
+    sampler = ClockSampler(local_rank)
+    head = run_config(args, args.config, rank, local_rank, world, device, full=True)
+    clocks = sampler.stop()
+    others = {}
+    if not args.no_others and args.config == HEADLINE:
+        for name in ('cfg1', 'cfg3', 'cfg4', 'cfg5'):
+            torch.cuda.empty_cache()
+            r = run_config(args, name, rank, local_rank, world, device, full=False)
+            roof = r.get('roofline')
+            others[name] = {'workload': r['config']['workload'], 'task': r['config']['task'], 'value': r['value'], 'unit': UNIT,
+                            'ms_per_step': r['ms_per_step'], 'steps': r['steps'], 'pairs_per_step': r['pairs_per_step'],
+                            'serial': r.get('serial'), 'counts': r['counts'], 'stream_check': r.get('stream_check'),
+                            'roofline': None if roof is None else {
+                                'kernel': roof['kernel'], 'bound': roof['bound'], 'achieved': roof['achieved'], 'peak': roof['peak'],
+                                'unit': roof['unit'], 'frac': roof['frac'],
+                                'kernels': {k: {kk: v[kk] for kk in ('ms', 'bound', 'achieved', 'unit', 'frac') if kk in v}
+                                            for k, v in roof['kernels'].items()}}}
+    if rank != 0:
+        parallel.shutdown()
+        return 0
+    cfg_line = dict(head['config'])
+    cfg_line['cpu_affinity_cores'] = bound
+    line = {'metric': METRIC, 'value': head['value'], 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(args.warmup, 3), 'ms_per_step': head['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32+f64', 'data': 'synthetic', 'config': cfg_line, 'clocks': clocks,
+            'e2e': head.get('e2e'), 'gpu_launches': head['gpu_launches'], 'roofline': head.get('roofline'),
+            'cpu_baseline': head.get('cpu_baseline'), 'counts': head['counts']}
+    for k in ('serial', 'stream_check'):
+        if head.get(k) is not None:
+            line[k] = head[k]
+    if others:
+        line['configs'] = others
     print(json.dumps(line))
     parallel.shutdown()
     return 0

@@ -27,36 +27,9 @@
 // priority) or when its candidate lists were complete (K <= top_k: raster order, extracter.py:217).
 // Anything else (negative scores, list overflow, nms_dist > 8) is flagged on the device for the
 // round-faithful kernel (kb_nms.cu), so results are exact in all cases.
-#include "kb_common.cuh"
+#include "kb_sparse.cuh"
 
 namespace kbsparse {
-
-constexpr int SAMPLES = 4096;
-constexpr int TAU_NT = 256;
-constexpr int DTH = 32, DTW = 128, DNT = 256;     // round-1 tile
-constexpr int SP_NT = 1024;                       // sparse kernel threads
-constexpr int MAX_CELLS = 8192;
-constexpr int LIST_CAP = 16384;                   // entries per list and map
-constexpr int SMEM_CAP = 12288;                   // candidates resolved in shared memory per map
-
-struct SparseParams {
-    const float* score;       // [B,H,W]
-    float* tau;               // [B]
-    uint64_t* listM;          // [B,LIST_CAP] round-1 maxima above tau
-    uint64_t* listO;          // [B,LIST_CAP] uncovered pixels above tau
-    int* cntM;                // [B]
-    int* cntO;                // [B]
-    int* flags;               // [B] bit0: has negative score
-    int* need_fallback;       // [B] (out) 1 = run the round-faithful path for this map
-    int* any_fallback;        // [1]
-    float* xyp;               // [B,top_k,3]
-    int* raster;              // [B,top_k]
-    int* count;               // [B]
-    int* path;                // [B] or null
-    int B, H, W, r, border, top_k, c_pix;
-    int cell_shift, gw, gh;   // coarse grid of the sparse stage
-    float threshold, min_score;
-};
 
 // ------------------------------------------------------------------------------------------------
 // tau: the rank-th largest of 4096 sampled pixels (bitwise counting select, no atomics)
@@ -578,7 +551,8 @@ __global__ void __launch_bounds__(SP_NT, 1) sparse_kernel(SparseParams p) {
                 const int idx = base + threadIdx.x;
                 uint64_t key = 0ull;
                 bool take = false;
-                if (idx < n) { key = L[idx]; take = (uint32_t)(key >> 32) >= tkey; }
+                // (the streaming round-1 kernel pads the blocks a warp reserved with null keys)
+                if (idx < n) { key = L[idx]; take = key != 0ull && (uint32_t)(key >> 32) >= tkey; }
                 int tot;
                 const int off = c + kb::block_exclusive_scan(take ? 1 : 0, s_scan, &tot);
                 if (take && off < SMEM_CAP) {
@@ -829,8 +803,11 @@ int kb_sparse_detect(const float* score, int B, int H, int W, int nms_dist, int 
         tau_kernel<<<B, TAU_NT, 0, st>>>(p);
         KB_LAUNCH_CHECK();
     }
+    // Round 1 has two kernels with identical lists: the tiled round1_kernel (default) and the full-width streaming
+    // kernel of kb_round1_stream.cu (phases bit 4; measured equal at 480x640 r = 6, slower elsewhere -- DESIGN.md).
     int rc = (phases & 2) ? KB_ERR_UNSUPPORTED : KB_OK;
-    if (phases & 2) switch (nms_dist) {
+    if ((phases & 2) && (phases & 16)) rc = launch_round1_stream(p, true, st);
+    if ((phases & 2) && rc == KB_ERR_UNSUPPORTED) switch (nms_dist) {
         case 1: rc = launch_round1<1>(p, st); break;
         case 2: rc = launch_round1<2>(p, st); break;
         case 3: rc = launch_round1<3>(p, st); break;

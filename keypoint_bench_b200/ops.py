@@ -148,7 +148,8 @@ def detect_batched(score: torch.Tensor, params: dict | None = None, phases: int 
     """``detection`` (utils/extracter.py:193-221) for every map of the batch independently.
     -> xyp[B,top_k,3] (x,y,p), count[B], raster[B,top_k], path[B].
     ``phases`` / ``state`` are a measurement hook (bench.py): ``state=[]`` receives the buffers of a full call,
-    a later call with the same ``state`` and ``phases`` in {1,2,4} re-runs just that kernel on them."""
+    a later call with the same ``state`` and ``phases`` in {1,2,4} re-runs just that kernel on them; ``phases | 8`` /
+    ``phases | 16`` force the tiled / the streaming round-1 kernel (identical output, include/kb_b200.h)."""
     _require_cuda(score, 'score')
     if params is None:
         nms_dist, threshold, border_dist, top_k, min_score = 4, 0.0, 8, 300, 0.0   # extracter.py:200-205
@@ -171,7 +172,7 @@ def detect_batched(score: torch.Tensor, params: dict | None = None, phases: int 
         check(lib.kb_detect_phases(s.data_ptr(), b, h, w, int(nms_dist), int(border_dist), float(threshold),
                                    float(min_score), int(top_k), xyp.data_ptr(), raster.data_ptr(), count.data_ptr(),
                                    path.data_ptr(), ws.data_ptr(), ws.numel(), int(phases), _stream()), 'kb_detect')
-    _count(5 if phases == 7 else 1)       # threshold estimate, round-1, resolve, (fallback NMS, fallback select: early exit)
+    _count(5 if (phases & 7) == 7 else 1)       # threshold estimate, round-1, resolve, (fallback NMS, fallback select: early exit)
     return xyp, count, raster, path
 
 
@@ -271,6 +272,12 @@ def match_batched(d0: torch.Tensor, d1: torch.Tensor, n0: torch.Tensor | None = 
     if return_ws:
         return pairs, dist, count, ws
     return pairs, dist, count
+
+
+def match_issue_factor(cross_check: bool) -> int:
+    """How many times the one-pass 2*n*m*D flops of a pair the tensor-core search issues (bench.py reports it beside the
+    algorithmic figure): 3 split-bf16 products (hi*hi, hi*lo, lo*hi) per direction, one Gram per direction."""
+    return 3 * (2 if cross_check else 1)
 
 
 def match_tc_debug(ws: torch.Tensor, b: int, n: int, m: int, dd: int) -> dict:

@@ -12,26 +12,10 @@ so each stage is one launch for 2P maps.
 """
 from __future__ import annotations
 
-from dataclasses import dataclass
-
 import torch
 
 from . import ops
-from .synth import PathConfig
-
-
-@dataclass
-class PairBatch:
-    """Device-resident inputs for P pairs (what the backbone + dataset would hand over)."""
-    score: torch.Tensor          # [2P,1,H,W]   first P = image 0, last P = image 1
-    desc: torch.Tensor | None    # [2P,C,h,w]
-    h33: torch.Tensor            # [2P,9]  first P = H01 (pixels of image 1), last P = H10
-    wh: torch.Tensor             # [2P,2]  (width,height) of the TARGET image of each warp
-    resize: int = 512
-
-    @property
-    def pairs(self) -> int:
-        return self.score.shape[0] // 2
+from .synth import FrameBatch, PairBatch, PathConfig  # noqa: F401  (re-exported: the batches are defined beside the inputs)
 
 
 def extract_match(batch: PairBatch, cfg: PathConfig, algo: int = -1, covisible_only: bool = True, timer=None) -> dict:
@@ -67,18 +51,6 @@ def _extract_match(batch, cfg, algo, covisible_only, timer) -> dict:
     return out
 
 
-@dataclass
-class FrameBatch:
-    """Device-resident inputs of a frame stream (KITTI-like sequences, tasks/visual_odometer.py,
-    tasks/FundamentalMatrix.py): F + 1 consecutive frames give F pairs (t-1, t)."""
-    score: torch.Tensor          # [F+1,1,H,W]
-    desc: torch.Tensor           # [F+1,C,h,w]
-
-    @property
-    def pairs(self) -> int:
-        return self.score.shape[0] - 1
-
-
 def extract_match_stream(frames: FrameBatch, cfg: PathConfig, algo: int = -1) -> dict:
     """Stream form of the path: every frame is detected and sampled ONCE and matched against its predecessor.
     The reference's per-pair step (models/model_interface.py:217-228 keeps the previous frame's maps and calls
@@ -112,7 +84,8 @@ def repeatability_counts(batch: PairBatch, cfg: PathConfig, th: float = 3.0, tim
     num_feat = torch.minimum(count[:P], count[P:])
     empty = (nv[:P] == 0) | (nv[P:] == 0)                     # repeatability.py:61-67 -> zeros
     return {'stats': stats, 'errors': errors, 'num_feat': torch.where(empty, torch.zeros_like(num_feat), num_feat),
-            'kpts': xyp, 'n_kpts': count, 'kcov': kv, 'kwarp': kw, 'n_cov': nv, 'empty': empty}
+            'kpts': xyp, 'n_kpts': count, 'raster': raster, 'path': path, 'kcov': kv, 'kwarp': kw, 'n_cov': nv,
+            'empty': empty}
 
 
 def accumulate_repeatability(res: dict) -> torch.Tensor:
@@ -134,6 +107,28 @@ def accumulate_matches(res: dict) -> torch.Tensor:
     """float64 [sum matches, n_pairs] (the stream / AUC configs count matches per pair)."""
     n = res['n_matches'].to(torch.float64)
     return torch.stack([n.sum(), n.new_full((), float(n.numel()))])
+
+
+def run_task(inputs, cfg: PathConfig, algo: int = -1, timer=None, th: float = 3.0):
+    """One step of the path as the task named by ``cfg.task`` runs it in the reference, -> (results, float64
+    accumulator contribution):
+
+    'repeatability'  detect x2 -> warp x2 -> val_key_points counting       (tasks/repeatability.py:95-122)
+    'mha'            detect x2 -> warp x2 -> sample + match the COVISIBLE keypoints (tasks/MHA.py:29-39; the host
+                     cv2 RANSAC that follows is out of scope)
+    'match'          detect x2 -> sample + match ALL keypoints, no warp     (tasks/AUC.py:115-120)
+    'stream'         ``inputs`` is a FrameBatch: every frame extracted once and matched with its predecessor, all
+                     keypoints (tasks/FundamentalMatrix.py:53-57 on models/model_interface.py:217-228's frame pairs)."""
+    if cfg.task == 'repeatability':
+        res = repeatability_counts(inputs, cfg, th, timer)
+        return res, accumulate_repeatability(res)
+    if cfg.task == 'stream':
+        res = extract_match_stream(inputs, cfg, algo)
+    elif cfg.task in ('mha', 'match'):
+        res = extract_match(inputs, cfg, algo=algo, covisible_only=(cfg.task == 'mha'), timer=timer)
+    else:
+        raise ValueError(f'unknown task {cfg.task!r}')
+    return res, accumulate_matches(res)
 
 
 class GraphedStep:

@@ -248,3 +248,116 @@ def lk_scene(c: int, h: int, w: int, seed: int, shift=(2.3, -1.7), sigma: float 
     grid = torch.stack([(xs - shift[0]) / (w - 1) * 2 - 1, (ys - shift[1]) / (h - 1) * 2 - 1], dim=-1)[None]
     img1 = torch.nn.functional.grid_sample(img0, grid, align_corners=True, padding_mode='border')
     return img0.to(device), img1.to(device)
+
+
+# ------------------------------------------------------------------------------------------------
+# Batches (what the backbone + dataset hand to the path).  They live here, not in pipeline.py, so that
+# code which only needs INPUTS (bench.py's reference arm, the oracle-side tests) never loads the CUDA library.
+# ------------------------------------------------------------------------------------------------
+
+@dataclass
+class PairBatch:
+    """Device-resident inputs for P pairs (what the backbone + dataset would hand over)."""
+    score: torch.Tensor          # [2P,1,H,W]   first P = image 0, last P = image 1
+    desc: torch.Tensor | None    # [2P,C,h,w]
+    h33: torch.Tensor            # [2P,9]  first P = H01 (pixels of image 1), last P = H10
+    wh: torch.Tensor             # [2P,2]  (width,height) of the TARGET image of each warp
+    resize: int = 512
+
+    @property
+    def pairs(self) -> int:
+        return self.score.shape[0] // 2
+
+
+@dataclass
+class FrameBatch:
+    """Device-resident inputs of a frame stream (KITTI-like sequences, tasks/visual_odometer.py,
+    tasks/FundamentalMatrix.py): F + 1 consecutive frames give F pairs (t-1, t)."""
+    score: torch.Tensor          # [F+1,1,H,W]
+    desc: torch.Tensor           # [F+1,C,h,w]
+
+    @property
+    def pairs(self) -> int:
+        return self.score.shape[0] - 1
+
+
+def make_batch(cfg: PathConfig, cfg_index: int, n_pairs: int, first_pair: int, device, kind: str = 'uniform'):
+    """P pairs resident on ``device`` per SURVEY 8(d): score A, score B = nearest-warp of A, descriptor map A
+    (unit-norm per pixel, or 2.67x for ALIKE-like configs), map B = bilinear warp of A + 0.05 noise.
+    -> (PairBatch, homographies [P,3,3])."""
+    H, W = cfg.height, cfg.width
+    g = torch.Generator(device=device)
+    g.manual_seed(pair_seed(cfg_index, first_pair))
+    hms = torch.stack([homography(pair_seed(cfg_index, first_pair + i) + 7) for i in range(n_pairs)])
+    if kind == 'uniform':
+        s0 = torch.rand(n_pairs, 1, H, W, generator=g, device=device)
+    else:
+        s0 = torch.cat([score_map(kind, H, W, pair_seed(cfg_index, first_pair + i), device) for i in range(n_pairs)])
+    s1 = torch.empty_like(s0)
+    chunk = 8
+    for i in range(0, n_pairs, chunk):
+        grids = torch.cat([_inverse_grid(hms[j], H, W, device) for j in range(i, min(i + chunk, n_pairs))])
+        s1[i:i + chunk] = F.grid_sample(s0[i:i + chunk], grids, mode='nearest', padding_mode='zeros', align_corners=True)
+    desc = None
+    if cfg.desc_dim:
+        dh, dw = H // cfg.desc_stride, W // cfg.desc_stride
+        d0 = F.normalize(torch.randn(n_pairs, cfg.desc_dim, dh, dw, generator=g, device=device), dim=1)
+        if not cfg.desc_normalized:
+            d0 = 2.67 * d0
+        d1 = torch.empty_like(d0)
+        for i in range(0, n_pairs, chunk):
+            grids = torch.cat([_inverse_grid(rescale_homography(hms[j], cfg.desc_stride), dh, dw, device)
+                               for j in range(i, min(i + chunk, n_pairs))])
+            d1[i:i + chunk] = F.grid_sample(d0[i:i + chunk], grids, mode='bilinear', padding_mode='zeros', align_corners=True)
+        d1 += 0.05 * torch.randn(d1.shape, generator=g, device=device)
+        desc = torch.cat([d0, d1])
+    h01 = hms.reshape(n_pairs, 9)
+    h10 = torch.linalg.inv(hms.double()).float().reshape(n_pairs, 9)
+    h33 = torch.cat([h01, h10]).to(device)
+    wh = torch.tensor([[float(W), float(H)]], device=device).expand(2 * n_pairs, 2).contiguous()
+    return PairBatch(score=torch.cat([s0, s1]), desc=desc, h33=h33, wh=wh, resize=512), hms
+
+
+def _hash_uniform(idx: torch.Tensor, seed: int) -> torch.Tensor:
+    """Counter-based U[0,1): integer mixing of an int64 index tensor (same bits on every device / rank)."""
+    def lsr(v, k):                               # logical shift right of an int64 tensor
+        return (v >> k) & ((1 << (64 - k)) - 1)
+    h = idx * 6364136223846793005 + (1442695040888963407 + 2 * int(seed) + 1)
+    h = h ^ lsr(h, 29)
+    h = h * -4658895280553007687                 # 0xBF58476D1CE4E5B9 as int64
+    h = h ^ lsr(h, 32)
+    h = h * -7723592293110705685                 # 0x94D049BB133111EB as int64
+    h = h ^ lsr(h, 29)
+    return lsr(h, 40).to(torch.float32) / 16777216.0
+
+
+PAN_PX = 3        # the synthetic camera pans 3 px per frame; new content enters on the left
+
+
+def make_frames(cfg: PathConfig, seed: int, first_frame: int, n_frames: int, total_frames: int, device) -> FrameBatch:
+    """Frames [first_frame, first_frame + n_frames) of a synthetic sequence of ``total_frames`` frames: windows of a
+    procedural panorama (a counter-based hash of the panorama pixel, so every rank generates exactly its own frames and
+    a frame's content depends only on its global index) plus per-frame descriptor noise."""
+    H, W, C = cfg.height, cfg.width, cfg.desc_dim
+    dh, dw = H // cfg.desc_stride, W // cfg.desc_stride
+    pano_w = W + PAN_PX * (total_frames - 1)
+    ys = torch.arange(H, dtype=torch.int64, device=device)[:, None]
+    xs = torch.arange(W, dtype=torch.int64, device=device)[None, :]
+    score = torch.empty(n_frames, 1, H, W, dtype=torch.float32, device=device)
+    desc = torch.empty(n_frames, C, dh, dw, dtype=torch.float32, device=device)
+    cs = torch.arange(C, dtype=torch.int64, device=device)[:, None, None]
+    dys = torch.arange(dh, dtype=torch.int64, device=device)[None, :, None]
+    dxs = torch.arange(dw, dtype=torch.int64, device=device)[None, None, :]
+    for i in range(n_frames):
+        t = first_frame + i
+        off = PAN_PX * (total_frames - 1 - t)                 # panorama column of the frame's column 0
+        score[i, 0] = _hash_uniform(ys * pano_w + (xs + off), seed)
+        doff = off // cfg.desc_stride
+        pidx = (cs * dh + dys) * (pano_w // cfg.desc_stride + 1) + (dxs + doff)
+        base = _hash_uniform(pidx, seed + 1) + _hash_uniform(pidx, seed + 2) + _hash_uniform(pidx, seed + 3) - 1.5
+        base = F.normalize(base, dim=0)
+        fidx = ((cs * dh + dys) * dw + dxs) * total_frames + t
+        noise = (_hash_uniform(fidx, seed + 4) + _hash_uniform(fidx, seed + 5) - 1.0) * 0.1225     # std ~0.05
+        d = base + noise
+        desc[i] = d if cfg.desc_normalized else 2.67 * d
+    return FrameBatch(score, desc)

@@ -59,6 +59,16 @@ def test_fast_nms_batch_is_joint_like_the_reference():
 
 # ------------------------------------------------------------------------------------------------ detection
 
+# round 1 of the sparse path has two kernels with identical output (kb_round1_stream.cu for large batches,
+# the tiled round1_kernel otherwise): phases bit 3 / bit 4 force one of them (include/kb_b200.h)
+ROUND1 = {'tiled': 7 | 8, 'stream': 7 | 16}
+
+
+@pytest.fixture(params=['tiled', 'stream'])
+def round1(request):
+    return ROUND1[request.param]
+
+
 def _check_detection(pts, want, raster=None, want_raster=None):
     assert pts.shape == want.shape
     uniq, cnt = np.unique(want[:, 2], return_counts=True)
@@ -83,17 +93,17 @@ def test_detection_matches_reference_fixtures(golden):
         assert np.array_equal(raster[0, :n].cpu().numpy().astype(np.int64), g[f'{tag}__raster']), tag
 
 
-def test_detection_1024_and_batched_against_oracle():
+def test_detection_1024_and_batched_against_oracle(round1):
     cfg = synth.CONFIGS['cfg4']
     s = synth.score_map('uniform', 1024, 1024, 9)
     want, want_r = ref_ops.detection(s, cfg.extractor_params, nms='greedy')
-    xyp, count, raster, _ = ops().detect_batched(s.to(DEV), cfg.extractor_params)
+    xyp, count, raster, _ = ops().detect_batched(s.to(DEV), cfg.extractor_params, phases=round1)
     n = int(count[0])
     _check_detection(xyp[0, :n].cpu().numpy(), want, raster[0, :n].cpu().numpy().astype(np.int64), want_r)
     # a batch of different maps is processed independently per map
     maps = [synth.score_map(k, 120, 160, 40 + i) for i, k in enumerate(['uniform', 'ties', 'alike', 'relu', 'uniform'])]
     params = dict(nms_dist=4, threshold=0.0, border_dist=8, top_k=50, min_score=0.0)
-    xyp, count, raster, _ = ops().detect_batched(torch.cat(maps, 0).to(DEV), params)
+    xyp, count, raster, _ = ops().detect_batched(torch.cat(maps, 0).to(DEV), params, phases=round1)
     for i, m in enumerate(maps):
         want, want_r = ref_ops.detection(m, params)
         n = int(count[i])
@@ -403,14 +413,14 @@ def test_corner_error_and_mha(golden):
 
 # ------------------------------------------------------------------------------------------------ sparse path
 
-def test_detect_paths_sparse_and_fallback():
+def test_detect_paths_sparse_and_fallback(round1):
     """uniform maps are certified by the sparse path (path 1); maps with negative scores, heavy ties or
     a top_k the candidate budget cannot reach fall back to the round-faithful kernel (path 2); both
     must equal the oracle."""
     params = dict(nms_dist=6, threshold=0.0, border_dist=8, top_k=1000, min_score=0.0)
     kinds = ['uniform', 'mixed', 'ties', 'uniform', 'alike', 'relu', 'negative', 'ramp']
     maps = [synth.score_map(k, 480, 640, 300 + i) for i, k in enumerate(kinds)]
-    xyp, count, raster, path = ops().detect_batched(torch.cat(maps, 0).to(DEV), params)
+    xyp, count, raster, path = ops().detect_batched(torch.cat(maps, 0).to(DEV), params, phases=round1)
     path = path.cpu().tolist()
     assert path[0] == 1 and path[3] == 1, path
     assert path[1] == 2 and path[6] == 2, path
@@ -423,7 +433,7 @@ def test_detect_paths_sparse_and_fallback():
 
 
 @pytest.mark.parametrize('seed', range(24))
-def test_detect_sparse_randomised_against_greedy_oracle(seed):
+def test_detect_sparse_randomised_against_greedy_oracle(seed, round1):
     rng = np.random.default_rng(seed)
     h, w = int(rng.integers(40, 300)), int(rng.integers(40, 400))
     params = dict(nms_dist=int(rng.integers(1, 9)), threshold=float(rng.choice([0.0, 0.0, 0.3, 0.9])),
@@ -432,11 +442,45 @@ def test_detect_sparse_randomised_against_greedy_oracle(seed):
     kind = ['uniform', 'relu', 'alike', 'ties'][seed % 4]
     m = synth.score_map(kind, h, w, 500 + seed)
     want, want_r = ref_ops.detection(m, params)
-    xyp, count, raster, path = ops().detect_batched(m.to(DEV), params)
+    xyp, count, raster, path = ops().detect_batched(m.to(DEV), params, phases=round1)
     n = int(count[0])
     assert n == want.shape[0], (params, kind, h, w, int(path[0]))
     assert np.array_equal(raster[0, :n].cpu().numpy().astype(np.int64), want_r), (params, kind, int(path[0]))
     assert np.array_equal(xyp[0, :n].cpu().numpy(), want)
+
+
+@pytest.mark.parametrize('h,w,r,top_k,nmaps', [(480, 640, 6, 1000, 96), (376, 1241, 6, 1000, 56), (480, 640, 4, 4096, 80),
+                                               (203, 517, 3, 300, 150)])
+def test_detect_large_batch_stream_equals_tiled_and_oracle(h, w, r, top_k, nmaps):
+    """A batch large enough for the automatic choice to be the streaming round-1 kernel (CTAs walk several bands,
+    bands cross map boundaries): automatic == forced streaming == forced tiled, bit for bit, and a few maps of the
+    batch equal the greedy oracle."""
+    params = dict(nms_dist=r, threshold=0.0, border_dist=8, top_k=top_k, min_score=0.0)
+    gen = torch.Generator(device=DEV).manual_seed(4242 + h)
+    s = torch.rand(nmaps, 1, h, w, generator=gen, device=DEV)
+    s[3] = torch.floor(s[3] * 8) / 8                          # a tie-heavy map in the middle of the batch
+    s[5, 0, h // 2, :] = 0.999                                # a row of equal values: first-of-ties rule
+    s[6, 0, :, w // 3] = 0.9995                               # a column of equal values
+    s[7] -= 0.5                                               # negative scores -> flagged for the round-faithful kernel
+    outs = {}
+    for name, ph in (('auto', 7), ('tiled', 7 | 8), ('stream', 7 | 16)):
+        with torch.no_grad():
+            xyp, count, raster, path = ops().detect_batched(s, params, phases=ph)
+        outs[name] = (xyp.cpu().numpy(), count.cpu().numpy(), raster.cpu().numpy(), path.cpu().numpy())
+    for name in ('tiled', 'stream'):
+        assert np.array_equal(outs['auto'][1], outs[name][1]), name
+        assert np.array_equal(outs['auto'][3], outs[name][3]), name
+        for b in range(nmaps):
+            n = int(outs['auto'][1][b])
+            assert np.array_equal(outs['auto'][2][b, :n], outs[name][2][b, :n]), (name, b)
+            assert np.array_equal(outs['auto'][0][b, :n], outs[name][0][b, :n]), (name, b)
+    assert outs['auto'][3][0] == 1 and outs['auto'][3][7] == 2, outs['auto'][3][:8]
+    for b in (0, 3, 5, 6, 7, nmaps - 1):
+        want, want_r = ref_ops.detection(s[b:b + 1].cpu(), params, nms='greedy' if b != 7 else 'separable')
+        n = int(outs['auto'][1][b])
+        assert n == want.shape[0], (b, n, want.shape[0])
+        assert np.array_equal(outs['auto'][2][b, :n].astype(np.int64), want_r), b
+        assert np.array_equal(outs['auto'][0][b, :n], want), b
 
 
 # ------------------------------------------------------------------------------------------------ tensor-core matcher internals
@@ -506,11 +550,11 @@ def test_sampling_plane_staged_path_cfg2_shape():
     ('ties', 480, 640, 6, 1000, None),      # eight distinct values: whichever path, result must be exact
     ('alike', 240, 320, 3, 300, None),      # odd radius (unaligned halo)
 ])
-def test_detection_full_size_configs_against_greedy_oracle(kind, h, w, r, top_k, want_path):
+def test_detection_full_size_configs_against_greedy_oracle(kind, h, w, r, top_k, want_path, round1):
     params = dict(nms_dist=r, threshold=0.0, border_dist=8, top_k=top_k, min_score=0.0)
     m = synth.score_map(kind, h, w, 77 + r)
     want, want_r = ref_ops.detection(m, params, nms='greedy')
-    xyp, count, raster, path = ops().detect_batched(m.to(DEV), params)
+    xyp, count, raster, path = ops().detect_batched(m.to(DEV), params, phases=round1)
     n = int(count[0])
     assert n == want.shape[0], (kind, n, want.shape[0], int(path[0]))
     assert np.array_equal(raster[0, :n].cpu().numpy().astype(np.int64), want_r), (kind, int(path[0]))
