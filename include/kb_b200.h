@@ -43,6 +43,14 @@ typedef void* kb_stream_t; /* cudaStream_t */
 KB_API int kb_version(void);
 /* Human-readable text for a return code of this library. */
 KB_API const char* kb_error_string(int code);
+/* Process-wide experiment knobs (tests and A/B measurements only; product callers never touch them).  Results never
+ * depend on KB_KNOB_TC_CLUSTER or KB_KNOB_REP_NO_SORT; KB_KNOB_TC_DEBUG is a bit mask of TIMING experiments of the
+ * tensor-core search kernel and makes results WRONG with bits 1, 2 or 8 set (4 = in-kernel pipeline wait counters).
+ * Returns the previous value, or KB_ERR_BAD_ARG for an unknown knob. */
+#define KB_KNOB_TC_CLUSTER 1  /* 2 = CTA-pair (cta_group::2) tensor-core search kernel; default 1 */
+#define KB_KNOB_TC_DEBUG 2    /* default 0 */
+#define KB_KNOB_REP_NO_SORT 3 /* 1 = kb_repeat_counts uses the tile-walking kernels instead of the sorted sweeps */
+KB_API int kb_debug_knob(int knob, int value);
 
 /* ---------------------------------------------------------------------------------------------
  * Stage 1a -- fast_nms(image_probs, nms_dist, max_iter, min_value)   utils/extracter.py:6-100
@@ -179,10 +187,7 @@ KB_API int kb_match_mnn_phases(const float* d0, const float* d1, const int* n0, 
  * (float best, second, third, pad; int argbest, argsecond, pad, pad), off[1] same for direction 1, off[2] int32[2] = rows that needed the exact float64 rescan,
  * rows settled by the two-candidate exact check,
  * off[3]/off[4] float32 squared row norms of d0/d1, off[5] int64[512][8] pipeline wait counters of the search
- * kernel (filled when the environment has KB_TC_DEBUG=4, scripts/tc_pipeline_profile.py).  `off` has SIX entries.
- * Environment switches read by the tensor-core path (experiments; results do not change): KB_TC_CLUSTER=2 selects
- * the CTA-pair (cta_group::2) search kernel, KB_TC_DEBUG is a bit mask of timing experiments (results are WRONG
- * with bits 1, 2 or 8 set). */
+ * kernel (filled with kb_debug_knob(KB_KNOB_TC_DEBUG, 4), scripts/tc_pipeline_profile.py).  `off` has SIX entries. */
 KB_API int kb_match_tc_debug_offsets(int B, int n_max, int m_max, int D, size_t* off);
 
 /* ---------------------------------------------------------------------------------------------

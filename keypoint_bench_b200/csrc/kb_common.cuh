@@ -16,6 +16,11 @@
         if (_e != cudaSuccess) return (int)_e;    \
     } while (0)
 
+// experiment knobs (kb_debug_knob, kb_api.cu); index = KB_KNOB_*
+extern int kb_knobs[8];
+// multiprocessor count of the current device (looked up once per device and process)
+int kb_sm_count(int* sms);
+
 static inline size_t kb_align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // Bump allocator over the caller's workspace (the library never allocates).

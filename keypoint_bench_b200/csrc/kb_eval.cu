@@ -868,7 +868,7 @@ extern "C" int kb_repeat_counts(const float* k0c, const float* k01c, const int* 
     // pruned sweeps for every map whose distances are provably below the 99999 diagonal mask ...
     rep_bound_kernel<<<B, 256, 0, st>>>(p, need_bf);
     KB_LAUNCH_CHECK();
-    const bool no_sort = getenv("KB_REP_NO_SORT") != nullptr;          // A/B timing and tests: the tile-walking kernels
+    const bool no_sort = kb_knobs[KB_KNOB_REP_NO_SORT] != 0;           // A/B timing and tests: the tile-walking kernels
     if (a_max <= SRT_MAX && b_max <= SRT_MAX && !no_sort) {
         int np2 = 1;
         while (np2 < (a_max > b_max ? a_max : b_max)) np2 <<= 1;

@@ -16,7 +16,7 @@
 //                   into per-row running (best, second, third, argbest, argsecond) with software-pipelined
 //                   tcgen05.ld.32x32b.x16; the [n,m] matrix never leaves the SM.  Both directions (rows->cols,
 //                   cols->rows for the cross-check) are work items of the same launch.  nn_top2_kernel<2> is the
-//                   CTA-pair variant (cluster of 2, cta_group::2, M=256), selectable with KB_TC_CLUSTER=2.
+//                   CTA-pair variant (cluster of 2, cta_group::2, M=256), selectable with kb_debug_knob(KB_KNOB_TC_CLUSTER, 2).
 //   resolve_kernel  merges the column slices; best-second above twice the a-priori error bound of the split
 //                   product certifies the argmax; best-third above it leaves two candidates that are compared
 //                   exactly in float64; anything else is queued for rescan_kernel, an exact float64 scan of the
@@ -25,7 +25,6 @@
 //                   caller wants pairs only, float64 distance inside the error band or when distances are returned.
 //   pairs_kernel    ordered compaction (per pair).
 #include <cuda.h>
-#include <cstdlib>
 #include <cuda_bf16.h>
 #include <math_constants.h>
 #include "kb_common.cuh"
@@ -288,8 +287,8 @@ struct MainParams {
     int B, n_max, m_max, cs0, cs1, KB, tiles0, tiles1, n_dirs, n_slots;
     int cl;                  // CTAs per cluster (1 or 2): a pair works on two adjacent query tiles and shares the database stream
     int align_slack;         // bytes the kernel may spend on aligning its tiles to 1024
-    long long* prof;         // timing experiments only (KB_TC_DEBUG & 4): per CTA 8 cycle counters, see scripts/tc_pipeline_profile.py
-    int dbg;                 // timing experiments only (KB_TC_DEBUG): 1 = epilogue skips the fold, 2 = no MMAs issued
+    long long* prof;         // timing experiments only (KB_KNOB_TC_DEBUG & 4): per CTA 8 cycle counters, see scripts/tc_pipeline_profile.py
+    int dbg;                 // timing experiments only (KB_KNOB_TC_DEBUG): 1 = epilogue skips the fold, 2 = no MMAs issued
 };
 
 struct Item {
@@ -1112,7 +1111,7 @@ static TcLayout tc_layout(int B, int n_max, int m_max, int D) {
     add((size_t)B * (n_max + m_max) * 8 * 16);  // rescan partial minima
     add((size_t)B * (n_max + m_max) * 4);       // rescan tickets
     add((size_t)B * n_max * 4);                 // tensor-core score of the direction-0 winners
-    add(8 * 512 * 8);                           // pipeline wait counters (KB_TC_DEBUG & 4)
+    add(8 * 512 * 8);                           // pipeline wait counters (KB_KNOB_TC_DEBUG & 4)
     L.bytes = n + 1024;
     return L;
 }
@@ -1210,9 +1209,8 @@ int kb_match_tc_run(const float* d0, const float* d1, const int* n0, const int* 
             KB_CUDA_TRY(cudaMemsetAsync(tb.tickets, 0, (size_t)B * (n_max + m_max) * 4, st));
         }
     }
-    int dev = 0, sms = 0;
-    KB_CUDA_TRY(cudaGetDevice(&dev));
-    KB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int sms = 0;
+    { const int rc_sm = kb_sm_count(&sms); if (rc_sm != KB_OK) return rc_sm; }
     {
         PrepPair pp;
         PrepParams& q0 = pp.side[0];
@@ -1233,10 +1231,24 @@ int kb_match_tc_run(const float* d0, const float* d1, const int* n0, const int* 
             KB_LAUNCH_CHECK();
         }
     }
+    // the two operand maps depend on (base, rows, row length) only: steady-state callers reuse their workspace, so the
+    // driver call that encodes a map is made once per distinct operand array and thread
+    struct MapCache { void* base; uint64_t rows, ks; CUtensorMap map; };
+    static thread_local MapCache cache[2] = {};
+    auto cached_map = [&](int slot, void* base, uint64_t rows, uint64_t ks, CUtensorMap* out) -> int {
+        MapCache& c = cache[slot];
+        if (c.base != base || c.rows != rows || c.ks != ks) {
+            const int r = make_map(&c.map, base, rows, ks);
+            if (r != KB_OK) { c.base = nullptr; return r; }
+            c.base = base; c.rows = rows; c.ks = ks;
+        }
+        *out = c.map;
+        return KB_OK;
+    };
     CUtensorMap map0, map1;
-    int rc = make_map(&map0, S0, (uint64_t)B * n_max, (uint64_t)2 * L.Dp);
+    int rc = cached_map(0, S0, (uint64_t)B * n_max, (uint64_t)2 * L.Dp, &map0);
     if (rc != KB_OK) return rc;
-    rc = make_map(&map1, S1, (uint64_t)B * m_max, (uint64_t)2 * L.Dp);
+    rc = cached_map(1, S1, (uint64_t)B * m_max, (uint64_t)2 * L.Dp, &map1);
     if (rc != KB_OK) return rc;
 
     MainParams mp;
@@ -1247,14 +1259,14 @@ int kb_match_tc_run(const float* d0, const float* d1, const int* n0, const int* 
     // 1024-byte boundary (128B swizzle) -- dynamic shared memory normally does, `slack` covers the rest
     const size_t fixed = 256 + 2 * BN * 4 + BM * 4;
     const size_t budget = 227 * 1024;
-    // CTA pairs (KB_TC_CLUSTER=2: thread-block clusters of 2, tcgen05 cta_group::2 MMAs with M = 256): the pair
+    // CTA pairs (kb_debug_knob(KB_KNOB_TC_CLUSTER, 2): thread-block clusters of 2, tcgen05 cta_group::2 MMAs with M = 256): the pair
     // multiplies two adjacent query tiles against one database stream of which every CTA holds half, so the operand
     // bytes per CTA halve and the ring is twice as deep.  Measured on B200 it is neither faster nor slower than the
     // 1-CTA kernel (172 vs 170-178 us on cfg2): the kernel's time goes to the tensor pipe sharing TMEM with the
     // epilogue's tcgen05.ld and to the epilogue itself, not to operand delivery (scripts/tc_pipeline_profile.py), so
     // the 1-CTA kernel stays the default and the pair kernel is kept selectable and tested.
     int cl = 1;
-    { const char* e = getenv("KB_TC_CLUSTER"); if (e && atoi(e) == 2 && (L.tiles0 > 1 || L.tiles1 > 1)) cl = 2; }
+    if (kb_knobs[KB_KNOB_TC_CLUSTER] == 2 && (L.tiles0 > 1 || L.tiles1 > 1)) cl = 2;
     mp.cl = cl;
     const size_t slot_bytes = cl == 2 ? TILE_BYTES : SLOT_BYTES;
     int n_slots = (int)((budget - fixed - (size_t)2 * L.KB * TILE_BYTES) / slot_bytes);
@@ -1266,10 +1278,14 @@ int kb_match_tc_run(const float* d0, const float* d1, const int* n0, const int* 
     mp.n_slots = n_slots;
     mp.align_slack = (int)slack;
     const size_t smem = used + slack;
-    { const char* e = getenv("KB_TC_DEBUG"); mp.dbg = e ? atoi(e) : 0; }
+    mp.dbg = kb_knobs[KB_KNOB_TC_DEBUG];
     mp.prof = tb.prof;
-    KB_CUDA_TRY(cudaFuncSetAttribute(nn_top2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    KB_CUDA_TRY(cudaFuncSetAttribute(nn_top2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static bool attr_set = false;                 // the opt-in to > 48 KB of dynamic shared memory is per process
+    if (!attr_set) {
+        KB_CUDA_TRY(cudaFuncSetAttribute(nn_top2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+        KB_CUDA_TRY(cudaFuncSetAttribute(nn_top2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+        attr_set = true;
+    }
     const int g0 = (L.tiles0 + cl - 1) / cl, g1 = (L.tiles1 + cl - 1) / cl;
     const int n_items = mp.n_dirs == 2 ? B * (g0 + g1) : B * g0;
     const int max_groups = sms / cl;

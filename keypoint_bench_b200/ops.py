@@ -37,6 +37,22 @@ def _out(*shape, dtype, device):
     return torch.zeros(*shape, dtype=dtype, device=device) if _zero_fill else torch.empty(*shape, dtype=dtype, device=device)
 
 
+class debug_knob:
+    """Context manager around ``kb_debug_knob`` (include/kb_b200.h): experiment switches for tests and A/B timings."""
+
+    def __init__(self, knob: int, value: int):
+        self.knob, self.value = knob, value
+
+    def __enter__(self):
+        self.prev = lib.kb_debug_knob(self.knob, self.value)
+        if self.prev == _lib.KB_ERR_BAD_ARG:
+            raise _lib.KbError(f'unknown knob {self.knob}')
+        return self
+
+    def __exit__(self, *exc):
+        lib.kb_debug_knob(self.knob, self.prev)
+
+
 def launches() -> int:
     return _launches
 
@@ -144,12 +160,27 @@ def select_batched(nms_map: torch.Tensor, border_dist: int, threshold: float, mi
     return xyp, count, raster, total
 
 
+SORT_CAP = 8192        # largest top_k the selection kernels sort on chip (kb_select.cu)
+DETECT_MAX_B = 2048    # maps per kb_detect call (larger batches are split here)
+
+
+def nms_keep_bound(h: int, w: int, nms_dist: int) -> int:
+    """Kept pixels are pairwise more than ``nms_dist`` apart (Chebyshev): at most ceil(h/(r+1)) * ceil(w/(r+1))."""
+    if nms_dist <= 0:
+        return h * w
+    return ((h + nms_dist) // (nms_dist + 1)) * ((w + nms_dist) // (nms_dist + 1))
+
+
 def detect_batched(score: torch.Tensor, params: dict | None = None, phases: int = 7, state=None):
     """``detection`` (utils/extracter.py:193-221) for every map of the batch independently.
     -> xyp[B,top_k,3] (x,y,p), count[B], raster[B,top_k], path[B].
     ``phases`` / ``state`` are a measurement hook (bench.py): ``state=[]`` receives the buffers of a full call,
     a later call with the same ``state`` and ``phases`` in {1,2,4} re-runs just that kernel on them; ``phases | 8`` /
-    ``phases | 16`` force the tiled / the streaming round-1 kernel (identical output, include/kb_b200.h)."""
+    ``phases | 16`` force the tiled / the streaming round-1 kernel (identical output, include/kb_b200.h).
+
+    Like the reference, any ``top_k`` is accepted: 0 gives no rows, and a ``top_k`` the NMS can never exceed (at least
+    ``nms_keep_bound``) means raster order for every map (extracter.py:217).  Only SORT_CAP < top_k < keep bound -- a
+    sort of more than 8192 survivors -- is not implemented and raises."""
     _require_cuda(score, 'score')
     if params is None:
         nms_dist, threshold, border_dist, top_k, min_score = 4, 0.0, 8, 300, 0.0   # extracter.py:200-205
@@ -158,6 +189,22 @@ def detect_batched(score: torch.Tensor, params: dict | None = None, phases: int 
         top_k, min_score = params['top_k'], params['min_score']
     s = _maps3(score)
     b, h, w = s.shape
+    if top_k <= 0 and state is None:                           # pts[argsort(...)[:0]] -- an empty result for every map
+        z = torch.zeros(b, dtype=torch.int32, device=s.device)
+        return (torch.zeros(b, 0, 3, dtype=torch.float32, device=s.device), z,
+                torch.zeros(b, 0, dtype=torch.int32, device=s.device), z.clone())
+    if top_k > SORT_CAP and state is None:
+        bound = nms_keep_bound(h, w, int(nms_dist)) if threshold >= 0 else h * w
+        if top_k < bound:
+            raise _lib.KbError(f'top_k = {top_k}: sorting more than {SORT_CAP} survivors per map is not implemented '
+                               f'(top_k >= {bound}, the most this NMS can keep on a {h}x{w} map, is accepted)')
+        # the top-k can never bind: round-faithful NMS, then every surviving pixel in raster order
+        nms = fast_nms_batched(s, int(nms_dist)) if nms_dist > 0 else s
+        xyp, count, raster, _ = select_batched(nms, int(border_dist), float(threshold), float(min_score), 0, cap=bound)
+        return xyp, count, raster, torch.full_like(count, 2)
+    if b > DETECT_MAX_B and state is None:
+        parts = [detect_batched(s[i:i + DETECT_MAX_B], params, phases) for i in range(0, b, DETECT_MAX_B)]
+        return tuple(torch.cat([p[k] for p in parts]) for k in range(4))
     if state:
         xyp, raster, count, path, ws = state
     else:
@@ -337,8 +384,8 @@ def warp_se3_batched(pts: torch.Tensor, count: torch.Tensor | None, depth0: torc
     p = _f32(pts)
     b, n = p.shape[0], p.shape[1]
     d0, d1 = _f32(depth0).reshape(b, depth0.shape[-2], depth0.shape[-1]), _f32(depth1).reshape(b, depth1.shape[-2], depth1.shape[-1])
-    # the reference inverts intrinsics0 in float32 on the fly (projection.py:46); float64 here, rounded once
-    kinv = torch.linalg.inv(k0.to(device=p.device, dtype=torch.float64)).to(torch.float32).reshape(b, 9).contiguous()
+    # the reference inverts intrinsics0 in float32 on the fly (torch.inverse, projection.py:46): same precision here
+    kinv = torch.linalg.inv(k0.to(device=p.device, dtype=torch.float32)).reshape(b, 9).contiguous()
     k1f = _f32(k1.to(p.device)).reshape(b, 9)
     pose = _f32(pose01.to(p.device)).reshape(b, 16)
     bb0, bb1 = _f32(bbox0.to(p.device)).reshape(b, 2), _f32(bbox1.to(p.device)).reshape(b, 2)

@@ -49,6 +49,27 @@ def detection(score_map: torch.Tensor, params: dict = None) -> torch.Tensor:
     if params is not None and params['nms_dist'] == 0 and params['border_dist'] > 0:
         # extracter.py:214-215: with nms_dist == 0 the border zeroing lands on the caller's tensor
         remove_border_points(score_map, params['border_dist'])
+    if s.dim() == 4 and s.shape[0] > 1:
+        # Only batch item 0 is returned (extracter.py:161), but fast_nms runs on the whole batch with ONE stopping
+        # rule (the maxima count summed over the batch, extracter.py:73-78).  On non-negative maps every item reaches
+        # its own fixed point whatever the others do, so item 0 alone gives the same rows; with negative scores the
+        # stopping round is observable and the batch is processed jointly by the round-faithful kernel.
+        nms_dist = 4 if params is None else params['nms_dist']
+        if nms_dist > 0 and bool((s < 0).any()):
+            border, thr, top_k, min_score = (8, 0.0, 300, 0.0) if params is None else (
+                params['border_dist'], params['threshold'], params['top_k'], params['min_score'])
+            nms = ops.fast_nms_batched(s, nms_dist)
+            if top_k <= 0:
+                return like(torch.zeros(0, 3, dtype=torch.float32, device=s.device), score_map)
+            cap = int(top_k)
+            if top_k > ops.SORT_CAP:                          # see ops.detect_batched: a top_k that can never bind
+                cap = ops.nms_keep_bound(s.shape[-2], s.shape[-1], int(nms_dist)) if thr >= 0 else s.shape[-2] * s.shape[-1]
+                if top_k < cap:
+                    raise ops._lib.KbError(f'top_k = {top_k}: sorting more than {ops.SORT_CAP} survivors is not implemented')
+                top_k = 0
+            xyp, count, _, _ = ops.select_batched(nms[0:1], int(border), float(thr), float(min_score), int(top_k), cap=cap)
+            return like(xyp[0, :int(count[0].item())], score_map)
+        s = s[0:1]
     xyp, count, _, _ = ops.detect_batched(s, params)
     n = int(count[0].item())
     return like(xyp[0, :n], score_map)

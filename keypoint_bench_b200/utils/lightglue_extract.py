@@ -49,8 +49,9 @@ def extract_batched(scores: torch.Tensor, descriptors: torch.Tensor, s: int, det
     # border rows/cols -> excluded, `> threshold`, top-k by score when more than k remain, raster order otherwise
     xyp, count, raster, _ = ops.select_batched(nms, int(pad), float(detection_threshold), 0.0, int(max_num_kps))
     live = torch.arange(raster.shape[1], device=raster.device)[None, :] < count[:, None]
-    kps = torch.stack([raster % w, raster // w], dim=-1).float() * live[..., None]       # (h, w) -> (x, y), lightglue.py:970
-    val = xyp[..., 2] * live
+    # (rows beyond the count may be uninitialised under ops.no_zero_fill: select, never multiply)
+    kps = torch.where(live[..., None], torch.stack([raster % w, raster // w], dim=-1).float(), 0.0)     # (h, w) -> (x, y), lightglue.py:970
+    val = torch.where(live, xyp[..., 2], 0.0)
     desc = ops.sample_batched(to_cuda(descriptors), kps, count, normalize=True, coord_mode=1, s=int(s))
     return kps, val, desc, count
 

@@ -1,4 +1,4 @@
-"""Where does nn_top2_kernel wait?  KB_TC_DEBUG=4 makes the producer / MMA / epilogue lanes accumulate the cycles
+"""Where does nn_top2_kernel wait?  kb_debug_knob(KB_KNOB_TC_DEBUG, 4) makes the producer / MMA / epilogue lanes accumulate the cycles
 they spend in mbarrier waits (clock64) and store them per CTA; this prints the median over CTAs as a share of the
 role's total loop time.  Diagnostic only (the counters perturb the kernel by a few percent)."""
 import ctypes
@@ -8,9 +8,9 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-os.environ['KB_TC_DEBUG'] = str(4 | int(os.environ.get('KB_TC_DEBUG_EXTRA', '0')))
-from keypoint_bench_b200 import ops
+from keypoint_bench_b200 import _lib, ops
 from keypoint_bench_b200._lib import lib, check
+lib.kb_debug_knob(_lib.KB_KNOB_TC_DEBUG, 4 | int(os.environ.get('KB_TC_DEBUG_EXTRA', '0')))
 
 shapes = [(64, 1000, 1000, 256), (16, 4096, 4096, 64)]
 g = torch.Generator().manual_seed(1)

@@ -8,12 +8,14 @@ import numpy as np
 import pytest
 import torch
 
+from helpers import explain_repeat_pair_diffs, oracle_dist_mutual
 from keypoint_bench_b200 import synth
 from oracle import ref_ops
 
 pytestmark = pytest.mark.gpu
 
 DEV = 'cuda'
+LK_TOL = 1e-4       # px; tracked positions of the Lucas-Kanade matcher (see test_lk_tracker_matches_reference_fixtures)
 
 
 def ops():
@@ -110,6 +112,43 @@ def test_detection_1024_and_batched_against_oracle(round1):
         assert n == want.shape[0]
         assert np.array_equal(raster[i, :n].cpu().numpy().astype(np.int64), want_r)
         assert np.array_equal(xyp[i, :n].cpu().numpy(), want)
+
+
+def test_detection_accepts_any_top_k_and_batch_like_the_reference():
+    """utils/extracter.py:193-221 takes any top_k (0 -> no rows; one the NMS can never exceed -> raster order), returns
+    batch item 0 only, and runs fast_nms on the whole batch with one stopping rule (observable with negative scores)."""
+    from keypoint_bench_b200.utils.extracter import detection
+    s = synth.score_map('uniform', 90, 120, 17)
+    base = dict(nms_dist=4, threshold=0.0, border_dist=8, min_score=0.0)
+    assert detection(s.to(DEV), dict(base, top_k=0)).shape == (0, 3)
+    for top_k in (10 ** 6, 90 * 120):
+        want, _ = ref_ops.detection(s, dict(base, top_k=top_k))
+        got = detection(s.to(DEV), dict(base, top_k=top_k)).cpu().numpy()
+        assert np.array_equal(got, want)
+    want, _ = ref_ops.detection(s, dict(base, nms_dist=0, top_k=10 ** 6))
+    assert np.array_equal(detection(s.clone().to(DEV), dict(base, nms_dist=0, top_k=10 ** 6)).cpu().numpy(), want)
+    with pytest.raises(Exception):
+        detection(torch.rand(1, 1, 700, 900, device=DEV), dict(base, nms_dist=1, top_k=9000))     # 8192 < top_k < keep bound
+    # batch of two maps with negative scores: the joint stopping rule decides item 0's rounds
+    # (seeds chosen so that item 0 processed alone stops at a DIFFERENT round than inside the batch: 8 pixels differ)
+    bt = torch.cat([synth.score_map('mixed', 40, 56, 2), synth.score_map('negative', 40, 56, 102)], dim=0)
+    params = dict(base, top_k=50, threshold=-2.0)
+    kept = ref_ops.nms_rounds_separable(bt.numpy()[:, 0], 4)[0]
+    assert not np.array_equal(kept, ref_ops.nms_rounds_separable(bt.numpy()[:1, 0], 4)[0])
+    pts, raster = ref_ops.positions_with_prob(ref_ops.clear_border(kept, 8)[None], -2.0)
+    sel = ref_ops.canonical_order(pts[:, 2], raster)[:50]
+    got = detection(bt.to(DEV), params).cpu().numpy()
+    assert np.array_equal(got, pts[sel])
+    # non-negative batch: item 0 alone
+    b2 = torch.cat([s, synth.score_map('uniform', 90, 120, 18)])
+    want, _ = ref_ops.detection(s, dict(base, top_k=100))
+    assert np.array_equal(detection(b2.to(DEV), dict(base, top_k=100)).cpu().numpy(), want)
+    # more maps than one kb_detect call takes
+    many = torch.rand(2100, 1, 24, 24, device=DEV)
+    xyp, count, raster, path = ops().detect_batched(many, dict(base, border_dist=2, top_k=5))
+    assert xyp.shape == (2100, 5, 3) and int(count.min()) >= 1
+    w5, _ = ref_ops.detection(many[2099:].cpu(), dict(base, border_dist=2, top_k=5))
+    assert np.array_equal(xyp[2099, :int(count[2099])].cpu().numpy(), w5)
 
 
 def test_positions_and_border_dropins():
@@ -275,8 +314,8 @@ def test_matcher_randomised_against_oracle(algo, seed):
             assert np.allclose(dist[i, :got.shape[0]].cpu().numpy(), D[got[:, 0], got[:, 1]], rtol=1e-12, atol=1e-12)
 
 
-def test_matcher_cta_pair_kernel_gives_same_pairs(monkeypatch):
-    """KB_TC_CLUSTER=2 selects the cta_group::2 variant of the tensor-core search (clusters of two CTAs, M = 256
+def test_matcher_cta_pair_kernel_gives_same_pairs():
+    """kb_debug_knob(KB_KNOB_TC_CLUSTER, 2) selects the cta_group::2 variant of the tensor-core search (clusters of two CTAs, M = 256
     MMAs issued by the leader, TMA loads completing on the leader's barriers): same pairs, same top-3 records."""
     gen = torch.Generator().manual_seed(77)
     cases = [(3, 1000, 1000, 256), (2, 700, 1300, 64), (1, 129, 300, 128), (2, 2048, 2048, 128)]
@@ -288,13 +327,13 @@ def test_matcher_cta_pair_kernel_gives_same_pairs(monkeypatch):
         n0 = torch.tensor([n - 37 * i for i in range(b)], dtype=torch.int32)
         n1 = torch.tensor([m - 91 * i for i in range(b)], dtype=torch.int32)
         out = {}
+        from keypoint_bench_b200 import _lib
         for mode in ('1', '2'):
-            monkeypatch.setenv('KB_TC_CLUSTER', mode)
-            p, _, c, ws = ops().match_batched(a.to(DEV), d.to(DEV), n0.to(DEV), n1.to(DEV), 0.9, True, algo=1,
-                                              return_ws=True)
+            with ops().debug_knob(_lib.KB_KNOB_TC_CLUSTER, int(mode)):
+                p, _, c, ws = ops().match_batched(a.to(DEV), d.to(DEV), n0.to(DEV), n1.to(DEV), 0.9, True, algo=1,
+                                                  return_ws=True)
             best = ops().match_tc_debug(ws, b, n, m, dim)['res0'][0][:int(n0[0])]
             out[mode] = (p.clone(), c.clone(), best.clone())
-        monkeypatch.delenv('KB_TC_CLUSTER')
         assert torch.equal(out['1'][1], out['2'][1]), (b, n, m, dim)
         assert torch.allclose(out['1'][2], out['2'][2], rtol=1e-6, atol=1e-6)        # the per-row best scores themselves
         for i in range(b):
@@ -361,15 +400,24 @@ def test_warp_and_val_key_points_match_reference_fixtures(golden):
         assert np.allclose(b.cpu().numpy(), g[f'{tag}__warp_proj'], rtol=1e-5, atol=1e-6)
         res = val_key_points(k0, k1, w01, w10, th=3, return_pairs=True)
         assert res['num_feat'] == int(g[f'{tag}__num_feat'])
-        # the reference quantises distances to 2^-7 before its equality test (99999 diagonal), so a
-        # 1-ulp difference in a distance can move one pair across a bucket edge: allow +-1
-        assert abs(res['gt_num'] - int(g[f'{tag}__gt_num'])) <= 1
-        assert abs(float(res['mean_error']) - float(g[f'{tag}__mean_error'])) < 1e-3
-        assert np.allclose(res['errors'].cpu().numpy(), g[f'{tag}__errors'], rtol=1e-5, atol=1e-5 * 512)
+        # (a) against the oracle, whose warp uses the same three rounded products as the kernel: EXACT counts and pairs
         ora = ref_ops.val_key_points(g[f'{tag}__k0'], g[f'{tag}__k1'], w01, w10, th=3)
         got_pairs = set(map(tuple, res['pairs'].tolist()))
         want_pairs = set(map(tuple, ora['pairs'].tolist()))
-        assert len(got_pairs ^ want_pairs) <= 2
+        assert got_pairs == want_pairs and res['gt_num'] == ora['gt_num']
+        assert np.array_equal(res['errors'].cpu().numpy(), ora['errors'])
+        assert abs(float(res['mean_error']) - ora['mean_error']) < 1e-5
+        # (b) against the fixture minted from the reference itself, whose torch.einsum rounds the warped coordinates
+        # differently by up to 1 ulp: mutual_argmin quantises distances to 2^-7 once the 99999 diagonal is present
+        # (repeatability.py:18-32), so such an ulp can move an entry across a bucket edge.  Every pair that differs must
+        # be such an edge case (within one bucket of both its row and its column maximum), and gt_num can differ by at
+        # most the number of such pairs.
+        ref_pairs = set(map(tuple, g[f'{tag}__pairs'].tolist())) if f'{tag}__pairs' in g.files else None
+        dm = oracle_dist_mutual(g[f'{tag}__k0'], g[f'{tag}__k1'], w01, w10)
+        n_edge = explain_repeat_pair_diffs(got_pairs, ref_pairs, dm) if ref_pairs is not None else 1
+        assert abs(res['gt_num'] - int(g[f'{tag}__gt_num'])) <= n_edge, (res['gt_num'], int(g[f'{tag}__gt_num']), n_edge)
+        assert abs(float(res['mean_error']) - float(g[f'{tag}__mean_error'])) < 1e-3
+        assert np.allclose(res['errors'].cpu().numpy(), g[f'{tag}__errors'], rtol=1e-5, atol=1e-5 * 512)
 
 
 def test_val_key_points_empty_and_unknown_mode():
@@ -675,7 +723,8 @@ def test_lightglue_extract_batched_against_oracle():
 
 def test_lk_tracker_matches_reference_fixtures(golden):
     """optical_flow_tensor (utils/matcher.py:188-203) on the fixtures minted from the reference, the random start
-    replayed; 1e-3 px on every point (float32 Gauss-Newton iteration; measured ~1e-5)."""
+    replayed.  Up to 40 float32 Gauss-Newton steps per level over win^2*C-sample sums: the reference's own CPU result and
+    its numpy restatement differ by up to 1.5e-5 px (oracle/REFCHECK.log); LK_TOL is the bound asserted here."""
     from keypoint_bench_b200.utils.matcher import OpticalFlow
     from oracle.make_golden import LK_CASES
     g = golden('ref_lk.npz')
@@ -687,7 +736,8 @@ def test_lk_tracker_matches_reference_fixtures(golden):
         out, err = OpticalFlow(params)(img0, img1, pts, pts, start=start)
         assert out.shape == (1, n, 2) and err.shape == (1, n)
         d = np.abs(out[0].cpu().numpy() - g[f'{tag}__out']).max()
-        assert d < 1e-3, (tag, d)
+        print(f'LK max |gpu - reference| {tag}: {d:.3e} px')
+        assert d < LK_TOL, (tag, d)
 
 
 def test_optical_flow_tensor_dropin_and_batched_against_oracle():
@@ -705,7 +755,9 @@ def test_optical_flow_tensor_dropin_and_batched_against_oracle():
     for b in range(2):
         k = int(cnt[b])
         want = ref_ops.lk_track(img0[b].numpy(), img1[b].numpy(), (pts[b, :k] * scale).numpy(), init[b, :k].numpy(), 11, 2, 8)
-        assert np.abs(out[b, :k].cpu().numpy() - want).max() < 1e-3, b
+        d = np.abs(out[b, :k].cpu().numpy() - want).max()
+        print(f'LK max |gpu - oracle| batch {b}: {d:.3e} px')
+        assert d < LK_TOL, (b, d)
         assert not out[b, k:].any()
     # the drop-in draws its own random start (matcher.py:55): most points must land on the true shift
     torch.manual_seed(0)
@@ -799,8 +851,8 @@ def test_repeat_counts_randomised_sorted_and_exhaustive_paths(seed):
         assert np.array_equal(errors[i, :A], (dm.min(axis=1) * np.float32(s10)).astype(np.float32)), (seed, i, scale)
 
 
-def test_repeat_counts_sorted_and_tile_walking_kernels_agree(monkeypatch):
-    """The y-sorted sweeps (default up to 4096 points per side) and the tile-walking pruned kernels (KB_REP_NO_SORT, also
+def test_repeat_counts_sorted_and_tile_walking_kernels_agree():
+    """The y-sorted sweeps (default up to 4096 points per side) and the tile-walking pruned kernels (KB_KNOB_REP_NO_SORT, also
     the path for larger sets) must give identical statistics and per-row minima."""
     rng = np.random.default_rng(99)
     b, a_max, b_max = 4, 1500, 1300
@@ -815,9 +867,9 @@ def test_repeat_counts_sorted_and_tile_walking_kernels_agree(monkeypatch):
     t = lambda x: torch.from_numpy(x).to(DEV)      # noqa: E731
     args = (t(k0c), t(k01c), na.to(DEV), t(k1c), t(k10c), nb.to(DEV), 512.0, 512.0, 3.0)
     s_sorted, e_sorted, _ = ops().repeat_batched(*args, want_errors=True)
-    monkeypatch.setenv('KB_REP_NO_SORT', '1')
-    s_tiles, e_tiles, _ = ops().repeat_batched(*args, want_errors=True)
-    monkeypatch.delenv('KB_REP_NO_SORT')
+    from keypoint_bench_b200 import _lib
+    with ops().debug_knob(_lib.KB_KNOB_REP_NO_SORT, 1):
+        s_tiles, e_tiles, _ = ops().repeat_batched(*args, want_errors=True)
     assert torch.equal(s_sorted, s_tiles)
     assert float(s_sorted[0, 0]) > 500
     for i in range(b):
