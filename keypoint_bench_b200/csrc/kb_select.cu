@@ -79,10 +79,13 @@ __global__ void __launch_bounds__(NT) select_kernel(SelectParams p) {
     uint64_t* cand = p.cand + (size_t)b * p.cand_cap;
 
     // ---- 1. raster-order compaction of (inside border) && (v > threshold) ---------------------
+    // remove_border_points ZEROES the border (extracter.py:177-188) and the comparison is `> threshold`
+    // (extracter.py:149): with a negative threshold the zeroed border pixels qualify too, as (x, y, 0) rows.
     const int y_lo = p.border, y_hi = H - p.border, x_lo = p.border, x_hi = W - p.border;
+    const bool border_counts = p.threshold < 0.0f && p.border > 0;
     int K = 0;
-    if (y_hi > y_lo && x_hi > x_lo) {
-        const int lo = y_lo * W, hi = y_hi * W;
+    if ((y_hi > y_lo && x_hi > x_lo) || border_counts) {
+        const int lo = border_counts ? 0 : y_lo * W, hi = border_counts ? H * W : y_hi * W;
         // 16 consecutive pixels per thread and step (four 16-byte loads when the row base allows it): one block-wide
         // scan per 16 K pixels instead of one per 4 K
         constexpr int PX = 16;
@@ -101,12 +104,15 @@ __global__ void __launch_bounds__(NT) select_kernel(SelectParams p) {
                 for (int e = 0; e < PX; ++e) v[e] = i0 + e < hi ? img[i0 + e] : 0.0f;
             }
             unsigned q = 0u;
-            int col = i0 < hi ? i0 % W : 0;
+            int row = i0 < hi ? i0 / W : 0;
+            int col = i0 < hi ? i0 - row * W : 0;
 #pragma unroll
             for (int e = 0; e < PX; ++e) {
-                // extracter.py:149 (strict); columns inside the border only
-                if (i0 + e < hi && col >= x_lo && col < x_hi && v[e] > p.threshold) q |= 1u << e;
-                if (++col == W) col = 0;
+                // extracter.py:149 (strict); columns inside the border only (rows too when the border counts)
+                const bool inside = col >= x_lo && col < x_hi && (!border_counts || (row >= y_lo && row < y_hi));
+                if (border_counts && !inside) v[e] = 0.0f;
+                if (i0 + e < hi && (inside || border_counts) && v[e] > p.threshold) q |= 1u << e;
+                if (++col == W) { col = 0; ++row; }
             }
             int tot;
             int off = K + kb::block_exclusive_scan(__popc(q), s_scan, &tot);

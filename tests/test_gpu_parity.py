@@ -15,7 +15,7 @@ from oracle import ref_ops
 pytestmark = pytest.mark.gpu
 
 DEV = 'cuda'
-LK_TOL = 1e-4       # px; tracked positions of the Lucas-Kanade matcher (see test_lk_tracker_matches_reference_fixtures)
+LK_TOL = 2e-5       # px (measured on B200: <= 1.53e-5 against the reference fixtures, 7.6e-6 against the oracle); tracked positions of the Lucas-Kanade matcher (see test_lk_tracker_matches_reference_fixtures)
 
 
 def ops():

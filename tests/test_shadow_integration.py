@@ -67,7 +67,7 @@ def test_reference_evaluators_run_unmodified_on_the_dropins(shadowed_reference, 
               'MHA_params': {'th': [3, 5, 7]}}
     for i in range(2):
         pair = synth.make_pair(cfg, 2, 40 + i)
-        img = torch.zeros(1, 3, cfg.height, cfg.width)
+        img = torch.zeros(1, 3, cfg.height, cfg.width, device=DEV)     # the batch's image lives where the maps do (MHA.py:41-42)
         s0, s1 = pair['score0'].to(DEV), pair['score1'].to(DEV)
         d0, d1 = pair['desc0'].to(DEV), pair['desc1'].to(DEV)
         w01, w10 = pair['warp01'], pair['warp10']                     # 0-dim int64 tensors, as the collate leaves them
