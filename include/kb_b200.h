@@ -50,6 +50,9 @@ KB_API const char* kb_error_string(int code);
 #define KB_KNOB_TC_CLUSTER 1  /* 2 = CTA-pair (cta_group::2) tensor-core search kernel; default 1 */
 #define KB_KNOB_TC_DEBUG 2    /* default 0 */
 #define KB_KNOB_REP_NO_SORT 3 /* 1 = kb_repeat_counts uses the tile-walking kernels instead of the sorted sweeps */
+#define KB_KNOB_TC_ONE_PASS 4 /* 1 = tensor-core cross-check from column-group maxima of ONE Gram pass (redux.sync in the
+                               * epilogue) instead of a second Gram with rows and columns swapped; same pairs, measured
+                               * slower, kept for A/B measurements.  Set it before sizing the workspace. */
 KB_API int kb_debug_knob(int knob, int value);
 
 /* ---------------------------------------------------------------------------------------------

@@ -15,14 +15,27 @@
 //                   through a TMA ring sized from the free shared memory.  The epilogue folds every 128x256 tile
 //                   into per-row running (best, second, third, argbest, argsecond) with software-pipelined
 //                   tcgen05.ld.32x32b.x16; the [n,m] matrix never leaves the SM.  Both directions (rows->cols,
-//                   cols->rows for the cross-check) are work items of the same launch.  nn_top2_kernel<2> is the
+//                   cols->rows for the cross-check) are work items of the same launch.  KB_KNOB_TC_ONE_PASS selects
+//                   the one-pass cross-check instead: while a warp holds 32 rows x 16 columns of a tile it also
+//                   reduces every COLUMN over its 32 rows (redux.sync.max on the order-preserving bits of
+//                   u = x.y - |x|^2/2 + offset) to the (largest, second largest) of that 32-row group, stored per
+//                   (group, column); whether row i is column j's best is then decided from those group maxima
+//                   (resolve / gate below), exactly or with a float64 rescan of the column when it is too close to
+//                   call.  Same pairs; measured SLOWER than the second Gram (two dependent redux.sync per column cost
+//                   more than folding the transposed tile in-lane), so it is not the default.  nn_top2_kernel<2, .> is the
 //                   CTA-pair variant (cluster of 2, cta_group::2, M=256), selectable with kb_debug_knob(KB_KNOB_TC_CLUSTER, 2).
 //   resolve_kernel  merges the column slices; best-second above twice the a-priori error bound of the split
 //                   product certifies the argmax; best-third above it leaves two candidates that are compared
 //                   exactly in float64; anything else is queued for rescan_kernel, an exact float64 scan of the
 //                   row (first of ties, as np.argmin).
-//   gate_kernel     mutual check + strict < max_distance: decided from the certified tensor-core score when the
-//                   caller wants pairs only, float64 distance inside the error band or when distances are returned.
+//                   With the one-pass cross-check its second grid plane reduces the group maxima of every column to
+//                   (largest, largest of the rest, group of the largest).
+//   gate_kernel     mutual check + strict < max_distance.  Row i (best column j, column-side score u(i,j)) is mutual
+//                   when u(i,j) is the largest of its group and beats everything else of column j by more than twice
+//                   the error bound, not mutual when something beats it by more than that, and otherwise queued for an
+//                   exact float64 rescan of column j (second rescan launch, second gate launch for those rows).  The
+//                   distance gate is decided from the certified tensor-core score when the caller wants pairs only,
+//                   float64 distance inside the error band or when distances are returned.
 //   pairs_kernel    ordered compaction (per pair).
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -42,8 +55,11 @@ constexpr int TMEM_COLS = 512;                   // two 256-column fp32 accumula
 constexpr int SLOT_BYTES = 2 * TILE_BYTES;       // one database block: 256 rows x 64 k (two TMA boxes)
 
 struct Top2 {                 // per query row: three best scores, indices of the best two (32 bytes)
-    float best, second, third, pad0;
-    int idx, idx2, pad1, pad2;
+    float best, second, third;
+    float u1;                 // column-side score u = x.y - |x|^2/2 + offset of (row, idx) -- one-pass cross-check
+    int idx, idx2;
+    float u2;                 // ... of (row, idx2)
+    int pad;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -287,6 +303,11 @@ struct MainParams {
     int B, n_max, m_max, cs0, cs1, KB, tiles0, tiles1, n_dirs, n_slots;
     int cl;                  // CTAs per cluster (1 or 2): a pair works on two adjacent query tiles and shares the database stream
     int align_slack;         // bytes the kernel may spend on aligning its tiles to 1024
+    float2* gm;              // [B, gm_groups, cs1] (largest, second largest) column-side score of every 32-row group
+    const unsigned int* maxn0;   // [B] max |x|^2, max |y|^2 (float bits) from prep_kernel: the offset of the column-side scores
+    const unsigned int* maxn1;
+    int gm_groups;           // 4 * tiles0
+    int colside;             // 1 = one-pass cross-check (direction-0 items only, group maxima per column)
     long long* prof;         // timing experiments only (KB_KNOB_TC_DEBUG & 4): per CTA 8 cycle counters, see scripts/tc_pipeline_profile.py
     int dbg;                 // timing experiments only (KB_KNOB_TC_DEBUG): 1 = epilogue skips the fold, 2 = no MMAs issued
 };
@@ -316,7 +337,7 @@ __device__ __forceinline__ bool decode_item(const MainParams& p, int item, int c
     return group * CL * BM < it.n_q && it.n_db > 0;
 }
 
-template <int CL>
+template <int CL, bool COLSIDE>
 __global__ void __launch_bounds__(NT, 1) nn_top2_kernel(const __grid_constant__ CUtensorMap map0,
                                                         const __grid_constant__ CUtensorMap map1, MainParams p) {
     extern __shared__ __align__(1024) unsigned char smem_dyn[];
@@ -549,6 +570,20 @@ __global__ void __launch_bounds__(NT, 1) nn_top2_kernel(const __grid_constant__ 
             // here: near-ties are settled exactly in the resolver.)
             float b1 = -CUDART_INF_F, b2 = -CUDART_INF_F, b3 = -CUDART_INF_F;
             int i1 = 0, i2 = 0;
+            float u1 = 0.0f, u2 = 0.0f;
+            // One-pass cross-check: u(i,j) = x_i.y_j - |x_i|^2/2 + offset ranks the ROWS of column j like their distances
+            // do.  The offset makes every valid score positive, so its float bits order like signed integers and
+            // redux.sync.max.s32 reduces a column over the warp's 32 rows; rows beyond the count carry -inf (negative as
+            // an integer, never a maximum).
+            constexpr bool colside = COLSIDE;
+            float kx = 0.0f;
+            float2* gmrow = nullptr;
+            if constexpr (colside) {
+                const float mx0 = __uint_as_float(p.maxn0[it.b]), mx1 = __uint_as_float(p.maxn1[it.b]);
+                const float off = (0.5f * mx0 + sqrtf(mx0 * mx1)) * 1.01f + 1e-6f;
+                kx = off + __ldg(p.c0 + (size_t)it.b * p.cs0 + it.q_row0 + row_in_tile);      // -inf beyond the count
+                gmrow = p.gm + ((size_t)it.b * p.gm_groups + (it.q_row0 >> 5) + quad) * p.cs1;
+            }
             const int n_ct = (it.n_db + BN - 1) / BN;
             // Each warp sees only a quarter of the columns, so on its own its third-best -- the threshold below
             // which columns are skipped -- rises four times more slowly than the row's.  After every tile a warp
@@ -574,6 +609,11 @@ __global__ void __launch_bounds__(NT, 1) nn_top2_kernel(const __grid_constant__ 
                     t[1] = __uint_as_float(v[4 * q + 1]) + t4.y;
                     t[2] = __uint_as_float(v[4 * q + 2]) + t4.z;
                     t[3] = __uint_as_float(v[4 * q + 3]) + t4.w;
+                    float uu[4] = {0.f, 0.f, 0.f, 0.f};
+                    if constexpr (colside) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) uu[e] = __uint_as_float(v[4 * q + e]) + kx;
+                    }
                     const float m4 = fmaxf(fmaxf(t[0], t[1]), fmaxf(t[2], t[3]));
                     // groups of four columns that cannot enter any lane's top-3 are skipped with one warp vote
                     if (__any_sync(0xffffffffu, m4 > b3)) {
@@ -587,6 +627,23 @@ __global__ void __launch_bounds__(NT, 1) nn_top2_kernel(const __grid_constant__ 
                             b1 = fmaxf(b1, te);
                             i2 = g1 ? i1 : (g2 ? j : i2);
                             i1 = g1 ? j : i1;
+                            if constexpr (colside) {
+                                u2 = g1 ? u1 : (g2 ? uu[e] : u2);
+                                u1 = g1 ? uu[e] : u1;
+                            }
+                        }
+                    }
+                    if constexpr (colside) {
+                        // every column: (largest, second largest) score over this warp's 32 rows
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int key = __float_as_int(uu[e]);
+                            const int m1 = __reduce_max_sync(0xffffffffu, key);
+                            const bool top = key == m1;
+                            const unsigned eq = __ballot_sync(0xffffffffu, top);
+                            int m2 = __reduce_max_sync(0xffffffffu, top ? (int)0x80000000 : key);
+                            if (eq & (eq - 1u)) m2 = m1;                          // the largest occurs twice
+                            if (lane == 0) gmrow[j0 + 4 * q + e] = make_float2(__int_as_float(m1), __int_as_float(m2));
                         }
                     }
                 }
@@ -646,8 +703,8 @@ __global__ void __launch_bounds__(NT, 1) nn_top2_kernel(const __grid_constant__ 
             const int qi = it.q_row0 + row_in_tile;
             if (qi < it.n_q) {
                 Top2 o;
-                o.best = b1; o.second = b2; o.third = fminf(b3, b2); o.pad0 = 0.0f;     // b3 may hold the adopted bound
-                o.idx = i1; o.idx2 = i2; o.pad1 = 0; o.pad2 = 0;
+                o.best = b1; o.second = b2; o.third = fminf(b3, b2);                    // b3 may hold the adopted bound
+                o.u1 = u1; o.idx = i1; o.idx2 = i2; o.u2 = u2; o.pad = 0;
                 (it.dir ? p.res1 : p.res0)[((size_t)it.q_base + qi) * EPI_SLICES + slice] = o;
             }
         }
@@ -685,6 +742,10 @@ struct ResolveParams {
     int* n_exact;            // [1] number of rows queued for the exact rescan
     int* n_pair;             // [1] rows settled by the two-candidate exact check (statistics)
     float* tsel;             // [B*n_max] tensor-core score t = x.y - |y|^2/2 of the direction-0 winner (NaN: unknown)
+    float* usel;             // [B*n_max] its column-side score u (one-pass cross-check; NaN: unknown)
+    const float2* gm;        // [B, gm_groups, cs1] group maxima of the column-side scores (search kernel)
+    int4* colinfo;           // [B*m_max] per column: (largest u, largest of everything else, group of the largest, 0) as int bits
+    int gm_groups, cs1, colside;
     int2* list;              // [list_cap] queued rows: (dir | b << 1, query row)
     int list_cap;
     struct RescanPart* parts;   // [list_cap, RESCAN_SPLIT] partial minima of the split rescan
@@ -721,12 +782,30 @@ __global__ void __launch_bounds__(256) resolve_kernel(ResolveParams p) {
     const int q = blockIdx.x * 256 + threadIdx.x, lane = threadIdx.x & 31;
     const int b = blockIdx.y, dir = blockIdx.z;
     const int n = p.n0 ? p.n0[b] : p.n_max, m = p.n1 ? p.n1[b] : p.m_max;
+    if (p.colside && dir == 1) {
+        // One-pass cross-check: column q of the database.  Over the 32-row groups of the query rows (every group of a
+        // row tile that the search kernel ran is written; rows beyond the count score -inf): the largest group maximum,
+        // its group, and the largest of EVERYTHING ELSE = max(second largest group maximum, second largest inside the
+        // winning group).  Scores are positive floats (or -inf), so their bits compare as signed integers.
+        if (q >= m || n <= 0) return;
+        const int n_groups = 4 * ((n + BM - 1) / BM);
+        const float2* g = p.gm + (size_t)b * p.gm_groups * p.cs1 + q;
+        int v1 = (int)0x80000000, v2 = (int)0x80000000, s1 = (int)0x80000000, g1 = 0;
+        for (int k = 0; k < n_groups; ++k) {
+            const float2 e = __ldg(g + (size_t)k * p.cs1);
+            const int a = __float_as_int(e.x), a2 = __float_as_int(e.y);
+            if (a > v1) { v2 = v1; v1 = a; g1 = k; s1 = a2; }
+            else if (a > v2) v2 = a;                               // a == v1 lands here: a tie between groups
+        }
+        p.colinfo[(size_t)b * p.m_max + q] = make_int4(v1, v2 > s1 ? v2 : s1, g1, 0);
+        return;
+    }
     const int nq = dir ? m : n, ndb = dir ? n : m;
     if (ndb <= 0) return;
     const int q_stride = dir ? p.m_max : p.n_max, db_stride = dir ? p.n_max : p.m_max;
     int mode = 0;                        // 0 nothing to do, 1 certified, 2 two candidates, 3 rescan
     int j1 = 0, j2 = 0;
-    float tbest = 0.0f, tsecond = 0.0f;
+    float tbest = 0.0f, tsecond = 0.0f, ubest = 0.0f, usecond = 0.0f;
     if (q < nq) {
         Top2 r = (dir ? p.res1 : p.res0)[((size_t)b * q_stride + q) * EPI_SLICES];
 #pragma unroll
@@ -734,6 +813,7 @@ __global__ void __launch_bounds__(256) resolve_kernel(ResolveParams p) {
             const Top2 o = (dir ? p.res1 : p.res0)[((size_t)b * q_stride + q) * EPI_SLICES + sl];
             const float cand[3] = {o.best, o.second, o.third};
             const int cix[3] = {o.idx, o.idx2, 0};
+            const float cu[3] = {o.u1, o.u2, 0.0f};
 #pragma unroll
             for (int e = 0; e < 3; ++e) {
                 const float te = cand[e];
@@ -743,6 +823,8 @@ __global__ void __launch_bounds__(256) resolve_kernel(ResolveParams p) {
                 r.best = fmaxf(r.best, te);
                 r.idx2 = g1 ? r.idx : (g2 ? cix[e] : r.idx2);
                 r.idx = g1 ? cix[e] : r.idx;
+                r.u2 = g1 ? r.u1 : (g2 ? cu[e] : r.u2);
+                r.u1 = g1 ? cu[e] : r.u1;
             }
         }
         const float nq2 = (dir ? p.norm2_1 : p.norm2_0)[(size_t)b * q_stride + q];
@@ -752,6 +834,7 @@ __global__ void __launch_bounds__(256) resolve_kernel(ResolveParams p) {
         const float e = 6.2e-5f * sqrtf(nq2) * sqrtf(dbmax2) + 3.1e-5f * dbmax2;
         j1 = r.idx; j2 = r.idx2;
         tbest = r.best; tsecond = r.second;
+        ubest = r.u1; usecond = r.u2;
         const bool ok1 = j1 >= 0 && j1 < ndb, ok2 = j2 >= 0 && j2 < ndb && j2 != j1;
         if (ok1 && (r.best - r.second) > 2.0f * e) mode = 1;
         else if (ok1 && ok2 && (r.best - r.third) > 2.0f * e) mode = 2;
@@ -759,7 +842,10 @@ __global__ void __launch_bounds__(256) resolve_kernel(ResolveParams p) {
     }
     int* nn = dir ? p.nn1 : p.nn0;
     if (mode == 1) nn[(size_t)b * q_stride + q] = j1;
-    if (dir == 0 && mode != 0) p.tsel[(size_t)b * q_stride + q] = mode == 1 ? tbest : CUDART_NAN_F;
+    if (dir == 0 && mode != 0) {
+        p.tsel[(size_t)b * q_stride + q] = mode == 1 ? tbest : CUDART_NAN_F;
+        p.usel[(size_t)b * q_stride + q] = mode == 1 ? ubest : CUDART_NAN_F;
+    }
     if (mode == 3) {
         const int slot = atomicAdd(p.n_exact, 1);
         if (slot < p.list_cap) p.list[slot] = make_int2(dir | (b << 1), q);
@@ -776,10 +862,14 @@ __global__ void __launch_bounds__(256) resolve_kernel(ResolveParams p) {
         const double d1 = warp_dist2(Qb + (size_t)qq * p.D, DBs + (size_t)a1 * p.D, p.D, lane);
         const double d2 = warp_dist2(Qb + (size_t)qq * p.D, DBs + (size_t)a2 * p.D, p.D, lane);
         const float t1 = __shfl_sync(0xffffffffu, tbest, src), t2 = __shfl_sync(0xffffffffu, tsecond, src);
+        const float w1 = __shfl_sync(0xffffffffu, ubest, src), w2 = __shfl_sync(0xffffffffu, usecond, src);
         if (lane == 0) {
             const bool first = d1 < d2 || (d1 == d2 && a1 < a2);
             nn[(size_t)b * q_stride + qq] = first ? a1 : a2;
-            if (dir == 0) p.tsel[(size_t)b * q_stride + qq] = first ? t1 : t2;
+            if (dir == 0) {
+                p.tsel[(size_t)b * q_stride + qq] = first ? t1 : t2;
+                p.usel[(size_t)b * q_stride + qq] = first ? w1 : w2;
+            }
             if (p.n_pair) atomicAdd(p.n_pair, 1);
         }
     }
@@ -892,12 +982,13 @@ __global__ void __launch_bounds__(RESCAN_WARPS * 32) rescan_kernel(ResolveParams
                     if (dt < best || (dt == best && jt < bjj)) { best = dt; bjj = jt; }
                 }
                 (dir ? p.nn1 : p.nn0)[(size_t)b * q_stride + q] = bjj;
+                p.tickets[e] = 0;                                          // ready for the next rescan launch of this call
             }
         }
     }
 }
 
-// One warp per row of d0: mutual check, float64 distance of the surviving pair, strict < max_distance.
+// One warp per four rows of d0: mutual check, float64 distance of the surviving pair, strict < max_distance.
 struct GateParams {
     const float* d0;
     const float* d1;
@@ -905,33 +996,72 @@ struct GateParams {
     const int* n1;
     const int* nn0;
     const int* nn1;
-    int* keep_j;             // [B*n_max] matched column or -1
+    int* keep_j;             // [B*n_max] matched column, -1 (no match) or -2 (waiting for the exact rescan of its column)
     double* dist_i;          // [B*n_max]
     const float* tsel;       // [B*n_max] tensor-core score of the winner (NaN: unknown)
+    const float* usel;       // [B*n_max] its column-side score (NaN: unknown)
+    const int4* colinfo;     // [B*m_max] see resolve_kernel
     const float* norm2_0;    // [B*n_max] |x|^2
+    const unsigned int* maxn0;   // [B] max |x|^2 (float bits)
     const unsigned int* maxn1;   // [B] max |y|^2 (float bits)
-    int n_max, m_max, D, cross_check, want_dist;
+    int2* list2;             // columns queued for the exact rescan: (1 | b << 1, column)
+    int* n_list2;
+    int list2_cap;
+    int n_max, m_max, D, cross_check, want_dist, colside;
     double max_distance;
 };
 
-__global__ void __launch_bounds__(256) gate_kernel(GateParams p) {
+// pass 0: every row.  pass 1 (after the rescan of the queued columns): the rows left at -2.
+__global__ void __launch_bounds__(256) gate_kernel(GateParams p, int pass) {
     constexpr int G = 4;                  // rows per warp, their loads issued together
     const int i0 = ((blockIdx.x * 256 + threadIdx.x) >> 5) * G, lane = threadIdx.x & 31;
     const int b = blockIdx.y;
     const int n = p.n0 ? p.n0[b] : p.n_max, m = p.n1 ? p.n1[b] : p.m_max;
     if (i0 >= n || m <= 0) return;
+    if (pass == 1 && *p.n_list2 == 0) return;
     int jj[G];
     bool live[G];
+    const float xmax2 = __uint_as_float(p.maxn0[b]), ymax2 = __uint_as_float(p.maxn1[b]);
 #pragma unroll
     for (int g = 0; g < G; ++g) {
         const int i = i0 + g;
-        jj[g] = i < n ? p.nn0[(size_t)b * p.n_max + i] : 0;
-        live[g] = i < n && (!p.cross_check || p.nn1[(size_t)b * p.m_max + jj[g]] == i);
+        const size_t row = (size_t)b * p.n_max + i;
+        jj[g] = 0;
+        live[g] = false;
+        if (i >= n) continue;
+        jj[g] = p.nn0[row];
+        int st;                             // 0 no match, 1 mutual, 2 too close to call, 3 leave the row alone
+        if (pass == 1) {
+            st = p.keep_j[row] == -2 ? (p.nn1[(size_t)b * p.m_max + jj[g]] == i ? 1 : 0) : 3;
+        } else if (!p.cross_check) {
+            st = 1;
+        } else if (!p.colside) {
+            st = p.nn1[(size_t)b * p.m_max + jj[g]] == i ? 1 : 0;
+        } else {
+            // Is row i the best row of column j?  u(i,j) against the group maxima of column j.  |u - exact| <= e for
+            // every row, so a lead of more than 2 e settles it either way; anything closer is rescanned exactly.
+            const float us = p.usel[row];
+            const int4 ci = p.colinfo[(size_t)b * p.m_max + jj[g]];
+            const float off = (0.5f * xmax2 + sqrtf(xmax2 * ymax2)) * 1.01f + 1e-6f;
+            const float e = 6.2e-5f * sqrtf(xmax2) * sqrtf(ymax2) + 3.1e-5f * xmax2 + 6.0e-7f * off;
+            st = 2;
+            if (us == us) {
+                const float v1 = __int_as_float(ci.x), rest = __int_as_float(ci.y);
+                if (ci.z == (i >> 5) && __float_as_int(us) == ci.x) { if (us - rest > 2.0f * e) st = 1; }
+                else if (v1 - us > 2.0f * e) st = 0;
+            }
+        }
+        if (st == 2 && lane == 0) {
+            p.keep_j[row] = -2;
+            const int slot = atomicAdd(p.n_list2, 1);
+            if (slot < p.list2_cap) p.list2[slot] = make_int2(1 | (b << 1), jj[g]);
+        }
+        if (st == 0 && lane == 0) p.keep_j[row] = -1;
+        live[g] = st == 1;
     }
     if (!p.want_dist) {
         // The caller only wants the pairs: |x - y|^2 = |x|^2 - 2 t with t = x.y - |y|^2/2 from the tensor cores,
         // known to within `err`; the float64 distance is evaluated only where that cannot decide d < max_distance.
-        const float ymax2 = __uint_as_float(p.maxn1[b]);
         const double md2 = p.max_distance * p.max_distance;
         bool any_exact = false;
 #pragma unroll
@@ -945,18 +1075,11 @@ __global__ void __launch_bounds__(256) gate_kernel(GateParams p) {
                 if (lane == 0) p.keep_j[row] = jj[g];
                 live[g] = false;
             } else if (d2 - err >= md2) {               // certainly outside
-                live[g] = false;                        // (keep_j is written as -1 below)
+                live[g] = false;
                 if (lane == 0) p.keep_j[row] = -1;
             } else {
                 any_exact = true;                       // NaN or too close to call: exact evaluation below
             }
-        }
-        // rows that were not live at all
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-            const int i = i0 + g;
-            if (lane == 0 && i < n && !(!p.cross_check || p.nn1[(size_t)b * p.m_max + jj[g]] == i))
-                p.keep_j[(size_t)b * p.n_max + i] = -1;
         }
         if (!any_exact) return;
     }
@@ -998,11 +1121,10 @@ __global__ void __launch_bounds__(256) gate_kernel(GateParams p) {
     for (int g = 0; g < G; ++g) {
         double a = acc[g];
         for (int s = 16; s > 0; s >>= 1) a += __shfl_xor_sync(0xffffffffu, a, s);
-        const int i = i0 + g;
-        if (lane == 0 && i < n && (p.want_dist || live[g])) {
+        if (lane == 0 && live[g]) {
             const double d = sqrt(a);
-            p.keep_j[(size_t)b * p.n_max + i] = (live[g] && d < p.max_distance) ? jj[g] : -1;
-            p.dist_i[(size_t)b * p.n_max + i] = d;
+            p.keep_j[(size_t)b * p.n_max + i0 + g] = d < p.max_distance ? jj[g] : -1;
+            p.dist_i[(size_t)b * p.n_max + i0 + g] = d;
         }
     }
 }
@@ -1111,6 +1233,11 @@ static TcLayout tc_layout(int B, int n_max, int m_max, int D) {
     add((size_t)B * (n_max + m_max) * 8 * 16);  // rescan partial minima
     add((size_t)B * (n_max + m_max) * 4);       // rescan tickets
     add((size_t)B * n_max * 4);                 // tensor-core score of the direction-0 winners
+    add((size_t)B * n_max * 4);                 // ... and their column-side score
+    if (kb_knobs[KB_KNOB_TC_ONE_PASS])
+        add((size_t)B * 4 * L.tiles0 * L.cs1 * 8);  // group maxima of the column-side scores (one-pass cross-check only)
+    add((size_t)B * m_max * 16);                // per-column summary of the group maxima
+    add((size_t)B * n_max * 8);                 // columns queued for the exact rescan
     add(8 * 512 * 8);                           // pipeline wait counters (KB_KNOB_TC_DEBUG & 4)
     L.bytes = n + 1024;
     return L;
@@ -1130,6 +1257,10 @@ struct TcBuffers {
     void* parts;
     int* tickets;
     float* tsel;
+    float* usel;
+    float2* gm;
+    int4* colinfo;
+    int2* list2;
     long long* prof;
     bool ok;
 };
@@ -1146,7 +1277,7 @@ static TcBuffers tc_carve(void* ws, size_t ws_bytes, int B, int n_max, int m_max
     t.maxn0 = arena.take<unsigned int>(B);
     t.maxn1 = arena.take<unsigned int>(B);
     // maxn0, maxn1, n_exact and the rescan tickets are zeroed per call: kept adjacent for one memset
-    t.n_exact = arena.take<int>(2);
+    t.n_exact = arena.take<int>(4);             // n_exact, n_pair, n_list2, -
     t.tickets = arena.take<int>((size_t)B * (n_max + m_max));
     t.zero_bytes = (size_t)((char*)(t.tickets + (size_t)B * (n_max + m_max)) - (char*)t.maxn0);
     t.res0 = arena.take<kbtc::Top2>((size_t)B * n_max * kbtc::EPI_SLICES);
@@ -1158,6 +1289,10 @@ static TcBuffers tc_carve(void* ws, size_t ws_bytes, int B, int n_max, int m_max
     t.keep_j = arena.take<int>((size_t)B * n_max);
     t.parts = arena.take<char>((size_t)B * (n_max + m_max) * 8 * 16);
     t.tsel = arena.take<float>((size_t)B * n_max);
+    t.usel = arena.take<float>((size_t)B * n_max);
+    t.gm = kb_knobs[KB_KNOB_TC_ONE_PASS] ? arena.take<float2>((size_t)B * 4 * L.tiles0 * L.cs1) : nullptr;
+    t.colinfo = arena.take<int4>((size_t)B * m_max);
+    t.list2 = arena.take<int2>((size_t)B * n_max);
     t.prof = arena.take<long long>(8 * 512);
     t.ok = arena.ok();
     return t;
@@ -1205,7 +1340,7 @@ int kb_match_tc_run(const float* d0, const float* d1, const int* n0, const int* 
             KB_CUDA_TRY(cudaMemsetAsync(maxn1, 0, (size_t)B * 4, st));
         }
         if (phases & 4) {
-            KB_CUDA_TRY(cudaMemsetAsync(n_exact, 0, 8, st));
+            KB_CUDA_TRY(cudaMemsetAsync(n_exact, 0, 16, st));
             KB_CUDA_TRY(cudaMemsetAsync(tb.tickets, 0, (size_t)B * (n_max + m_max) * 4, st));
         }
     }
@@ -1254,7 +1389,10 @@ int kb_match_tc_run(const float* d0, const float* d1, const int* n0, const int* 
     MainParams mp;
     mp.n0 = n0; mp.n1 = n1; mp.c0 = c0; mp.c1 = c1; mp.res0 = res0; mp.res1 = res1;
     mp.B = B; mp.n_max = n_max; mp.m_max = m_max; mp.cs0 = L.cs0; mp.cs1 = L.cs1; mp.KB = L.KB;
-    mp.tiles0 = L.tiles0; mp.tiles1 = L.tiles1; mp.n_dirs = cross_check ? 2 : 1;
+    // cross-check: the two-direction search (default), or one Gram pass + column-group maxima (KB_KNOB_TC_ONE_PASS)
+    const int colside = (cross_check && kb_knobs[KB_KNOB_TC_ONE_PASS]) ? 1 : 0;
+    mp.tiles0 = L.tiles0; mp.tiles1 = L.tiles1; mp.n_dirs = (cross_check && !colside) ? 2 : 1;
+    mp.gm = tb.gm; mp.maxn0 = maxn0; mp.maxn1 = maxn1; mp.gm_groups = 4 * L.tiles0; mp.colside = colside;
     // after the tiles: barriers (256 bytes), the 2 x 256-float c buffer and the 128-float shared bound; the tiles must start on a
     // 1024-byte boundary (128B swizzle) -- dynamic shared memory normally does, `slack` covers the rest
     const size_t fixed = 256 + 2 * BN * 4 + BM * 4;
@@ -1282,8 +1420,10 @@ int kb_match_tc_run(const float* d0, const float* d1, const int* n0, const int* 
     mp.prof = tb.prof;
     static bool attr_set = false;                 // the opt-in to > 48 KB of dynamic shared memory is per process
     if (!attr_set) {
-        KB_CUDA_TRY(cudaFuncSetAttribute(nn_top2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
-        KB_CUDA_TRY(cudaFuncSetAttribute(nn_top2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+        KB_CUDA_TRY(cudaFuncSetAttribute(nn_top2_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+        KB_CUDA_TRY(cudaFuncSetAttribute(nn_top2_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+        KB_CUDA_TRY(cudaFuncSetAttribute(nn_top2_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+        KB_CUDA_TRY(cudaFuncSetAttribute(nn_top2_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
         attr_set = true;
     }
     const int g0 = (L.tiles0 + cl - 1) / cl, g1 = (L.tiles1 + cl - 1) / cl;
@@ -1291,7 +1431,8 @@ int kb_match_tc_run(const float* d0, const float* d1, const int* n0, const int* 
     const int max_groups = sms / cl;
     const int grid = (n_items < max_groups ? n_items : max_groups) * cl;
     if ((phases & 2) && cl == 1) {
-        nn_top2_kernel<1><<<grid, NT, smem, st>>>(map0, map1, mp);
+        if (colside) nn_top2_kernel<1, true><<<grid, NT, smem, st>>>(map0, map1, mp);
+        else nn_top2_kernel<1, false><<<grid, NT, smem, st>>>(map0, map1, mp);
         KB_LAUNCH_CHECK();
     } else if (phases & 2) {
         cudaLaunchConfig_t cfg = {};
@@ -1300,7 +1441,8 @@ int kb_match_tc_run(const float* d0, const float* d1, const int* n0, const int* 
         attr.id = cudaLaunchAttributeClusterDimension;
         attr.val.clusterDim.x = cl; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
         cfg.attrs = &attr; cfg.numAttrs = 1;
-        KB_CUDA_TRY(cudaLaunchKernelEx(&cfg, nn_top2_kernel<2>, map0, map1, mp));
+        if (colside) KB_CUDA_TRY(cudaLaunchKernelEx(&cfg, nn_top2_kernel<2, true>, map0, map1, mp));
+        else KB_CUDA_TRY(cudaLaunchKernelEx(&cfg, nn_top2_kernel<2, false>, map0, map1, mp));
         KB_LAUNCH_CHECK();
     }
     if (!(phases & 4)) return KB_OK;
@@ -1310,10 +1452,12 @@ int kb_match_tc_run(const float* d0, const float* d1, const int* n0, const int* 
     rp.norm2_0 = norm2_0; rp.norm2_1 = norm2_1; rp.maxn0 = maxn0; rp.maxn1 = maxn1;
     rp.nn0 = nn0; rp.nn1 = nn1; rp.n_exact = n_exact; rp.n_pair = n_exact + 1;
     rp.list = tb.list; rp.list_cap = B * (n_max + m_max);
-    rp.parts = (RescanPart*)tb.parts; rp.tickets = tb.tickets; rp.tsel = tb.tsel;
+    rp.parts = (RescanPart*)tb.parts; rp.tickets = tb.tickets; rp.tsel = tb.tsel; rp.usel = tb.usel;
+    rp.gm = tb.gm; rp.colinfo = tb.colinfo; rp.gm_groups = mp.gm_groups; rp.cs1 = L.cs1; rp.colside = colside;
     rp.B = B; rp.n_max = n_max; rp.m_max = m_max; rp.D = D; rp.n_dirs = mp.n_dirs;
     const int qmax = n_max > m_max ? n_max : m_max;
-    resolve_kernel<<<dim3((qmax + 255) / 256, B, mp.n_dirs), 256, 0, st>>>(rp);
+    // grid plane 1: the other direction's rows (two-pass) or the per-column summary of the group maxima (one-pass)
+    resolve_kernel<<<dim3((qmax + 255) / 256, B, cross_check ? 2 : 1), 256, 0, st>>>(rp);
     KB_LAUNCH_CHECK();
     if ((size_t)D * 4 > 48 * 1024) return KB_ERR_UNSUPPORTED;
     rescan_kernel<<<dim3(RESCAN_SPLIT, sms), RESCAN_WARPS * 32, (size_t)D * 4, st>>>(rp);
@@ -1322,9 +1466,21 @@ int kb_match_tc_run(const float* d0, const float* d1, const int* n0, const int* 
     GateParams gp;
     gp.d0 = d0; gp.d1 = d1; gp.n0 = n0; gp.n1 = n1; gp.nn0 = nn0; gp.nn1 = nn1; gp.keep_j = tb.keep_j; gp.dist_i = d2_0;
     gp.n_max = n_max; gp.m_max = m_max; gp.D = D; gp.cross_check = cross_check; gp.max_distance = max_distance;
-    gp.tsel = tb.tsel; gp.norm2_0 = norm2_0; gp.maxn1 = maxn1; gp.want_dist = dist != nullptr;
-    gate_kernel<<<dim3(((n_max + 3) / 4 * 32 + 255) / 256, B), 256, 0, st>>>(gp);
+    gp.tsel = tb.tsel; gp.usel = tb.usel; gp.colinfo = tb.colinfo; gp.norm2_0 = norm2_0; gp.maxn0 = maxn0; gp.maxn1 = maxn1;
+    gp.list2 = tb.list2; gp.n_list2 = n_exact + 2; gp.list2_cap = B * n_max; gp.colside = colside;
+    gp.want_dist = dist != nullptr;
+    const dim3 gate_grid(((n_max + 3) / 4 * 32 + 255) / 256, B);
+    gate_kernel<<<gate_grid, 256, 0, st>>>(gp, 0);
     KB_LAUNCH_CHECK();
+    if (colside) {
+        // the columns that were too close to call: exact float64 rescan, then the gate for the rows waiting on them
+        ResolveParams rp2 = rp;
+        rp2.list = tb.list2; rp2.n_exact = n_exact + 2; rp2.n_pair = nullptr; rp2.list_cap = B * n_max;
+        rescan_kernel<<<dim3(RESCAN_SPLIT, sms), RESCAN_WARPS * 32, (size_t)D * 4, st>>>(rp2);
+        KB_LAUNCH_CHECK();
+        gate_kernel<<<gate_grid, 256, 0, st>>>(gp, 1);
+        KB_LAUNCH_CHECK();
+    }
 
     PairsParams pp;
     pp.n0 = n0; pp.n1 = n1; pp.keep_j = tb.keep_j; pp.dist_i = d2_0; pp.pairs = pairs; pp.dist = dist;

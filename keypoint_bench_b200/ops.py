@@ -315,7 +315,7 @@ def match_batched(d0: torch.Tensor, d1: torch.Tensor, n0: torch.Tensor | None = 
         check(lib.kb_match_mnn_phases(a.data_ptr(), bm.data_ptr(), _ptr(c0), _ptr(c1), b, n, m, dd, float(max_distance),
                                       int(bool(cross_check)), int(algo), pairs.data_ptr(), _ptr(dist), count.data_ptr(),
                                       ws.data_ptr(), ws.numel(), int(phases), _stream()), 'kb_match_mnn')
-    _count(2 if (algo == 0 or dd > 256) else (6 if phases == 7 else 1))
+    _count(2 if (algo == 0 or dd > 256) else (8 if phases == 7 else 1))   # prep, search, resolve, rescan, gate, rescan, gate, pairs
     if return_ws:
         return pairs, dist, count, ws
     return pairs, dist, count
@@ -323,8 +323,11 @@ def match_batched(d0: torch.Tensor, d1: torch.Tensor, n0: torch.Tensor | None = 
 
 def match_issue_factor(cross_check: bool) -> int:
     """How many times the one-pass 2*n*m*D flops of a pair the tensor-core search issues (bench.py reports it beside the
-    algorithmic figure): 3 split-bf16 products (hi*hi, hi*lo, lo*hi) per direction, one Gram per direction."""
-    return 3 * (2 if cross_check else 1)
+    algorithmic figure): 3 split-bf16 products (hi*hi, hi*lo, lo*hi) per direction, one Gram per direction (one
+    direction only under the one-pass cross-check, KB_KNOB_TC_ONE_PASS)."""
+    one_pass = lib.kb_debug_knob(_lib.KB_KNOB_TC_ONE_PASS, 0)
+    lib.kb_debug_knob(_lib.KB_KNOB_TC_ONE_PASS, one_pass)
+    return 3 * (2 if (cross_check and not one_pass) else 1)
 
 
 def match_tc_debug(ws: torch.Tensor, b: int, n: int, m: int, dd: int) -> dict:
@@ -343,6 +346,7 @@ def match_tc_debug(ws: torch.Tensor, b: int, n: int, m: int, dd: int) -> dict:
         return best, second, idx.gather(1, arg[:, None])[:, 0]
     return {'res0': rec(off[0], b * n), 'res1': rec(off[1], b * m),
             'n_exact': ws[off[2]:off[2] + 4].view(torch.int32), 'n_pair': ws[off[2] + 4:off[2] + 8].view(torch.int32),
+            'n_col_rescan': ws[off[2] + 8:off[2] + 12].view(torch.int32),
             'norm2_0': ws[off[3]:off[3] + 4 * b * n].view(torch.float32),
             'norm2_1': ws[off[4]:off[4] + 4 * b * m].view(torch.float32)}
 

@@ -345,6 +345,42 @@ def test_matcher_cta_pair_kernel_gives_same_pairs():
         assert want.shape[0] > 0
 
 
+@pytest.mark.parametrize('b,n,m,dim,dups', [(3, 1000, 977, 256, 0), (2, 700, 1300, 64, 40), (2, 2048, 2048, 128, 5),
+                                            (1, 4096, 4096, 64, 0), (2, 130, 90, 32, 20), (1, 33, 1, 16, 0)])
+def test_matcher_one_pass_cross_check_equals_two_pass(b, n, m, dim, dups):
+    """KB_KNOB_TC_ONE_PASS decides the cross-check of the tensor-core path from column-group maxima of ONE Gram pass
+    (redux.sync in the epilogue, exact rescan of the columns that are too close to call) instead of the second Gram with
+    rows and columns swapped (the default).  Same pairs -- also with duplicated rows, which tie exactly on a column --
+    and the exact float64 oracle agrees."""
+    from keypoint_bench_b200 import _lib
+    gen = torch.Generator().manual_seed(b * 1000 + n + dim)
+    a = torch.nn.functional.normalize(torch.randn(b, n, dim, generator=gen), dim=2)
+    d = torch.nn.functional.normalize(torch.randn(b, m, dim, generator=gen), dim=2)
+    k = min(n, m) // 2
+    d[:, :k] = a[:, :k] + 0.05 * torch.randn(b, k, dim, generator=gen)
+    for t in range(dups):                                       # row 2t+1 duplicates row 2t: both are column t's best
+        a[:, 2 * t + 1] = a[:, 2 * t]
+    n0 = torch.tensor([n - 13 * i for i in range(b)], dtype=torch.int32)
+    n1 = torch.tensor([max(m - 29 * i, 1) for i in range(b)], dtype=torch.int32)
+    for maxd, cc in ((math.inf, True), (0.9, True)):
+        out = {}
+        for two_pass in (0, 1):
+            with ops().debug_knob(_lib.KB_KNOB_TC_ONE_PASS, 1 - two_pass):
+                p, _, c, ws = ops().match_batched(a.to(DEV), d.to(DEV), n0.to(DEV), n1.to(DEV), maxd, cc, algo=1,
+                                                  return_ws=True, want_dist=False)
+                out[two_pass] = (p.clone(), c.clone(), int(ops().match_tc_debug(ws, b, n, m, dim)['n_col_rescan'][0]))
+        assert torch.equal(out[0][1], out[1][1]), (maxd, out[0][1], out[1][1])
+        for i in range(b):
+            kk = int(out[0][1][i])
+            assert torch.equal(out[0][0][i, :kk], out[1][0][i, :kk]), (maxd, i)
+        assert out[1][2] == 0                                   # the two-pass path never queues a column
+        assert out[0][2] <= b * (2 * dups + 8), out[0][2]       # only the tied columns (and a rare near-tie) are rescanned
+        if dups:
+            assert out[0][2] >= dups
+        _exact_pairs_or_near_tie(out[0][0][0, :int(out[0][1][0])].cpu().numpy().astype(np.int64), a[0, :n0[0]].numpy(),
+                                 d[0, :n1[0]].numpy(), maxd, cc)
+
+
 @pytest.mark.parametrize('algo', [0, 1])
 def test_matcher_ragged_batch_and_ties(algo):
     gen = torch.Generator().manual_seed(11)
