@@ -53,7 +53,12 @@ KB_API const char* kb_error_string(int code);
 #define KB_KNOB_TC_ONE_PASS 4 /* 1 = tensor-core cross-check from column-group maxima of ONE Gram pass (redux.sync in the
                                * epilogue) instead of a second Gram with rows and columns swapped; same pairs, measured
                                * slower, kept for A/B measurements.  Set it before sizing the workspace. */
+#define KB_KNOB_SPARSE_PROF 5 /* 1 = the per-map resolve kernel of kb_detect records clock64 at its phase boundaries */
 KB_API int kb_debug_knob(int knob, int value);
+/* Diagnostics: the 16 values map 0's CTA of the last kb_detect recorded under KB_KNOB_SPARSE_PROF (synchronises):
+ * [0..7] clock64 at start / after the cut / candidates loaded / cell grid built / decisions done / kept compacted /
+ * sorted / rows written, [8] candidates on chip, [9] kept interior, [10] [11] list lengths, [12] attempt. */
+KB_API int kb_debug_sparse_prof(long long* host_out);
 
 /* ---------------------------------------------------------------------------------------------
  * Stage 1a -- fast_nms(image_probs, nms_dist, max_iter, min_value)   utils/extracter.py:6-100

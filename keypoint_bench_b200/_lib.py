@@ -16,13 +16,14 @@ KB_OK = 0
 KB_ERR_BAD_ARG = -1
 KB_ERR_WORKSPACE = -2
 KB_ERR_UNSUPPORTED = -3
-KB_KNOB_TC_CLUSTER, KB_KNOB_TC_DEBUG, KB_KNOB_REP_NO_SORT, KB_KNOB_TC_ONE_PASS = 1, 2, 3, 4
+KB_KNOB_TC_CLUSTER, KB_KNOB_TC_DEBUG, KB_KNOB_REP_NO_SORT, KB_KNOB_TC_ONE_PASS, KB_KNOB_SPARSE_PROF = 1, 2, 3, 4, 5
 
 # name -> (restype, argtypes); mirrors include/kb_b200.h one to one
 PROTOTYPES = {
     'kb_version': (c_int, []),
     'kb_error_string': (ctypes.c_char_p, [c_int]),
     'kb_debug_knob': (c_int, [c_int, c_int]),
+    'kb_debug_sparse_prof': (c_int, [c_void_p]),
     'kb_fast_nms_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
     'kb_fast_nms': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
                             c_size_t, c_void_p]),

@@ -29,6 +29,7 @@ struct SparseParams {
     int B, H, W, r, border, top_k, c_pix;
     int cell_shift, gw, gh;   // coarse grid of the sparse stage
     float threshold, min_score;
+    int prof;                 // KB_KNOB_SPARSE_PROF: map 0's CTA records clock64 at its phase boundaries
 };
 
 

@@ -377,82 +377,181 @@ __device__ void bitonic_desc(uint64_t* a, int n) {
     __syncthreads();
 }
 
-// Same sort with E = n / SP_NT keys per thread held in registers (blocked layout: thread t owns a[t*E .. t*E+E-1]):
-// compare-exchange distances below E stay inside a thread, distances below 32*E are 64-bit warp shuffles, and only
-// the remaining ones go through shared memory -- 15 block-wide barriers instead of 27 (plus 39 warp barriers and a
-// shared-memory round trip per step) for 2048 keys, where the plain version took 45 % of sparse_kernel (44 k cycles;
-// ~34 k with this one: 1024 threads x 66 steps of 64-bit compare-exchanges are issue-bound either way).
+// Same sort by a TEAM of the CTA's first n / E threads with E keys per thread held in registers (blocked layout:
+// thread t owns a[t*E .. t*E+E-1]): compare-exchange distances below E stay inside a thread, distances below 32*E
+// are 64-bit warp shuffles, and only the remaining ones go through shared memory behind a named barrier of the team.
+// The sort is a chain of ~log^2(n)/2 dependent steps, so its time is (steps that synchronise) x (cost of the
+// synchronisation), not instruction issue: with 8 keys per thread 2048 keys need 6 team barriers among 256 threads
+// where one or two keys per thread over all 1024 threads needed 15-27 block-wide ones (34 k cycles -> measured
+// in profiles/r02_sparse_phases.txt).  The rest of the CTA waits at the closing __syncthreads.
 // `spare` (may be null): n more keys of scratch, which saves the second barrier of every shared-memory step.
+__device__ __forceinline__ void team_barrier(int nts) { asm volatile("bar.sync 1, %0;" ::"r"(nts) : "memory"); }
+
 template <int E>
-__device__ void bitonic_desc_regs(uint64_t* a, uint64_t* spare, int n) {
-    const int t = threadIdx.x;
-    uint64_t v[E];
+__device__ void bitonic_desc_team(uint64_t* a, uint64_t* spare, int n) {
+    const int t = threadIdx.x, nts = n / E;               // nts is a multiple of 32
+    if (t < nts) {
+        uint64_t v[E];
 #pragma unroll
-    for (int s = 0; s < E; ++s) v[s] = a[t * E + s];
-    int flip = 0;
-    for (int k = 2; k <= n; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            if (j >= 32 * E) {
-                uint64_t* buf = (spare != nullptr && (flip & 1)) ? spare : a;
-                if (spare == nullptr) __syncthreads();          // everybody has read the previous step's values
+        for (int s = 0; s < E; ++s) v[s] = a[t * E + s];
+        int flip = 0;
+        for (int k = 2; k <= n; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                if (j >= 32 * E) {
+                    uint64_t* buf = (spare != nullptr && (flip & 1)) ? spare : a;
+                    if (spare == nullptr && nts > 32) team_barrier(nts);      // everybody has read the previous step's values
 #pragma unroll
-                for (int s = 0; s < E; ++s) buf[t * E + s] = v[s];
-                __syncthreads();
+                    for (int s = 0; s < E; ++s) buf[t * E + s] = v[s];
+                    team_barrier(nts);
 #pragma unroll
-                for (int s = 0; s < E; ++s) {
-                    const int e = t * E + s, q = e ^ j;
-                    const uint64_t o = buf[q];
-                    const bool up = (e & k) == 0, first = e < q;
-                    const bool take_max = up == first;            // descending block: the lower index keeps the larger key
-                    v[s] = take_max ? (v[s] > o ? v[s] : o) : (v[s] < o ? v[s] : o);
-                }
-                ++flip;
-            } else if (j >= E) {
-                const int lane_mask = j / E;
+                    for (int s = 0; s < E; ++s) {
+                        const int e = t * E + s, q = e ^ j;
+                        const uint64_t o = buf[q];
+                        const bool up = (e & k) == 0, first = e < q;
+                        const bool take_max = up == first;            // descending block: the lower index keeps the larger key
+                        v[s] = take_max ? (v[s] > o ? v[s] : o) : (v[s] < o ? v[s] : o);
+                    }
+                    ++flip;
+                } else if (j >= E) {
+                    const int lane_mask = j / E;
 #pragma unroll
-                for (int s = 0; s < E; ++s) {
-                    const int e = t * E + s;
-                    const uint64_t o = __shfl_xor_sync(0xffffffffu, v[s], lane_mask);
-                    const bool up = (e & k) == 0, first = (e & j) == 0;
-                    const bool take_max = up == first;
-                    v[s] = take_max ? (v[s] > o ? v[s] : o) : (v[s] < o ? v[s] : o);
-                }
-            } else {
-                // j < E: both keys live in this thread; j must be a compile-time constant for v[] to stay in registers
+                    for (int s = 0; s < E; ++s) {
+                        const int e = t * E + s;
+                        const uint64_t o = __shfl_xor_sync(0xffffffffu, v[s], lane_mask);
+                        const bool up = (e & k) == 0, first = (e & j) == 0;
+                        const bool take_max = up == first;
+                        v[s] = take_max ? (v[s] > o ? v[s] : o) : (v[s] < o ? v[s] : o);
+                    }
+                } else {
+                    // j < E: both keys live in this thread; j must be a compile-time constant for v[] to stay in registers
 #pragma unroll
-                for (int J = E / 2; J > 0; J >>= 1) {
-                    if (J == j) {
+                    for (int J = E / 2; J > 0; J >>= 1) {
+                        if (J == j) {
 #pragma unroll
-                        for (int s = 0; s < E; ++s) {
-                            if ((s & J) == 0) {
-                                const int e = t * E + s;
-                                const bool up = (e & k) == 0;
-                                const uint64_t x = v[s], y = v[s | J];
-                                const bool swap = up ? (x < y) : (x > y);
-                                v[s] = swap ? y : x;
-                                v[s | J] = swap ? x : y;
+                            for (int s = 0; s < E; ++s) {
+                                if ((s & J) == 0) {
+                                    const int e = t * E + s;
+                                    const bool up = (e & k) == 0;
+                                    const uint64_t x = v[s], y = v[s | J];
+                                    const bool swap = up ? (x < y) : (x > y);
+                                    v[s] = swap ? y : x;
+                                    v[s | J] = swap ? x : y;
+                                }
                             }
                         }
                     }
                 }
             }
         }
-    }
-    __syncthreads();                                              // the last readers of `a` are done
+        if (nts > 32) team_barrier(nts);                              // the last readers of `a` are done
 #pragma unroll
-    for (int s = 0; s < E; ++s) a[t * E + s] = v[s];
+        for (int s = 0; s < E; ++s) a[t * E + s] = v[s];
+    }
     __syncthreads();
 }
 
-// dispatch on the padded size; `cap` = keys that fit behind a[0..n) for the spare buffer
+// dispatch on the padded size (a power of two); `cap` = keys that fit behind a[0..n) for the spare buffer
 __device__ void sort_desc(uint64_t* a, int n, int cap) {
     uint64_t* spare = (2 * n <= cap) ? a + n : nullptr;
-    switch (n / SP_NT) {
-        case 1: bitonic_desc_regs<1>(a, spare, n); break;
-        case 2: bitonic_desc_regs<2>(a, spare, n); break;
-        case 4: bitonic_desc_regs<4>(a, spare, n); break;
-        default: bitonic_desc(a, n); break;       // fewer than SP_NT keys, or 8+ per thread (measured slower in registers)
+    if (n < 64) { bitonic_desc(a, n); return; }
+    if (n >= 256) bitonic_desc_team<8>(a, spare, n);                  // 32 .. 1024 threads (16 keys per thread would spill
+                                                                      // under the 64-register cap of a 1024-thread CTA)
+    else if (n == 128) bitonic_desc_team<4>(a, spare, n);             // one warp: no barrier at all
+    else bitonic_desc_team<2>(a, spare, n);
+}
+
+// The first `want` keys of the DESCENDING order of src[0..n) into dst (dst must hold n keys and not overlap src).
+// Bucket sort: the keys' upper halves (the score's order-preserving bits) are spread linearly over NBINS buckets
+// between their minimum and maximum, a counting sort puts every key into its bucket, and the buckets that reach
+// into the first `want` places -- a handful of keys each -- are put in order by one thread each.  About ten
+// block-wide barriers and a few passes over the keys, where the bitonic network is a chain of log^2(n)/2 dependent
+// 64-bit compare-exchange steps (2048 keys: 40 k cycles; this: measured in profiles/r02_sparse_phases.txt).
+// Returns false (dst unspecified, src intact) when some bucket is too full for that -- heavily tied scores -- and the
+// caller falls back to the bitonic sort.  `hist` = NBINS + 1 words of scratch.
+constexpr int SORT_BINS = 4096;
+constexpr int SORT_BIN_MAX = 48;
+
+__device__ bool bucket_sort_desc(const uint64_t* src, uint64_t* dst, int n, int want, uint32_t* hist, int* s_scan, int* s_part) {
+    __shared__ uint32_t s_lo, s_hi;
+    __shared__ int s_bad;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // 1. range of the score bits
+    uint32_t lo = 0xffffffffu, hi = 0u;
+    for (int i = threadIdx.x; i < n; i += SP_NT) {
+        const uint32_t k = (uint32_t)(src[i] >> 32);
+        lo = min(lo, k); hi = max(hi, k);
     }
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    uint32_t* s_w = reinterpret_cast<uint32_t*>(s_part);            // SP_NT / 32 words: minima, then maxima
+    if (lane == 0) s_w[warp] = lo;
+    for (int i = threadIdx.x; i <= SORT_BINS; i += SP_NT) hist[i] = 0u;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t v = s_w[lane];
+        v = __reduce_min_sync(0xffffffffu, v);
+        if (lane == 0) s_lo = v;
+    }
+    __syncthreads();
+    if (lane == 0) s_w[warp] = hi;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t v = s_w[lane];
+        v = __reduce_max_sync(0xffffffffu, v);
+        if (lane == 0) { s_hi = v; s_bad = 0; }
+    }
+    __syncthreads();
+    lo = s_lo; hi = s_hi;
+    const uint32_t range = hi - lo;
+    int shift = 0;
+    while (shift < 32 && (range >> shift) >= (uint32_t)SORT_BINS) ++shift;
+    // 2. bucket sizes (bucket 0 = the largest scores)
+    for (int i = threadIdx.x; i < n; i += SP_NT) {
+        const uint32_t k = (uint32_t)(src[i] >> 32);
+        atomicAdd(&hist[SORT_BINS - 1 - (int)((k - lo) >> shift)], 1u);
+    }
+    __syncthreads();
+    // 3. exclusive scan of the bucket sizes -> first place of every bucket; too full a bucket among the wanted ones?
+    {
+        constexpr int PERB = SORT_BINS / SP_NT;                       // 4
+        uint32_t loc[PERB];
+        int sum = 0;
+#pragma unroll
+        for (int i = 0; i < PERB; ++i) { loc[i] = hist[threadIdx.x * PERB + i]; sum += (int)loc[i]; }
+        int tot;
+        int run = kb::block_exclusive_scan(sum, s_scan, &tot);
+        bool bad = false;
+#pragma unroll
+        for (int i = 0; i < PERB; ++i) {
+            hist[threadIdx.x * PERB + i] = (uint32_t)run;
+            bad |= run < want && (int)loc[i] > SORT_BIN_MAX;
+            run += (int)loc[i];
+        }
+        if (threadIdx.x == SP_NT - 1) hist[SORT_BINS] = (uint32_t)run;
+        if (bad) s_bad = 1;
+    }
+    __syncthreads();
+    if (s_bad) return false;
+    // 4. scatter: hist[b] walks from the first place of bucket b to the first place of bucket b + 1
+    for (int i = threadIdx.x; i < n; i += SP_NT) {
+        const uint64_t key = src[i];
+        const int bin = SORT_BINS - 1 - (int)(((uint32_t)(key >> 32) - lo) >> shift);
+        dst[atomicAdd(&hist[bin], 1u)] = key;
+    }
+    __syncthreads();
+    // 5. order inside the buckets that matter (bucket b now ends at hist[b] and starts where bucket b-1 ends)
+    for (int bin = threadIdx.x; bin < SORT_BINS; bin += SP_NT) {
+        const int start = bin ? (int)hist[bin - 1] : 0, end = (int)hist[bin];
+        if (start >= want || end - start < 2) continue;
+        for (int i = start + 1; i < end; ++i) {                      // insertion sort, descending
+            const uint64_t key = dst[i];
+            int j = i - 1;
+            while (j >= start && dst[j] < key) { dst[j + 1] = dst[j]; --j; }
+            dst[j + 1] = key;
+        }
+    }
+    __syncthreads();
+    return true;
 }
 
 __device__ __forceinline__ int block_sum(int v, int* s_part) {
@@ -468,19 +567,24 @@ __device__ __forceinline__ int block_sum(int v, int* s_part) {
 
 constexpr uint8_t ST_DEAD = 0, ST_UNDEC = 1, ST_KEPT = 2;
 
+// phase timestamps of map 0's CTA (clock64), written when KB_KNOB_SPARSE_PROF is set: kb_debug_sparse_prof reads them
+__device__ long long g_sparse_prof[16];
+#define KB_SP_PROF(k) do { if (p.prof && b == 0 && threadIdx.x == 0) g_sparse_prof[k] = clock64(); } while (0)
+
 __global__ void __launch_bounds__(SP_NT, 1) sparse_kernel(SparseParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);                   // [SMEM_CAP]
     uint32_t* pos = reinterpret_cast<uint32_t*>(keys + SMEM_CAP);             // [SMEM_CAP] y << 16 | x
     uint32_t* cstart = pos + SMEM_CAP;                                        // [MAX_CELLS + 1]
-    uint16_t* items = reinterpret_cast<uint16_t*>(cstart + MAX_CELLS + 1);    // [SMEM_CAP] cell-sorted candidate ids
-    volatile uint8_t* state = reinterpret_cast<volatile uint8_t*>(items + SMEM_CAP);   // [SMEM_CAP]
+    volatile uint8_t* state = reinterpret_cast<volatile uint8_t*>(cstart + MAX_CELLS + 1);   // [SMEM_CAP]
     __shared__ int s_scan[33];
     __shared__ int s_part[SP_NT / 32];
     __shared__ int s_cut[3];
+    __shared__ int s_cnt;
 
     const int b = blockIdx.x;
     const int H = p.H, W = p.W, r = p.r;
+    KB_SP_PROF(0);
     auto fallback = [&]() {
         if (threadIdx.x == 0) { p.need_fallback[b] = 1; atomicExch(p.any_fallback, 1); }
     };
@@ -497,90 +601,73 @@ __global__ void __launch_bounds__(SP_NT, 1) sparse_kernel(SparseParams p) {
         long long ksel = attempt == 0 ? (long long)p.top_k + p.top_k / 4 + 32
                        : attempt == 1 ? 3LL * p.top_k + 64 : (long long)LIST_CAP + 1;
         // ---- cut: score key of the ksel-th largest round-1 maximum (0 = take everything) -------
+        // Radix select on the score key's bits 31..12 (any cut is exact, so the 12 low bits are not resolved): a
+        // 2048-bin histogram of bits 31..21, then a 512-bin histogram of bits 20..12 inside the bin that holds the
+        // ksel-th largest -- a dozen block-wide barriers where one counting vote per bit took 20 to 40.
         uint32_t tkey = 0u;
         if ((long long)nM > ksel) {
-            // (any cut is exact, so the 12 low bits of the score key are not resolved)
-            constexpr int PER = LIST_CAP / SP_NT;                 // 16
-            const int per = (nM + SP_NT - 1) / SP_NT;
-            if (per <= 2) {                                       // the usual case: at most 2048 maxima listed
-                const uint32_t ka = threadIdx.x < nM ? (uint32_t)(LM[threadIdx.x] >> 32) : 0u;
-                const uint32_t kb2 = SP_NT + threadIdx.x < nM ? (uint32_t)(LM[SP_NT + threadIdx.x] >> 32) : 0u;
-                for (int bit = 31; bit >= 12; --bit) {
-                    const uint32_t t = tkey | (1u << bit);
-                    int c = __syncthreads_count(ka >= t);
-                    if (per == 2) c += __syncthreads_count(kb2 >= t);
-                    if ((long long)c >= ksel) tkey = t;
-                }
-            } else {
-                uint32_t k32[PER];
-#pragma unroll
-                for (int i = 0; i < PER; ++i) {
-                    const int idx = i * SP_NT + threadIdx.x;
-                    k32[i] = (i < per && idx < nM) ? (uint32_t)(LM[idx] >> 32) : 0u;
-                }
-                // one block-wide barrier per bit instead of one per bit and key: every warp adds its count to a shared
-                // counter (three rotating counters: the one for bit+2 is cleared after the barrier of bit, a full
-                // barrier before it is used)
-                if (threadIdx.x < 3) s_cut[threadIdx.x] = 0;
-                __syncthreads();
-                int rot = 0;
-                for (int bit = 31; bit >= 12; --bit) {
-                    const uint32_t t = tkey | (1u << bit);
-                    int local = 0;
-#pragma unroll
-                    for (int i = 0; i < PER; ++i)
-                        if (i < per) local += k32[i] >= t ? 1 : 0;
-                    local = __reduce_add_sync(0xffffffffu, local);
-                    if ((threadIdx.x & 31) == 0 && local) atomicAdd(&s_cut[rot], local);
-                    __syncthreads();
-                    const int c = s_cut[rot];
-                    if (threadIdx.x == 0) s_cut[(rot + 2) % 3] = 0;
-                    rot = (rot + 1) % 3;
-                    if ((long long)c >= ksel) tkey = t;
-                }
+            uint32_t* hist = cstart;                               // scratch until the cell grid is built
+            for (int i = threadIdx.x; i < 2048 + 512; i += SP_NT) hist[i] = 0u;
+            if (threadIdx.x == 0) { s_cut[0] = -1; s_cut[1] = 0; s_cut[2] = -1; }
+            __syncthreads();
+            for (int i = threadIdx.x; i < nM; i += SP_NT) {
+                const uint64_t key = LM[i];
+                if (key != 0ull) atomicAdd(&hist[(uint32_t)(key >> 53)], 1u);       // bits 31..21 of the score key
             }
+            __syncthreads();
+            {   // thread t owns bins 2047-2t and 2046-2t: S(d) = number of keys with digit >= d
+                const int d0 = 2047 - 2 * (int)threadIdx.x, d1 = d0 - 1;
+                const int h0 = (int)hist[d0], h1 = (int)hist[d1];
+                int tot;
+                const int above = kb::block_exclusive_scan(h0 + h1, s_scan, &tot);
+                if ((long long)above < ksel && (long long)(above + h0) >= ksel) { s_cut[0] = d0; s_cut[1] = above; }
+                else if ((long long)(above + h0) < ksel && (long long)(above + h0 + h1) >= ksel) { s_cut[0] = d1; s_cut[1] = above + h0; }
+            }
+            __syncthreads();
+            const int dA = s_cut[0], aboveA = s_cut[1];
+            if (dA >= 0) {                                          // (fewer than ksel real keys: take everything)
+                uint32_t* hist2 = hist + 2048;
+                for (int i = threadIdx.x; i < nM; i += SP_NT) {
+                    const uint32_t k32 = (uint32_t)(LM[i] >> 32);
+                    if ((int)(k32 >> 21) == dA && LM[i] != 0ull) atomicAdd(&hist2[(k32 >> 12) & 0x1ffu], 1u);
+                }
+                __syncthreads();
+                {
+                    const int d = 511 - (int)threadIdx.x;
+                    const int h = d >= 0 ? (int)hist2[d] : 0;
+                    int tot;
+                    const int above = aboveA + kb::block_exclusive_scan(h, s_scan, &tot);
+                    if (d >= 0 && (long long)above < ksel && (long long)(above + h) >= ksel) s_cut[2] = d;
+                }
+                __syncthreads();
+                const int dB = s_cut[2] >= 0 ? s_cut[2] : 0;
+                tkey = ((uint32_t)dA << 21) | ((uint32_t)dB << 12);
+            }
+            __syncthreads();                                        // s_cut and the histograms are free again
         }
         const bool cut_complete = lists_complete && tkey == 0u;
-        // ---- load the candidates at or above the cut: maxima first, then the uncovered ones -----
-        int c = 0, cM = 0;
-        bool overflow = false;
-        for (int pass = 0; pass < 2; ++pass) {
-            const uint64_t* L = pass ? LO : LM;
-            const int n = pass ? nO : nM;
-            for (int base = 0; base < n; base += SP_NT) {
-                const int idx = base + threadIdx.x;
-                uint64_t key = 0ull;
-                bool take = false;
-                // (the streaming round-1 kernel pads the blocks a warp reserved with null keys)
-                if (idx < n) { key = L[idx]; take = key != 0ull && (uint32_t)(key >> 32) >= tkey; }
-                int tot;
-                const int off = c + kb::block_exclusive_scan(take ? 1 : 0, s_scan, &tot);
-                if (take && off < SMEM_CAP) {
-                    keys[off] = key;
-                    const uint32_t ras = kb::key_raster(key);
-                    const uint32_t y = ras / (uint32_t)W;
-                    pos[off] = (y << 16) | (ras - y * (uint32_t)W);
-                    state[off] = pass ? ST_UNDEC : ST_KEPT;
-                }
-                c += tot;
-                if (c > SMEM_CAP) { overflow = true; break; }
-            }
-            if (overflow) break;
-            if (pass == 0) cM = c;
-        }
-        __syncthreads();
-        if (overflow) { fallback(); return; }
-
-        // ---- coarse cell grid (counting sort of the candidates by cell) ---------------------------
+        KB_SP_PROF(1);
+        // ---- the candidates at or above the cut, stored in CELL ORDER -------------------------------
+        // A counting sort by coarse cell straight from the two lists (read twice: count, then place), so that the
+        // neighbourhood of a candidate is three contiguous runs of (position, key, state) entries -- no index
+        // indirection between a cell and its candidates.
         const int n_cells = p.gw * p.gh;
         for (int i = threadIdx.x; i <= n_cells; i += SP_NT) cstart[i] = 0u;
         __syncthreads();
-        for (int i = threadIdx.x; i < c; i += SP_NT) {
-            const uint32_t q = pos[i];
-            const int cell = (int)((q >> 16) >> p.cell_shift) * p.gw + (int)((q & 0xffffu) >> p.cell_shift);
-            atomicAdd(&cstart[cell + 1], 1u);
+        for (int pass = 0; pass < 2; ++pass) {
+            const uint64_t* L = pass ? LO : LM;
+            const int n = pass ? nO : nM;
+            for (int idx = threadIdx.x; idx < n; idx += SP_NT) {
+                const uint64_t key = L[idx];
+                // (the streaming round-1 kernel pads the blocks a warp reserved with null keys)
+                if (key == 0ull || (uint32_t)(key >> 32) < tkey) continue;
+                const uint32_t ras = kb::key_raster(key);
+                const uint32_t y = ras / (uint32_t)W, x = ras - y * (uint32_t)W;
+                atomicAdd(&cstart[(int)(y >> p.cell_shift) * p.gw + (int)(x >> p.cell_shift) + 1], 1u);
+            }
         }
         __syncthreads();
+        int c = 0;
         {   // inclusive scan over cstart[1..n_cells] -> cstart[k] = first slot of cell k
             constexpr int PERC = MAX_CELLS / SP_NT;               // 8
             uint32_t loc[PERC];
@@ -591,8 +678,7 @@ __global__ void __launch_bounds__(SP_NT, 1) sparse_kernel(SparseParams p) {
                 loc[i] = cell < n_cells ? cstart[cell + 1] : 0u;
                 sum += (int)loc[i];
             }
-            int tot;
-            int run = kb::block_exclusive_scan(sum, s_scan, &tot);
+            int run = kb::block_exclusive_scan(sum, s_scan, &c);
 #pragma unroll
             for (int i = 0; i < PERC; ++i) {
                 const int cell = threadIdx.x * PERC + i;
@@ -601,47 +687,69 @@ __global__ void __launch_bounds__(SP_NT, 1) sparse_kernel(SparseParams p) {
             }
         }
         __syncthreads();
-        // cstart[cell+1] holds the start of `cell`; bumping it while scattering leaves the start of cell+1
-        for (int i = threadIdx.x; i < c; i += SP_NT) {
-            const uint32_t q = pos[i];
-            const int cell = (int)((q >> 16) >> p.cell_shift) * p.gw + (int)((q & 0xffffu) >> p.cell_shift);
-            const uint32_t slot = atomicAdd(&cstart[cell + 1], 1u);
-            items[slot] = (uint16_t)i;
+        if (c > SMEM_CAP) { fallback(); return; }
+        KB_SP_PROF(2);
+        // cstart[cell+1] holds the start of `cell`; bumping it while placing leaves the start of cell+1
+        for (int pass = 0; pass < 2; ++pass) {
+            const uint64_t* L = pass ? LO : LM;
+            const int n = pass ? nO : nM;
+            for (int idx = threadIdx.x; idx < n; idx += SP_NT) {
+                const uint64_t key = L[idx];
+                if (key == 0ull || (uint32_t)(key >> 32) < tkey) continue;
+                const uint32_t ras = kb::key_raster(key);
+                const uint32_t y = ras / (uint32_t)W, x = ras - y * (uint32_t)W;
+                const uint32_t slot = atomicAdd(&cstart[(int)(y >> p.cell_shift) * p.gw + (int)(x >> p.cell_shift) + 1], 1u);
+                keys[slot] = key;
+                pos[slot] = (y << 16) | x;
+                state[slot] = pass ? ST_UNDEC : ST_KEPT;            // a round-1 maximum is kept for certain
+            }
         }
         __syncthreads();
-        // now cell k occupies items[cstart[k] .. cstart[k+1])  (cstart[0] == 0)
+        // now cell k occupies slots cstart[k] .. cstart[k+1]  (cstart[0] == 0)
+        KB_SP_PROF(3);
 
         // ---- keep / suppress decisions by priority -------------------------------------------------
-        while (true) {
-            int undecided = 0;
-            for (int i = cM + threadIdx.x; i < c; i += SP_NT) {
-                if (state[i] != ST_UNDEC) continue;
-                const uint32_t q = pos[i];
-                const int x = (int)(q & 0xffffu), y = (int)(q >> 16);
-                const uint64_t key = keys[i];
-                const int cx = x >> p.cell_shift, cy = y >> p.cell_shift;
-                const int cx0 = max(cx - 1, 0), cx1 = min(cx + 1, p.gw - 1);
-                bool blocked = false, wait = false;
-                for (int yy = max(cy - 1, 0); yy <= min(cy + 1, p.gh - 1) && !blocked; ++yy) {
-                    const uint32_t lo = cstart[yy * p.gw + cx0], hi = cstart[yy * p.gw + cx1 + 1];
-                    for (uint32_t t = lo; t < hi; ++t) {
-                        const int j = items[t];
-                        const uint32_t qj = pos[j];
-                        const int dx = (int)(qj & 0xffffu) - x, dy = (int)(qj >> 16) - y;
-                        if (dx > r || dx < -r || dy > r || dy < -r) continue;
-                        if (keys[j] <= key) continue;             // lower priority (or itself)
-                        const uint8_t sj = state[j];
-                        if (sj == ST_KEPT) { blocked = true; break; }
-                        wait |= (sj == ST_UNDEC);
+        // A candidate is dead once a kept neighbour of higher priority exists and kept once every such neighbour is
+        // dead; it waits while one is undecided.  No block-wide barrier per round: every thread re-examines ITS
+        // undecided candidates until none is left -- the states are volatile shared memory, a decision made by any warp
+        // is seen by the others on their next look, and the undecided candidate of highest priority can always be
+        // decided, so the loops terminate.  (The round count is capped all the same: a stuck CTA must not hang the GPU.)
+        bool stuck = false;
+        {
+            bool pending = true;
+            int rounds = 0;
+            while (pending) {
+                pending = false;
+                for (int i = threadIdx.x; i < c; i += SP_NT) {
+                    if (state[i] != ST_UNDEC) continue;
+                    const uint32_t q = pos[i];
+                    const int x = (int)(q & 0xffffu), y = (int)(q >> 16);
+                    const uint64_t key = keys[i];
+                    const int cx = x >> p.cell_shift, cy = y >> p.cell_shift;
+                    const int cx0 = max(cx - 1, 0), cx1 = min(cx + 1, p.gw - 1);
+                    bool blocked = false, wait = false;
+                    for (int yy = max(cy - 1, 0); yy <= min(cy + 1, p.gh - 1) && !blocked; ++yy) {
+                        const int lo = (int)cstart[yy * p.gw + cx0], hi = (int)cstart[yy * p.gw + cx1 + 1];
+                        for (int t = lo; t < hi; ++t) {
+                            const uint32_t qj = pos[t];
+                            const uint64_t kj = keys[t];
+                            const uint8_t sj = state[t];
+                            const int dx = (int)(qj & 0xffffu) - x, dy = (int)(qj >> 16) - y;
+                            if (dx > r || dx < -r || dy > r || dy < -r || kj <= key) continue;   // far, lower priority or itself
+                            if (sj == ST_KEPT) { blocked = true; break; }
+                            wait |= (sj == ST_UNDEC);
+                        }
                     }
+                    if (blocked) state[i] = ST_DEAD;
+                    else if (!wait) state[i] = ST_KEPT;
+                    else pending = true;
                 }
-                if (blocked) state[i] = ST_DEAD;
-                else if (!wait) state[i] = ST_KEPT;
-                else undecided = 1;
+                if (++rounds > 100000) { stuck = true; break; }
             }
-            if (!__syncthreads_or(undecided)) break;
         }
+        if (__syncthreads_or(stuck)) { fallback(); return; }
 
+        KB_SP_PROF(4);
         // ---- kept interior candidates, compacted to the front of keys[] ---------------------------
         int n_ki = 0;
         for (int base = 0; base < c; base += SP_NT) {
@@ -661,23 +769,34 @@ __global__ void __launch_bounds__(SP_NT, 1) sparse_kernel(SparseParams p) {
         }
         __syncthreads();
 
+        KB_SP_PROF(5);
         if (n_ki > p.top_k) {
             // K > top_k: rows sorted by score descending (extracter.py:217-218), canonical tie order
-            int n2 = 1;
-            while (n2 < n_ki) n2 <<= 1;
-            for (int i = n_ki + threadIdx.x; i < n2; i += SP_NT) keys[i] = 0ull;
-            __syncthreads();
-            __syncthreads();
-            sort_desc(keys, n2, SMEM_CAP);
+            // pos[] is dead now: 48 KB behind keys[] that take the bucket-sorted keys
+            uint64_t* sorted = reinterpret_cast<uint64_t*>(pos);
+            constexpr int SORTED_CAP = SMEM_CAP / 2;               // pos[] alone: 6144 keys (cstart, the scratch, follows it)
+            bool done = false;
+            if (n_ki <= SORTED_CAP) done = bucket_sort_desc(keys, sorted, n_ki, p.top_k, cstart, s_scan, s_part);
+            if (!done) {
+                int n2 = 1;
+                while (n2 < n_ki) n2 <<= 1;
+                for (int i = n_ki + threadIdx.x; i < n2; i += SP_NT) keys[i] = 0ull;
+                __syncthreads();
+                sort_desc(keys, n2, SMEM_CAP);
+                sorted = keys;
+            }
+            KB_SP_PROF(6);
             int cnt = 0;
             for (int i = threadIdx.x; i < p.top_k; i += SP_NT) {
-                const uint64_t key = keys[i];
+                const uint64_t key = sorted[i];
                 const float sc = kb::key_score(key);
                 // rows with score <= min_score form a suffix of the sorted list (extracter.py:219-220)
                 if (!(p.min_score > 0.0f) || sc > p.min_score) { emit(p, b, i, sc, kb::key_raster(key)); ++cnt; }
             }
             const int tot = block_sum(cnt, s_part);
             if (threadIdx.x == 0) { p.count[b] = tot; if (p.path) p.path[b] = 1; }
+            KB_SP_PROF(7);
+            if (p.prof && b == 0 && threadIdx.x == 0) { g_sparse_prof[8] = c; g_sparse_prof[9] = n_ki; g_sparse_prof[10] = nM; g_sparse_prof[11] = nO; g_sparse_prof[12] = attempt; }
             return;
         }
         if (cut_complete) {
@@ -731,7 +850,7 @@ static int launch_round1(const SparseParams& p, cudaStream_t st) {
 }
 
 constexpr size_t sparse_smem_bytes() {
-    return (size_t)SMEM_CAP * 8 + (size_t)SMEM_CAP * 4 + (size_t)(MAX_CELLS + 1) * 4 + (size_t)SMEM_CAP * 2 + SMEM_CAP + 64;
+    return (size_t)SMEM_CAP * 8 + (size_t)SMEM_CAP * 4 + (size_t)(MAX_CELLS + 1) * 4 + SMEM_CAP + 64;
 }
 
 }  // namespace kbsparse
@@ -795,6 +914,7 @@ int kb_sparse_detect(const float* score, int B, int H, int W, int nms_dist, int 
     p.B = B; p.H = H; p.W = W; p.r = nms_dist; p.border = border; p.top_k = top_k; p.c_pix = pl.c_pix;
     p.cell_shift = pl.cell_shift; p.gw = pl.gw; p.gh = pl.gh;
     p.threshold = threshold; p.min_score = min_score;
+    p.prof = kb_knobs[KB_KNOB_SPARSE_PROF];
     *need_fallback_out = p.need_fallback;
     *any_fallback_out = p.any_fallback;
     // `phases` (bit 0 tau, bit 1 round-1, bit 2 sparse resolve) lets the benchmark time one kernel alone on a
@@ -824,5 +944,11 @@ int kb_sparse_detect(const float* score, int B, int H, int W, int nms_dist, int 
     KB_CUDA_TRY(cudaFuncSetAttribute(sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     sparse_kernel<<<B, SP_NT, smem, st>>>(p);
     KB_LAUNCH_CHECK();
+    return KB_OK;
+}
+
+extern "C" int kb_debug_sparse_prof(long long* host_out) {
+    if (!host_out) return KB_ERR_BAD_ARG;
+    KB_CUDA_TRY(cudaMemcpyFromSymbol(host_out, kbsparse::g_sparse_prof, 16 * sizeof(long long)));
     return KB_OK;
 }
