@@ -10,7 +10,8 @@ import os
 from ctypes import c_double, c_float, c_int, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'csrc', 'libkb_b200.so')
+# KB_LIB selects another build of the same library (the debug build with bounds asserts: `make -C csrc debug`)
+LIB_PATH = os.path.abspath(os.environ['KB_LIB']) if os.environ.get('KB_LIB') else os.path.join(_HERE, 'csrc', 'libkb_b200.so')
 
 KB_OK = 0
 KB_ERR_BAD_ARG = -1

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 #include "../../include/kb_b200.h"
 
 #define KB_CUDA_TRY(expr)                         \
@@ -15,6 +16,15 @@
         cudaError_t _e = cudaGetLastError();      \
         if (_e != cudaSuccess) return (int)_e;    \
     } while (0)
+
+// Bounds checks of the debug build (`make debug` -> libkb_b200_dbg.so, -DKB_BOUNDS): compute-sanitizer is closed on the
+// GPU pool, so the kernels carry their own index asserts; a failed one traps (the launch then returns an error instead
+// of silently corrupting memory).  Compiled out of the release library.
+#ifdef KB_BOUNDS
+#define KB_ASSERT(cond) do { if (!(cond)) { printf("KB_ASSERT failed: %s  (%s:%d, block %d thread %d)\n", #cond, __FILE__, __LINE__, (int)blockIdx.x, (int)threadIdx.x); __trap(); } } while (0)
+#else
+#define KB_ASSERT(cond) do { } while (0)
+#endif
 
 // experiment knobs (kb_debug_knob, kb_api.cu); index = KB_KNOB_*
 extern int kb_knobs[8];

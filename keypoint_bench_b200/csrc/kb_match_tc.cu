@@ -231,7 +231,35 @@ __global__ void __launch_bounds__(256) prep_kernel(PrepPair pp) {
     const int n = p.cnt ? p.cnt[b] : p.n_max;
     const bool vec = (p.D & 3) == 0 && (reinterpret_cast<uintptr_t>(p.d) & 15u) == 0;
     for (int row0 = warp0 * PREP_ROWS; row0 < p.cs; row0 += n_warps * PREP_ROWS)
-    if (vec && row0 + PREP_ROWS <= n) {
+    if (vec && p.D == 256 && row0 + PREP_ROWS <= n) {
+        // D = 256: eight components per lane -- the whole row in one step, 16-byte stores of the hi and lo halves
+        const float* x = p.d + ((size_t)b * p.n_max + row0) * 256 + 8 * lane;
+        __nv_bfloat16* out = p.S + ((size_t)b * p.n_max + row0) * 512 + 8 * lane;
+        float4 v[PREP_ROWS][2];
+#pragma unroll
+        for (int r = 0; r < PREP_ROWS; ++r) {
+            v[r][0] = __ldg(reinterpret_cast<const float4*>(x + (size_t)r * 256));
+            v[r][1] = __ldg(reinterpret_cast<const float4*>(x + (size_t)r * 256) + 1);
+        }
+#pragma unroll
+        for (int r = 0; r < PREP_ROWS; ++r) {
+            const float f[8] = {v[r][0].x, v[r][0].y, v[r][0].z, v[r][0].w, v[r][1].x, v[r][1].y, v[r][1].z, v[r][1].w};
+            __align__(16) __nv_bfloat16 h[8], l[8];
+            // the summation order of the 4-component path (k = 4*lane, then k + 128): this lane holds components
+            // 8*lane .. 8*lane+7, i.e. the partial sums of two "4-component lanes" -- any order is a valid |row|^2, the
+            // error bound of the resolver covers the fp32 rounding of the sum
+            float ss = 0.0f;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                h[e] = __float2bfloat16_rn(f[e]);
+                l[e] = __float2bfloat16_rn(f[e] - __bfloat162float(h[e]));
+                ss = fmaf(f[e], f[e], ss);
+            }
+            *reinterpret_cast<uint4*>(out + (size_t)r * 512) = *reinterpret_cast<const uint4*>(h);
+            *reinterpret_cast<uint4*>(out + (size_t)r * 512 + 256) = *reinterpret_cast<const uint4*>(l);
+            wmax = fmaxf(wmax, prep_finish_row(p, b, row0 + r, ss, lane));
+        }
+    } else if (vec && row0 + PREP_ROWS <= n) {
         // fast path: four valid rows, 4 components per lane and step
         const float* x = p.d + ((size_t)b * p.n_max + row0) * p.D;
         __nv_bfloat16* out = p.S + ((size_t)b * p.n_max + row0) * (2 * p.Dp);
@@ -643,6 +671,7 @@ __global__ void __launch_bounds__(NT, 1) nn_top2_kernel(const __grid_constant__ 
                             const unsigned eq = __ballot_sync(0xffffffffu, top);
                             int m2 = __reduce_max_sync(0xffffffffu, top ? (int)0x80000000 : key);
                             if (eq & (eq - 1u)) m2 = m1;                          // the largest occurs twice
+                            KB_ASSERT(j0 + 4 * q + e < p.cs1 && (it.q_row0 >> 5) + quad < p.gm_groups);
                             if (lane == 0) gmrow[j0 + 4 * q + e] = make_float2(__int_as_float(m1), __int_as_float(m2));
                         }
                     }
@@ -702,6 +731,7 @@ __global__ void __launch_bounds__(NT, 1) nn_top2_kernel(const __grid_constant__ 
             }
             const int qi = it.q_row0 + row_in_tile;
             if (qi < it.n_q) {
+                KB_ASSERT(i1 >= 0 && i1 < it.n_db + BN && it.q_base + qi < (it.dir ? p.B * p.m_max : p.B * p.n_max));
                 Top2 o;
                 o.best = b1; o.second = b2; o.third = fminf(b3, b2);                    // b3 may hold the adopted bound
                 o.u1 = u1; o.idx = i1; o.idx2 = i2; o.u2 = u2; o.pad = 0;

@@ -118,6 +118,7 @@ __device__ __forceinline__ void append_bits(ListStream& s, uint64_t* list, int* 
             if (i >= done && i < done + take) {
                 const int slot = s.cur + s.fill + (i - done);
                 const int row = row0 + (bit >> 2), x = x4 + (bit & 3);
+                KB_ASSERT(slot >= 0 && row >= 0 && x < Wd);
                 if (slot < LIST_CAP)
                     list[slot] = kb::priority_key(raw[(row & (RING - 1)) * P + x], (uint32_t)(row * Wd + x));
             }
@@ -229,6 +230,7 @@ __global__ void __launch_bounds__(MAX_NT, 1) round1_stream_kernel(SparseParams p
                                     const int lo = max(x - R, 0), hi = min(x + R, P - 1);
                                     const int w0 = lo >> 5, w1 = hi >> 5;
                                     const uint32_t m0 = FULL << (lo & 31), m1 = FULL >> (31 - (hi & 31));
+                                    KB_ASSERT(w0 >= 0 && w1 < WW && x >= 0 && x < P);
                                     uint32_t* crow = Cr + ((row + lane - R) & (RING - 1)) * WW;
                                     if (w0 == w1) {
                                         atomicOr(&crow[w0], m0 & m1);

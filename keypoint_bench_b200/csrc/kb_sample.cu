@@ -183,6 +183,8 @@ __global__ void __launch_bounds__(PL_NT, 2) sample_planes_kernel(SampleParams p)
         const bool in_y0 = y0 >= 0 && y0 < p.h, in_y1 = y1 >= 0 && y1 < p.h;
         const bool t_nw = in_x0 && in_y0, t_ne = in_x1 && in_y0, t_sw = in_x0 && in_y1, t_se = in_x1 && in_y1;
         const int o_nw = y0 * p.w + x0, o_ne = o_nw + 1, o_sw = o_nw + p.w, o_se = o_sw + 1;
+        KB_ASSERT(!t_nw || (o_nw >= 0 && o_nw < hw));
+        KB_ASSERT(!t_se || (o_se >= 0 && o_se < hw));
         float val[PL_C];
 #pragma unroll
         for (int c = 0; c < PL_C; ++c) {

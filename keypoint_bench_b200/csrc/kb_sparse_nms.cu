@@ -349,6 +349,7 @@ __global__ void __launch_bounds__(DNT) round1_kernel(SparseParams p) {
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void emit(const SparseParams& p, int b, int slot, float score, uint32_t ras) {
     const int row = ras / p.W, col = ras - row * p.W;
+    KB_ASSERT(slot >= 0 && slot < p.top_k && ras < (uint32_t)(p.H * p.W));
     float* o = p.xyp + ((size_t)b * p.top_k + slot) * 3;
     o[0] = ((float)col + 0.5f) / (float)p.W;          // extracter.py:149,158
     o[1] = ((float)row + 0.5f) / (float)p.H;
@@ -536,7 +537,10 @@ __device__ bool bucket_sort_desc(const uint64_t* src, uint64_t* dst, int n, int 
     for (int i = threadIdx.x; i < n; i += SP_NT) {
         const uint64_t key = src[i];
         const int bin = SORT_BINS - 1 - (int)(((uint32_t)(key >> 32) - lo) >> shift);
-        dst[atomicAdd(&hist[bin], 1u)] = key;
+        KB_ASSERT(bin >= 0 && bin < SORT_BINS);
+        const uint32_t place = atomicAdd(&hist[bin], 1u);
+        KB_ASSERT(place < (uint32_t)n);
+        dst[place] = key;
     }
     __syncthreads();
     // 5. order inside the buckets that matter (bucket b now ends at hist[b] and starts where bucket b-1 ends)
@@ -580,7 +584,6 @@ __global__ void __launch_bounds__(SP_NT, 1) sparse_kernel(SparseParams p) {
     __shared__ int s_scan[33];
     __shared__ int s_part[SP_NT / 32];
     __shared__ int s_cut[3];
-    __shared__ int s_cnt;
 
     const int b = blockIdx.x;
     const int H = p.H, W = p.W, r = p.r;
@@ -612,6 +615,7 @@ __global__ void __launch_bounds__(SP_NT, 1) sparse_kernel(SparseParams p) {
             __syncthreads();
             for (int i = threadIdx.x; i < nM; i += SP_NT) {
                 const uint64_t key = LM[i];
+                KB_ASSERT((uint32_t)(key >> 53) < 2048u);
                 if (key != 0ull) atomicAdd(&hist[(uint32_t)(key >> 53)], 1u);       // bits 31..21 of the score key
             }
             __syncthreads();
@@ -698,7 +702,9 @@ __global__ void __launch_bounds__(SP_NT, 1) sparse_kernel(SparseParams p) {
                 if (key == 0ull || (uint32_t)(key >> 32) < tkey) continue;
                 const uint32_t ras = kb::key_raster(key);
                 const uint32_t y = ras / (uint32_t)W, x = ras - y * (uint32_t)W;
+                KB_ASSERT((int)(y >> p.cell_shift) * p.gw + (int)(x >> p.cell_shift) < n_cells && y < (uint32_t)H);
                 const uint32_t slot = atomicAdd(&cstart[(int)(y >> p.cell_shift) * p.gw + (int)(x >> p.cell_shift) + 1], 1u);
+                KB_ASSERT(slot < (uint32_t)c && c <= SMEM_CAP);
                 keys[slot] = key;
                 pos[slot] = (y << 16) | x;
                 state[slot] = pass ? ST_UNDEC : ST_KEPT;            // a round-1 maximum is kept for certain
@@ -730,6 +736,7 @@ __global__ void __launch_bounds__(SP_NT, 1) sparse_kernel(SparseParams p) {
                     bool blocked = false, wait = false;
                     for (int yy = max(cy - 1, 0); yy <= min(cy + 1, p.gh - 1) && !blocked; ++yy) {
                         const int lo = (int)cstart[yy * p.gw + cx0], hi = (int)cstart[yy * p.gw + cx1 + 1];
+                        KB_ASSERT(lo >= 0 && lo <= hi && hi <= c);
                         for (int t = lo; t < hi; ++t) {
                             const uint32_t qj = pos[t];
                             const uint64_t kj = keys[t];
