@@ -194,50 +194,53 @@ __global__ void __launch_bounds__(MAX_NT, 1) round1_stream_kernel(SparseParams p
             Cr[((S * (k + 2)) & (RING - 1)) * WW + t] = 0u;       // the 8 coverage rows of chunk k+2: NT words
             uint32_t hot = 0u, mx = 0u;
             if (active) {
+                // dense part, branch-free over the 8 rows: window maxima, `score > tau`, candidates (bit 4*o + j)
+                uint32_t cand = 0u;
 #pragma unroll
                 for (int o = 0; o < S; ++o) {
-                    const int row = S * k + o, slot = row & (RING - 1);
-                    const float* vmrow = VM + o * VP + 8;
-                    const float4 wm = window_max_cols<R>(vmrow, x4, out[o]);
+                    const int slot = (S * k + o) & (RING - 1);
+                    const float4 wm = window_max_cols<R>(VM + o * VP + 8, x4, out[o]);
                     const float4 v = *reinterpret_cast<const float4*>(raw + slot * P + x4);
                     negbits |= __float_as_uint(v.x) | __float_as_uint(v.y) | __float_as_uint(v.z) | __float_as_uint(v.w);
                     const uint32_t hn = (v.x > tau ? 1u : 0u) | (v.y > tau ? 2u : 0u) | (v.z > tau ? 4u : 0u) | (v.w > tau ? 8u : 0u);
                     const uint32_t cn = ((v.x == wm.x ? 1u : 0u) | (v.y == wm.y ? 2u : 0u) | (v.z == wm.z ? 4u : 0u) | (v.w == wm.w ? 8u : 0u)) & hn;
                     hot |= hn << (4 * o);
-                    unsigned pend = __ballot_sync(FULL, cn != 0u);
-                    while (pend) {                                // rare: ~1 pixel in (2R+1)^2; the whole warp takes one at a time
-                        const int src = __ffs(pend) - 1;
-                        pend &= pend - 1;
-                        unsigned cb = __shfl_sync(FULL, cn, src);
-                        while (cb) {
-                            const int jx = __ffs(cb) - 1;
-                            cb &= cb - 1;
-                            const float mine = jx == 0 ? v.x : jx == 1 ? v.y : jx == 2 ? v.z : v.w;
-                            const float vv = __shfl_sync(FULL, mine, src);
-                            const int x = 4 * ((t & ~31) + src) + jx;
-                            // lanes 0..2R: does column x-R+lane of the window hold vv (row buffer)?  lanes 2R+1..3R: does the
-                            // own column hold it 1..R rows above?
-                            bool e = false;
-                            if (lane <= 2 * R) e = vmrow[x + lane - R] == vv;
-                            else if (lane <= 3 * R) e = raw[((row - (lane - 2 * R)) & (RING - 1)) * P + x] == vv;
-                            const unsigned eq = __ballot_sync(FULL, e);
-                            bool earlier;
-                            if ((eq & ((2u << (2 * R)) - 1u)) == (1u << R)) earlier = (eq >> (2 * R + 1)) != 0u;
-                            else earlier = earlier_equal_warp<R>(raw, P, x, row, vv, lane);
-                            if (!earlier) {                       // a round-1 maximum: its bit, its coverage (one window row per lane)
-                                if (lane == src) mx |= 1u << (4 * o + jx);
-                                if (lane <= 2 * R) {
-                                    const int lo = max(x - R, 0), hi = min(x + R, P - 1);
-                                    const int w0 = lo >> 5, w1 = hi >> 5;
-                                    const uint32_t m0 = FULL << (lo & 31), m1 = FULL >> (31 - (hi & 31));
-                                    KB_ASSERT(w0 >= 0 && w1 < WW && x >= 0 && x < P);
-                                    uint32_t* crow = Cr + ((row + lane - R) & (RING - 1)) * WW;
-                                    if (w0 == w1) {
-                                        atomicOr(&crow[w0], m0 & m1);
-                                    } else {
-                                        atomicOr(&crow[w0], m0);
-                                        atomicOr(&crow[w1], m1);
-                                    }
+                    cand |= cn << (4 * o);
+                }
+                // candidates: rare (~1 pixel in (2R+1)^2); the whole warp takes one at a time
+                unsigned pend = __ballot_sync(FULL, cand != 0u);
+                while (pend) {
+                    const int src = __ffs(pend) - 1;
+                    pend &= pend - 1;
+                    unsigned cb = __shfl_sync(FULL, cand, src);
+                    const int xb = 4 * ((t & ~31) + src);
+                    while (cb) {
+                        const int bit = __ffs(cb) - 1;
+                        cb &= cb - 1;
+                        const int o = bit >> 2, x = xb + (bit & 3), row = S * k + o;
+                        const float vv = raw[(row & (RING - 1)) * P + x];                 // (one address for the warp)
+                        // lanes 0..2R: does column x-R+lane of the window hold vv (row buffer)?  lanes 2R+1..3R: does the
+                        // own column hold it 1..R rows above?
+                        bool e = false;
+                        if (lane <= 2 * R) e = VM[o * VP + 8 + x + lane - R] == vv;
+                        else if (lane <= 3 * R) e = raw[((row - (lane - 2 * R)) & (RING - 1)) * P + x] == vv;
+                        const unsigned eq = __ballot_sync(FULL, e);
+                        bool earlier;
+                        if ((eq & ((2u << (2 * R)) - 1u)) == (1u << R)) earlier = (eq >> (2 * R + 1)) != 0u;
+                        else earlier = earlier_equal_warp<R>(raw, P, x, row, vv, lane);
+                        if (!earlier) {                           // a round-1 maximum: its bit, its coverage (one window row per lane)
+                            if (lane == src) mx |= 1u << bit;
+                            if (lane <= 2 * R) {
+                                const int lo = max(x - R, 0), hi = min(x + R, P - 1);
+                                const int w0 = lo >> 5, w1 = hi >> 5;
+                                const uint32_t m0 = FULL << (lo & 31), m1 = FULL >> (31 - (hi & 31));
+                                KB_ASSERT(w0 >= 0 && w1 < WW && x >= 0 && x < P);
+                                uint32_t* crow = Cr + ((row + lane - R) & (RING - 1)) * WW;
+                                if (w0 == w1) {
+                                    atomicOr(&crow[w0], m0 & m1);
+                                } else {
+                                    atomicOr(&crow[w0], m0);
+                                    atomicOr(&crow[w1], m1);
                                 }
                             }
                         }
