@@ -273,14 +273,14 @@ def kernel_table(cfg, inputs, res, algo, tc, pk):
     if tc:
         mst = []
         ops.match_batched(*margs, algo=1, state=mst, want_dist=False)
-        passes = ops.match_issue_factor(bool(cfg.cross_check))
-        k['match.prep (hi/lo bf16 split + norms)'] = {
+        passes = ops.match_issue_factor(bool(cfg.cross_check), cfg.desc_dim)
+        k['match.prep (hi/lo 16-bit split + norms)'] = {
             'ms': time_ms(lambda: ops.match_batched(*margs, algo=1, phases=1, state=mst, want_dist=False)), 'bound': 'hbm',
             'algorithmic_bytes': 0.0}
         k['match.search (tcgen05 Gram + fused top-3 epilogue)'] = {
             'ms': time_ms(lambda: ops.match_batched(*margs, algo=1, phases=2, state=mst, want_dist=False)), 'bound': 'tensor',
             'algorithmic_flops': flops, 'issued_flops': flops * passes,
-            'issued_note': f'{passes}x the one-pass flops are issued to the tensor pipe (directions x split-bf16 passes)'}
+            'issued_note': f'{passes}x the one-pass flops are issued to the tensor pipe (directions x products of the split operands)'}
         k['match.tail (certify / rescan / gate / pairs)'] = {
             'ms': time_ms(lambda: ops.match_batched(*margs, algo=1, phases=4, state=mst, want_dist=False)), 'bound': 'latency',
             'algorithmic_bytes': 12.0 * float(res['n_matches'].float().sum().item())}
@@ -313,7 +313,8 @@ def run_config(args, name, rank, local_rank, world, device, full):
     algo = args.algo
     tc = cfg.desc_dim > 0 and (algo == 1 or (algo < 0 and cfg.desc_dim <= 256))
     if cfg.desc_dim:
-        config['matcher'] = 'tcgen05 split-bf16 Gram + float64 certify' if tc else 'float64 SIMT'
+        config['matcher'] = ('tcgen05 Gram of split 16-bit operands (fp16 x 2 products for D > 64, bf16 x 3 for D <= 64) + float64 certify'
+                             if tc else 'float64 SIMT')
     stream = cfg.task == 'stream'
     depth = 1 if args.no_graph else max(1, args.in_flight)
     total_frames = world * P + 1                                  # one sequence per step slot, sharded over the ranks

@@ -3,9 +3,14 @@
 // Reference semantics: utils/matcher.py:227-234 -> skimage match_descriptors over float64 cdist.
 //
 // For a query row x and database rows y_j:  argmin_j |x-y_j|^2  ==  argmax_j  t_j = x.y_j - |y_j|^2/2.
-//   prep_kernel     float32 descriptors -> split-bf16 operand rows [hi(D) | lo(D)] (x = hi + lo up to
-//                   2^-18 |x|), c_j = -|y_j|^2/2, row norms.  Three bf16 MMAs (hi.hi + hi.lo + lo.hi)
-//                   reproduce x.y to ~2^-16 relative: float32-grade, at bf16 tensor throughput.
+//   prep_kernel     float32 descriptors -> split operand rows [hi(D) | lo(D)] of 16-bit floats, c_j = -|y_j|^2/2, row
+//                   norms.  Default for D > 64: fp16 halves (x = hi + lo up to 2^-22 |x|) and TWO products per Gram,
+//                   (hi_x + lo_x).hi_y -- the database side is represented by its fp16 rounding alone, so x.y is
+//                   reproduced to 2^-12 |x||y| (a-priori bound, part of the certification), at two thirds of the MMA
+//                   work and half the database bytes of the alternative (the default for D <= 64, where the epilogue is
+//                   the bound; KB_KNOB_TC_BF16X3 = 1 / 2 forces either): bf16 halves and THREE
+//                   products hi.hi + lo.hi + hi.lo, ~2^-16 relative.  Either way the pairs are certified exactly; the
+//                   wider bound only sends ~3 % instead of ~1 % of the unmatched rows to the two-candidate float64 check.
 //   nn_top2_kernel  persistent, warp-specialised, 640 threads: warp 0 TMA producer, warp 1 MMA issuer (both run
 //                   their loops warp-uniformly and predicate only the issue on lane 0), warp 2 TMEM allocation,
 //                   16 epilogue warps (4 TMEM lane quadrants x 4 column slices).  tcgen05.mma kind::f16,
@@ -39,6 +44,7 @@
 //   pairs_kernel    ordered compaction (per pair).
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <math_constants.h>
 #include "kb_common.cuh"
 
@@ -188,17 +194,45 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
     return (uint64_t)((smem_addr & 0x3ffffu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)64 << 32) | ((uint64_t)1 << 46) |
            ((uint64_t)2 << 61);
 }
-// kind::f16: D=f32 (bit 4), A=B=bf16 (bits 7, 10), both K-major, N>>3 at bit 17, M>>4 at bit 24
+// kind::f16: D=f32 (bit 4), A=B=bf16 (bits 7, 10; cleared = fp16), both K-major, N>>3 at bit 17, M>>4 at bit 24
+constexpr uint32_t IDESC_BF16_BITS = (1u << 7) | (1u << 10);
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 constexpr uint32_t IDESC_PAIR = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
 
 // ------------------------------------------------------------------------------------------------
 // operand preparation
 // ------------------------------------------------------------------------------------------------
+// x -> (hi, lo) as raw 16-bit patterns: fp16 halves (two-product Gram) or bf16 halves (three-product Gram)
+__device__ __forceinline__ void split16(float f, int fp16, unsigned short& h, unsigned short& l) {
+    if (fp16) {
+        const __half hh = __float2half_rn(f);
+        h = __half_as_ushort(hh);
+        l = __half_as_ushort(__float2half_rn(f - __half2float(hh)));
+    } else {
+        const __nv_bfloat16 hh = __float2bfloat16_rn(f);
+        h = __bfloat16_as_ushort(hh);
+        l = __bfloat16_as_ushort(__float2bfloat16_rn(f - __bfloat162float(hh)));
+    }
+}
+
+// A-priori bound on |t_computed - t_exact| for a query of squared norm xq2 against a database whose largest squared
+// norm is ymax2 (t = x.y - |y|^2/2), Dp = padded descriptor length.
+//   bf16 x 3: dropped lo.lo / residual terms (3 * 2^-18 |x||y|), fp32 accumulation in the tensor core (K/16 roundings)
+//             and the fp32 -|y|^2/2 term, generous factor on top;
+//   fp16 x 2: the database enters by its fp16 rounding alone: |x.(y - hi_y)| <= 2^-12 |x||y| (2.44e-4), plus the same
+//             accumulation and -|y|^2/2 terms, plus the absolute rounding of fp16 subnormals (2^-25 per component).
+__device__ __forceinline__ float tc_err_bound(float xq2, float ymax2, int fp16, int Dp) {
+    const float xy = sqrtf(xq2) * sqrtf(ymax2);
+    if (!fp16) return 6.2e-5f * xy + 3.1e-5f * ymax2;
+    return 2.8e-4f * xy + 3.1e-5f * ymax2 + 3.0e-8f * sqrtf((float)Dp) * (sqrtf(xq2) + sqrtf(ymax2));
+}
+constexpr float FP16_NORM2_LIMIT = 4.0e9f;      // |row|^2 below this keeps every component inside fp16's range (65504^2 = 4.29e9)
+
 struct PrepParams {
     const float* d;          // [B,n_max,D]
     const int* cnt;          // [B] or null
-    __nv_bfloat16* S;        // [B*n_max, 2*Dp]
+    unsigned short* S;       // [B*n_max, 2*Dp] 16-bit float patterns
+    int fp16;                // 1: fp16 halves, 0: bf16 halves
     float* c;                // [B, cs]   -|y|^2/2, -inf beyond the count
     float* norm2;            // [B*n_max]
     unsigned int* maxn;      // [B] max |row|^2 (float bits)
@@ -234,7 +268,7 @@ __global__ void __launch_bounds__(256) prep_kernel(PrepPair pp) {
     if (vec && p.D == 256 && row0 + PREP_ROWS <= n) {
         // D = 256: eight components per lane -- the whole row in one step, 16-byte stores of the hi and lo halves
         const float* x = p.d + ((size_t)b * p.n_max + row0) * 256 + 8 * lane;
-        __nv_bfloat16* out = p.S + ((size_t)b * p.n_max + row0) * 512 + 8 * lane;
+        unsigned short* out = p.S + ((size_t)b * p.n_max + row0) * 512 + 8 * lane;
         float4 v[PREP_ROWS][2];
 #pragma unroll
         for (int r = 0; r < PREP_ROWS; ++r) {
@@ -244,15 +278,14 @@ __global__ void __launch_bounds__(256) prep_kernel(PrepPair pp) {
 #pragma unroll
         for (int r = 0; r < PREP_ROWS; ++r) {
             const float f[8] = {v[r][0].x, v[r][0].y, v[r][0].z, v[r][0].w, v[r][1].x, v[r][1].y, v[r][1].z, v[r][1].w};
-            __align__(16) __nv_bfloat16 h[8], l[8];
+            __align__(16) unsigned short h[8], l[8];
             // the summation order of the 4-component path (k = 4*lane, then k + 128): this lane holds components
             // 8*lane .. 8*lane+7, i.e. the partial sums of two "4-component lanes" -- any order is a valid |row|^2, the
             // error bound of the resolver covers the fp32 rounding of the sum
             float ss = 0.0f;
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-                h[e] = __float2bfloat16_rn(f[e]);
-                l[e] = __float2bfloat16_rn(f[e] - __bfloat162float(h[e]));
+                split16(f[e], p.fp16, h[e], l[e]);
                 ss = fmaf(f[e], f[e], ss);
             }
             *reinterpret_cast<uint4*>(out + (size_t)r * 512) = *reinterpret_cast<const uint4*>(h);
@@ -262,7 +295,7 @@ __global__ void __launch_bounds__(256) prep_kernel(PrepPair pp) {
     } else if (vec && row0 + PREP_ROWS <= n) {
         // fast path: four valid rows, 4 components per lane and step
         const float* x = p.d + ((size_t)b * p.n_max + row0) * p.D;
-        __nv_bfloat16* out = p.S + ((size_t)b * p.n_max + row0) * (2 * p.Dp);
+        unsigned short* out = p.S + ((size_t)b * p.n_max + row0) * (2 * p.Dp);
         float ss[PREP_ROWS] = {0.f, 0.f, 0.f, 0.f};
         for (int k = 4 * lane; k < p.Dp; k += 128) {
             float4 v[PREP_ROWS];
@@ -272,14 +305,13 @@ __global__ void __launch_bounds__(256) prep_kernel(PrepPair pp) {
 #pragma unroll
             for (int r = 0; r < PREP_ROWS; ++r) {
                 const float f[4] = {v[r].x, v[r].y, v[r].z, v[r].w};
-                __nv_bfloat16 h[4], l[4];
+                __align__(8) unsigned short h[4], l[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    h[e] = __float2bfloat16_rn(f[e]);
-                    l[e] = __float2bfloat16_rn(f[e] - __bfloat162float(h[e]));
+                    split16(f[e], p.fp16, h[e], l[e]);
                     ss[r] = fmaf(f[e], f[e], ss[r]);
                 }
-                __nv_bfloat16* o = out + (size_t)r * (2 * p.Dp);
+                unsigned short* o = out + (size_t)r * (2 * p.Dp);
                 *reinterpret_cast<uint2*>(o + k) = *reinterpret_cast<const uint2*>(h);
                 *reinterpret_cast<uint2*>(o + p.Dp + k) = *reinterpret_cast<const uint2*>(l);
             }
@@ -291,9 +323,9 @@ __global__ void __launch_bounds__(256) prep_kernel(PrepPair pp) {
             if (lane == 0) p.c[(size_t)b * p.cs + row] = -CUDART_INF_F;
             continue;
         }
-        __nv_bfloat16* out = p.S + ((size_t)b * p.n_max + row) * (2 * p.Dp);
+        unsigned short* out = p.S + ((size_t)b * p.n_max + row) * (2 * p.Dp);
         if (row >= n) {
-            for (int k = lane; k < 2 * p.Dp; k += 32) out[k] = __float2bfloat16(0.0f);
+            for (int k = lane; k < 2 * p.Dp; k += 32) out[k] = 0;
             if (lane == 0) { p.c[(size_t)b * p.cs + row] = -CUDART_INF_F; p.norm2[(size_t)b * p.n_max + row] = 0.0f; }
             continue;
         }
@@ -301,8 +333,8 @@ __global__ void __launch_bounds__(256) prep_kernel(PrepPair pp) {
         float ss = 0.0f;
         for (int k = lane; k < p.Dp; k += 32) {
             const float v = k < p.D ? x[k] : 0.0f;
-            const __nv_bfloat16 h = __float2bfloat16_rn(v);
-            const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+            unsigned short h, l;
+            split16(v, p.fp16, h, l);
             out[k] = h;
             out[p.Dp + k] = l;
             ss = fmaf(v, v, ss);
@@ -335,6 +367,7 @@ struct MainParams {
     const unsigned int* maxn0;   // [B] max |x|^2, max |y|^2 (float bits) from prep_kernel: the offset of the column-side scores
     const unsigned int* maxn1;
     int gm_groups;           // 4 * tiles0
+    int fp16;                // 1 = fp16 halves, two products (the database's lo half is never loaded); 0 = bf16, three
     int colside;             // 1 = one-pass cross-check (direction-0 items only, group maxima per column)
     long long* prof;         // timing experiments only (KB_KNOB_TC_DEBUG & 4): per CTA 8 cycle counters, see scripts/tc_pipeline_profile.py
     int dbg;                 // timing experiments only (KB_KNOB_TC_DEBUG): 1 = epilogue skips the fold, 2 = no MMAs issued
@@ -461,8 +494,7 @@ __global__ void __launch_bounds__(NT, 1) nn_top2_kernel(const __grid_constant__ 
             for (int ct = 0; ct < n_ct; ++ct) {
                 const int row = it.db_base + ct * BN;
                 for (int kb = 0; kb < KB; ++kb) {
-#pragma unroll
-                    for (int part = 0; part < 2; ++part) {          // hi block then lo block
+                    for (int part = 0; part < (p.fp16 ? 1 : 2); ++part) {          // hi block (then lo block: three-product Gram)
                         mbar_wait_prof(bar_b_empty + 8 * slot, b_phase ^ 1, prof, w_bempty);
                         if (issuer) {
                             if constexpr (CL == 2) {
@@ -491,8 +523,9 @@ __global__ void __launch_bounds__(NT, 1) nn_top2_kernel(const __grid_constant__ 
     } else if (warp == 1 && crank == 0) {
         // ================================ MMA issuer (the leader CTA of a pair issues for both) ==
         const bool issuer = lane == 0;
-        constexpr uint32_t ID = CL == 2 ? IDESC_PAIR : IDESC;
-        auto mma = [](uint32_t d, uint64_t a, uint64_t b, uint32_t acc) {
+        const bool two = p.fp16 != 0;                               // fp16 halves: (hi_x + lo_x).hi_y only
+        const uint32_t ID = (CL == 2 ? IDESC_PAIR : IDESC) & ~(two ? IDESC_BF16_BITS : 0u);
+        auto mma = [ID](uint32_t d, uint64_t a, uint64_t b, uint32_t acc) {
             if constexpr (CL == 2) tc_mma_pair(d, a, b, ID, acc); else tc_mma(d, a, b, ID, acc);
         };
         auto commit = [](uint32_t bar) {
@@ -532,25 +565,30 @@ __global__ void __launch_bounds__(NT, 1) nn_top2_kernel(const __grid_constant__ 
                         mma(d_tmem, a_lo + 4, bt + 4, 1u);
                         mma(d_tmem, a_lo + 6, bt + 6, 1u);
                     }
-                    if (issuer) commit(bar_b_empty + 8 * slot);
-                    __syncwarp();
-                    if (++slot == (uint32_t)NSLOT) { slot = 0; b_phase ^= 1; }
-                    // ---- database lo block: hi.lo
-                    mbar_wait_prof(bar_b_full + 8 * slot, b_phase, prof, w_bfull);
-                    tc_fence_after();
-                    bt = desc0 | (uint64_t)((b_slots + slot * SLOTB) >> 4);
-                    if (issuer && !(p.dbg & 2)) {
-                        mma(d_tmem, a_hi, bt, 1u);
-                        mma(d_tmem, a_hi + 2, bt + 2, 1u);
-                        mma(d_tmem, a_hi + 4, bt + 4, 1u);
-                        mma(d_tmem, a_hi + 6, bt + 6, 1u);
-                    }
                     if (issuer) {
                         commit(bar_b_empty + 8 * slot);
-                        if (ct == n_ct - 1) commit(bar_a_free + 8 * kb);         // query block kb may be overwritten
+                        if (two && ct == n_ct - 1) commit(bar_a_free + 8 * kb);  // query block kb may be overwritten
                     }
                     __syncwarp();
                     if (++slot == (uint32_t)NSLOT) { slot = 0; b_phase ^= 1; }
+                    if (!two) {
+                        // ---- database lo block: hi.lo (three-product Gram only)
+                        mbar_wait_prof(bar_b_full + 8 * slot, b_phase, prof, w_bfull);
+                        tc_fence_after();
+                        bt = desc0 | (uint64_t)((b_slots + slot * SLOTB) >> 4);
+                        if (issuer && !(p.dbg & 2)) {
+                            mma(d_tmem, a_hi, bt, 1u);
+                            mma(d_tmem, a_hi + 2, bt + 2, 1u);
+                            mma(d_tmem, a_hi + 4, bt + 4, 1u);
+                            mma(d_tmem, a_hi + 6, bt + 6, 1u);
+                        }
+                        if (issuer) {
+                            commit(bar_b_empty + 8 * slot);
+                            if (ct == n_ct - 1) commit(bar_a_free + 8 * kb);     // query block kb may be overwritten
+                        }
+                        __syncwarp();
+                        if (++slot == (uint32_t)NSLOT) { slot = 0; b_phase ^= 1; }
+                    }
                 }
                 if (issuer) commit(bar_t_full + 8 * acc_buf);       // accumulator ready for the epilogue
                 __syncwarp();
@@ -776,6 +814,7 @@ struct ResolveParams {
     const float2* gm;        // [B, gm_groups, cs1] group maxima of the column-side scores (search kernel)
     int4* colinfo;           // [B*m_max] per column: (largest u, largest of everything else, group of the largest, 0) as int bits
     int gm_groups, cs1, colside;
+    int fp16, Dp;            // operand split of the search (error bound), padded descriptor length
     int2* list;              // [list_cap] queued rows: (dir | b << 1, query row)
     int list_cap;
     struct RescanPart* parts;   // [list_cap, RESCAN_SPLIT] partial minima of the split rescan
@@ -859,22 +898,23 @@ __global__ void __launch_bounds__(256) resolve_kernel(ResolveParams p) {
         }
         const float nq2 = (dir ? p.norm2_1 : p.norm2_0)[(size_t)b * q_stride + q];
         const float dbmax2 = __uint_as_float((dir ? p.maxn0 : p.maxn1)[b]);
-        // bound on |t_computed - t_exact|: dropped lo.lo / residual terms (3*2^-18 |x||y|), fp32
-        // accumulation in the tensor core (K/16 roundings) and the fp32 -|y|^2/2 term; generous factor on top
-        const float e = 6.2e-5f * sqrtf(nq2) * sqrtf(dbmax2) + 3.1e-5f * dbmax2;
+        const float e = tc_err_bound(nq2, dbmax2, p.fp16, p.Dp);      // bound on |t_computed - t_exact|
         j1 = r.idx; j2 = r.idx2;
         tbest = r.best; tsecond = r.second;
         ubest = r.u1; usecond = r.u2;
         const bool ok1 = j1 >= 0 && j1 < ndb, ok2 = j2 >= 0 && j2 < ndb && j2 != j1;
-        if (ok1 && (r.best - r.second) > 2.0f * e) mode = 1;
-        else if (ok1 && ok2 && (r.best - r.third) > 2.0f * e) mode = 2;
+        // fp16 operands need every component inside fp16's range: guaranteed below a squared-norm limit, otherwise
+        // (absurdly large descriptors) every row of the pair is resolved by the exact rescan
+        const bool in_range = !p.fp16 || (__uint_as_float(p.maxn0[b]) < FP16_NORM2_LIMIT && __uint_as_float(p.maxn1[b]) < FP16_NORM2_LIMIT);
+        if (in_range && ok1 && (r.best - r.second) > 2.0f * e) mode = 1;
+        else if (in_range && ok1 && ok2 && (r.best - r.third) > 2.0f * e) mode = 2;
         else mode = 3;
     }
     int* nn = dir ? p.nn1 : p.nn0;
     if (mode == 1) nn[(size_t)b * q_stride + q] = j1;
     if (dir == 0 && mode != 0) {
         p.tsel[(size_t)b * q_stride + q] = mode == 1 ? tbest : CUDART_NAN_F;
-        p.usel[(size_t)b * q_stride + q] = mode == 1 ? ubest : CUDART_NAN_F;
+        if (p.colside) p.usel[(size_t)b * q_stride + q] = mode == 1 ? ubest : CUDART_NAN_F;
     }
     if (mode == 3) {
         const int slot = atomicAdd(p.n_exact, 1);
@@ -898,7 +938,7 @@ __global__ void __launch_bounds__(256) resolve_kernel(ResolveParams p) {
             nn[(size_t)b * q_stride + qq] = first ? a1 : a2;
             if (dir == 0) {
                 p.tsel[(size_t)b * q_stride + qq] = first ? t1 : t2;
-                p.usel[(size_t)b * q_stride + qq] = first ? w1 : w2;
+                if (p.colside) p.usel[(size_t)b * q_stride + qq] = first ? w1 : w2;
             }
             if (p.n_pair) atomicAdd(p.n_pair, 1);
         }
@@ -1037,7 +1077,7 @@ struct GateParams {
     int2* list2;             // columns queued for the exact rescan: (1 | b << 1, column)
     int* n_list2;
     int list2_cap;
-    int n_max, m_max, D, cross_check, want_dist, colside;
+    int n_max, m_max, D, cross_check, want_dist, colside, fp16, Dp;
     double max_distance;
 };
 
@@ -1052,28 +1092,36 @@ __global__ void __launch_bounds__(256) gate_kernel(GateParams p, int pass) {
     int jj[G];
     bool live[G];
     const float xmax2 = __uint_as_float(p.maxn0[b]), ymax2 = __uint_as_float(p.maxn1[b]);
+    // (the loads of the four rows are issued together: first every row's column, then what depends on it)
+    const bool use_nn1 = pass == 1 || (p.cross_check && !p.colside);
+    int back[G], kept[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) jj[g] = i0 + g < n ? p.nn0[(size_t)b * p.n_max + i0 + g] : 0;
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        back[g] = (use_nn1 && i0 + g < n) ? p.nn1[(size_t)b * p.m_max + jj[g]] : -1;
+        kept[g] = (pass == 1 && i0 + g < n) ? p.keep_j[(size_t)b * p.n_max + i0 + g] : 0;
+    }
 #pragma unroll
     for (int g = 0; g < G; ++g) {
         const int i = i0 + g;
         const size_t row = (size_t)b * p.n_max + i;
-        jj[g] = 0;
         live[g] = false;
         if (i >= n) continue;
-        jj[g] = p.nn0[row];
         int st;                             // 0 no match, 1 mutual, 2 too close to call, 3 leave the row alone
         if (pass == 1) {
-            st = p.keep_j[row] == -2 ? (p.nn1[(size_t)b * p.m_max + jj[g]] == i ? 1 : 0) : 3;
+            st = kept[g] == -2 ? (back[g] == i ? 1 : 0) : 3;
         } else if (!p.cross_check) {
             st = 1;
         } else if (!p.colside) {
-            st = p.nn1[(size_t)b * p.m_max + jj[g]] == i ? 1 : 0;
+            st = back[g] == i ? 1 : 0;
         } else {
             // Is row i the best row of column j?  u(i,j) against the group maxima of column j.  |u - exact| <= e for
             // every row, so a lead of more than 2 e settles it either way; anything closer is rescanned exactly.
             const float us = p.usel[row];
             const int4 ci = p.colinfo[(size_t)b * p.m_max + jj[g]];
             const float off = (0.5f * xmax2 + sqrtf(xmax2 * ymax2)) * 1.01f + 1e-6f;
-            const float e = 6.2e-5f * sqrtf(xmax2) * sqrtf(ymax2) + 3.1e-5f * xmax2 + 6.0e-7f * off;
+            const float e = tc_err_bound(ymax2, xmax2, p.fp16, p.Dp) + 6.0e-7f * off;   // (the rows are the "database" of a column)
             st = 2;
             if (us == us) {
                 const float v1 = __int_as_float(ci.x), rest = __int_as_float(ci.y);
@@ -1099,7 +1147,7 @@ __global__ void __launch_bounds__(256) gate_kernel(GateParams p, int pass) {
             if (!live[g]) continue;
             const size_t row = (size_t)b * p.n_max + i0 + g;
             const float t = p.tsel[row], x2 = p.norm2_0[row];
-            const float e = 6.2e-5f * sqrtf(x2) * sqrtf(ymax2) + 3.1e-5f * ymax2;
+            const float e = tc_err_bound(x2, ymax2, p.fp16, p.Dp);
             const double d2 = (double)x2 - 2.0 * (double)t, err = 2.0 * (double)e + 4e-6 * (double)x2;
             if (d2 + err < md2) {                       // certainly inside the gate
                 if (lane == 0) p.keep_j[row] = jj[g];
@@ -1216,14 +1264,14 @@ static PFN_encodeTiled get_encode() {
     return fn;
 }
 
-static int make_map(CUtensorMap* map, void* base, uint64_t rows, uint64_t ks) {
+static int make_map(CUtensorMap* map, void* base, uint64_t rows, uint64_t ks, int fp16) {
     PFN_encodeTiled enc = get_encode();
     if (!enc) return KB_ERR_UNSUPPORTED;
     cuuint64_t dims[2] = {ks, rows};
     cuuint64_t strides[1] = {ks * 2};
     cuuint32_t box[2] = {(cuuint32_t)kbtc::BK, (cuuint32_t)kbtc::BM};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr,
+    CUresult r = enc(map, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? KB_OK : KB_ERR_UNSUPPORTED;
@@ -1274,7 +1322,7 @@ static TcLayout tc_layout(int B, int n_max, int m_max, int D) {
 }
 
 struct TcBuffers {
-    __nv_bfloat16 *S0, *S1;
+    unsigned short *S0, *S1;
     float *c0, *c1, *norm2_0, *norm2_1;
     unsigned int *maxn0, *maxn1;
     kbtc::Top2 *res0, *res1;
@@ -1298,8 +1346,8 @@ struct TcBuffers {
 static TcBuffers tc_carve(void* ws, size_t ws_bytes, int B, int n_max, int m_max, const TcLayout& L) {
     KbArena arena(ws, ws_bytes);
     TcBuffers t;
-    t.S0 = arena.take<__nv_bfloat16>((size_t)B * n_max * 2 * L.Dp);
-    t.S1 = arena.take<__nv_bfloat16>((size_t)B * m_max * 2 * L.Dp);
+    t.S0 = arena.take<unsigned short>((size_t)B * n_max * 2 * L.Dp);
+    t.S1 = arena.take<unsigned short>((size_t)B * m_max * 2 * L.Dp);
     t.c0 = arena.take<float>((size_t)B * L.cs0);
     t.c1 = arena.take<float>((size_t)B * L.cs1);
     t.norm2_0 = arena.take<float>((size_t)B * n_max);
@@ -1355,7 +1403,11 @@ int kb_match_tc_run(const float* d0, const float* d1, const int* n0, const int* 
     if (L.KB > 4) return KB_ERR_UNSUPPORTED;                // query tile would not stay resident in shared memory
     TcBuffers tb = tc_carve(ws, ws_bytes, B, n_max, m_max, L);
     if (!tb.ok) return KB_ERR_WORKSPACE;
-    __nv_bfloat16 *S0 = tb.S0, *S1 = tb.S1;
+    unsigned short *S0 = tb.S0, *S1 = tb.S1;
+    // operand split: fp16 halves x 2 products where the search is MMA-bound (D > 64), bf16 halves x 3 where its
+    // epilogue is the bound anyway (D <= 64: the wider error bound would only add two-candidate checks and rescans);
+    // KB_KNOB_TC_BF16X3 = 1 / 2 forces bf16 x 3 / fp16 x 2
+    const int fp16 = kb_knobs[KB_KNOB_TC_BF16X3] == 1 ? 0 : (kb_knobs[KB_KNOB_TC_BF16X3] == 2 ? 1 : (L.Dp > 64 ? 1 : 0));
     float *c0 = tb.c0, *c1 = tb.c1, *norm2_0 = tb.norm2_0, *norm2_1 = tb.norm2_1;
     unsigned int *maxn0 = tb.maxn0, *maxn1 = tb.maxn1;
     Top2 *res0 = tb.res0, *res1 = tb.res1;
@@ -1380,7 +1432,7 @@ int kb_match_tc_run(const float* d0, const float* d1, const int* n0, const int* 
         PrepPair pp;
         PrepParams& q0 = pp.side[0];
         q0.d = d0; q0.cnt = n0; q0.S = S0; q0.c = c0; q0.norm2 = norm2_0; q0.maxn = maxn0;
-        q0.B = B; q0.n_max = n_max; q0.D = D; q0.Dp = L.Dp; q0.cs = L.cs0;
+        q0.B = B; q0.n_max = n_max; q0.D = D; q0.Dp = L.Dp; q0.cs = L.cs0; q0.fp16 = fp16;
         PrepParams& q1 = pp.side[1];
         q1 = q0;
         q1.d = d1; q1.cnt = n1; q1.S = S1; q1.c = c1; q1.norm2 = norm2_1; q1.maxn = maxn1;
@@ -1398,14 +1450,14 @@ int kb_match_tc_run(const float* d0, const float* d1, const int* n0, const int* 
     }
     // the two operand maps depend on (base, rows, row length) only: steady-state callers reuse their workspace, so the
     // driver call that encodes a map is made once per distinct operand array and thread
-    struct MapCache { void* base; uint64_t rows, ks; CUtensorMap map; };
+    struct MapCache { void* base; uint64_t rows, ks; int fp16; CUtensorMap map; };
     static thread_local MapCache cache[2] = {};
     auto cached_map = [&](int slot, void* base, uint64_t rows, uint64_t ks, CUtensorMap* out) -> int {
         MapCache& c = cache[slot];
-        if (c.base != base || c.rows != rows || c.ks != ks) {
-            const int r = make_map(&c.map, base, rows, ks);
+        if (c.base != base || c.rows != rows || c.ks != ks || c.fp16 != fp16) {
+            const int r = make_map(&c.map, base, rows, ks, fp16);
             if (r != KB_OK) { c.base = nullptr; return r; }
-            c.base = base; c.rows = rows; c.ks = ks;
+            c.base = base; c.rows = rows; c.ks = ks; c.fp16 = fp16;
         }
         *out = c.map;
         return KB_OK;
@@ -1422,6 +1474,7 @@ int kb_match_tc_run(const float* d0, const float* d1, const int* n0, const int* 
     // cross-check: the two-direction search (default), or one Gram pass + column-group maxima (KB_KNOB_TC_ONE_PASS)
     const int colside = (cross_check && kb_knobs[KB_KNOB_TC_ONE_PASS]) ? 1 : 0;
     mp.tiles0 = L.tiles0; mp.tiles1 = L.tiles1; mp.n_dirs = (cross_check && !colside) ? 2 : 1;
+    mp.fp16 = fp16;
     mp.gm = tb.gm; mp.maxn0 = maxn0; mp.maxn1 = maxn1; mp.gm_groups = 4 * L.tiles0; mp.colside = colside;
     // after the tiles: barriers (256 bytes), the 2 x 256-float c buffer and the 128-float shared bound; the tiles must start on a
     // 1024-byte boundary (128B swizzle) -- dynamic shared memory normally does, `slack` covers the rest
@@ -1484,7 +1537,7 @@ int kb_match_tc_run(const float* d0, const float* d1, const int* n0, const int* 
     rp.list = tb.list; rp.list_cap = B * (n_max + m_max);
     rp.parts = (RescanPart*)tb.parts; rp.tickets = tb.tickets; rp.tsel = tb.tsel; rp.usel = tb.usel;
     rp.gm = tb.gm; rp.colinfo = tb.colinfo; rp.gm_groups = mp.gm_groups; rp.cs1 = L.cs1; rp.colside = colside;
-    rp.B = B; rp.n_max = n_max; rp.m_max = m_max; rp.D = D; rp.n_dirs = mp.n_dirs;
+    rp.B = B; rp.n_max = n_max; rp.m_max = m_max; rp.D = D; rp.n_dirs = mp.n_dirs; rp.fp16 = fp16; rp.Dp = L.Dp;
     const int qmax = n_max > m_max ? n_max : m_max;
     // grid plane 1: the other direction's rows (two-pass) or the per-column summary of the group maxima (one-pass)
     resolve_kernel<<<dim3((qmax + 255) / 256, B, cross_check ? 2 : 1), 256, 0, st>>>(rp);
@@ -1498,7 +1551,7 @@ int kb_match_tc_run(const float* d0, const float* d1, const int* n0, const int* 
     gp.n_max = n_max; gp.m_max = m_max; gp.D = D; gp.cross_check = cross_check; gp.max_distance = max_distance;
     gp.tsel = tb.tsel; gp.usel = tb.usel; gp.colinfo = tb.colinfo; gp.norm2_0 = norm2_0; gp.maxn0 = maxn0; gp.maxn1 = maxn1;
     gp.list2 = tb.list2; gp.n_list2 = n_exact + 2; gp.list2_cap = B * n_max; gp.colside = colside;
-    gp.want_dist = dist != nullptr;
+    gp.want_dist = dist != nullptr; gp.fp16 = fp16; gp.Dp = L.Dp;
     const dim3 gate_grid(((n_max + 3) / 4 * 32 + 255) / 256, B);
     gate_kernel<<<gate_grid, 256, 0, st>>>(gp, 0);
     KB_LAUNCH_CHECK();

@@ -321,13 +321,20 @@ def match_batched(d0: torch.Tensor, d1: torch.Tensor, n0: torch.Tensor | None = 
     return pairs, dist, count
 
 
-def match_issue_factor(cross_check: bool) -> int:
+def _knob(k: int) -> int:
+    v = lib.kb_debug_knob(k, 0)
+    lib.kb_debug_knob(k, v)
+    return v
+
+
+def match_issue_factor(cross_check: bool, dim: int = 256) -> int:
     """How many times the one-pass 2*n*m*D flops of a pair the tensor-core search issues (bench.py reports it beside the
-    algorithmic figure): 3 split-bf16 products (hi*hi, hi*lo, lo*hi) per direction, one Gram per direction (one
-    direction only under the one-pass cross-check, KB_KNOB_TC_ONE_PASS)."""
-    one_pass = lib.kb_debug_knob(_lib.KB_KNOB_TC_ONE_PASS, 0)
-    lib.kb_debug_knob(_lib.KB_KNOB_TC_ONE_PASS, one_pass)
-    return 3 * (2 if (cross_check and not one_pass) else 1)
+    algorithmic figure): two fp16 products (hi + lo of the query against the fp16 rounding of the database; three bf16
+    products under KB_KNOB_TC_BF16X3) per direction, one Gram per direction (one direction only under the one-pass
+    cross-check, KB_KNOB_TC_ONE_PASS)."""
+    k = _knob(_lib.KB_KNOB_TC_BF16X3)
+    products = 3 if k == 1 else (2 if k == 2 else (2 if dim > 64 else 3))
+    return products * (2 if (cross_check and not _knob(_lib.KB_KNOB_TC_ONE_PASS)) else 1)
 
 
 def match_tc_debug(ws: torch.Tensor, b: int, n: int, m: int, dd: int) -> dict:

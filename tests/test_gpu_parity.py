@@ -302,8 +302,10 @@ def test_matcher_randomised_against_oracle(algo, seed):
     maxd = float(rng.choice([math.inf, 5.0 * typical, 0.6 * typical, 0.1 * typical]))
     cc = bool(rng.integers(0, 2))
     want_dist = bool(rng.integers(0, 2))
-    pairs, dist, count = ops().match_batched(a.to(DEV), d.to(DEV), n0.to(DEV), n1.to(DEV), maxd, cc, algo=algo,
-                                             want_dist=want_dist)
+    from keypoint_bench_b200 import _lib
+    with ops().debug_knob(_lib.KB_KNOB_TC_BF16X3, seed % 3):       # operand split: automatic / bf16 x 3 / fp16 x 2
+        pairs, dist, count = ops().match_batched(a.to(DEV), d.to(DEV), n0.to(DEV), n1.to(DEV), maxd, cc, algo=algo,
+                                                 want_dist=want_dist)
     for i in range(b):
         ai, di = a[i, :n0[i]].numpy(), d[i, :n1[i]].numpy()
         got = pairs[i, :int(count[i])].cpu().numpy().astype(np.int64)
@@ -374,11 +376,28 @@ def test_matcher_one_pass_cross_check_equals_two_pass(b, n, m, dim, dups):
             kk = int(out[0][1][i])
             assert torch.equal(out[0][0][i, :kk], out[1][0][i, :kk]), (maxd, i)
         assert out[1][2] == 0                                   # the two-pass path never queues a column
-        assert out[0][2] <= b * (2 * dups + 8), out[0][2]       # only the tied columns (and a rare near-tie) are rescanned
+        assert out[0][2] <= b * (2 * dups + 8) + int(n0.sum()) // 50, out[0][2]   # the tied columns and the rare near-ties (< 2 % of the rows) are rescanned
         if dups:
             assert out[0][2] >= dups
         _exact_pairs_or_near_tie(out[0][0][0, :int(out[0][1][0])].cpu().numpy().astype(np.int64), a[0, :n0[0]].numpy(),
                                  d[0, :n1[0]].numpy(), maxd, cc)
+
+
+@pytest.mark.parametrize('scale', [1e-6, 3e-4, 300.0, 5e4])
+def test_matcher_fp16_operands_at_extreme_magnitudes(scale):
+    """The default operand split for D > 64 is fp16: descriptors whose components underflow fp16's normal range (the
+    absolute rounding term of the bound) or overflow it (|row|^2 above the limit: every row of the pair goes to the
+    exact rescan) must still give the float64 oracle's pairs."""
+    gen = torch.Generator().manual_seed(int(scale * 7) % 1000 + 3)
+    n, m, dim = 260, 240, 128
+    a = torch.randn(2, n, dim, generator=gen) * scale
+    d = torch.randn(2, m, dim, generator=gen) * scale
+    d[:, :150] = a[:, :150] + 0.05 * scale * torch.randn(2, 150, dim, generator=gen)
+    typical = float(np.sqrt(2 * dim)) * scale
+    for maxd, cc in ((math.inf, True), (0.7 * typical, True), (math.inf, False)):
+        pairs, _, count = ops().match_batched(a.to(DEV), d.to(DEV), None, None, maxd, cc, algo=1, want_dist=False)
+        for i in range(2):
+            _exact_pairs_or_near_tie(pairs[i, :int(count[i])].cpu().numpy().astype(np.int64), a[i].numpy(), d[i].numpy(), maxd, cc)
 
 
 @pytest.mark.parametrize('algo', [0, 1])
@@ -578,17 +597,23 @@ def test_matcher_auto_falls_back_beyond_256_dims():
     assert np.array_equal(pairs[0, :int(count[0])].cpu().numpy().astype(np.int64), want)
 
 
+@pytest.mark.parametrize('bf16x3', [2, 1])
 @pytest.mark.parametrize('n,m,dim,normed', [(1000, 977, 256, True), (700, 900, 64, False), (300, 300, 128, True)])
-def test_tensor_core_scores_stay_inside_the_certification_bound(n, m, dim, normed):
-    """The split-bf16 Gram scores t = x.y - |y|^2/2 must lie within the a-priori bound the resolver
-    certifies with (kb_match_tc.cu), measured against float64."""
+def test_tensor_core_scores_stay_inside_the_certification_bound(n, m, dim, normed, bf16x3):
+    """The tensor-core Gram scores t = x.y - |y|^2/2 -- two fp16 products (default) or three bf16 products
+    (KB_KNOB_TC_BF16X3) -- must lie within the a-priori bound the resolver certifies with (tc_err_bound,
+    kb_match_tc.cu), measured against float64; both operand splits give the same pairs."""
+    from keypoint_bench_b200 import _lib
     gen = torch.Generator().manual_seed(n + dim)
     a = torch.randn(2, n, dim, generator=gen) * (1.0 if normed else 3.0)
     b = torch.randn(2, m, dim, generator=gen) * (1.0 if normed else 3.0)
     if normed:
         a, b = torch.nn.functional.normalize(a, dim=2), torch.nn.functional.normalize(b, dim=2)
     a, b = a.to(DEV), b.to(DEV)
-    pairs, dist, count, ws = ops().match_batched(a, b, None, None, math.inf, True, algo=1, return_ws=True)
+    with ops().debug_knob(_lib.KB_KNOB_TC_BF16X3, bf16x3):
+        pairs, dist, count, ws = ops().match_batched(a, b, None, None, math.inf, True, algo=1, return_ws=True)
+    p0, _, c0 = ops().match_batched(a, b, None, None, math.inf, True, algo=0)
+    assert torch.equal(count, c0) and all(torch.equal(pairs[i, :int(c0[i])], p0[i, :int(c0[i])]) for i in range(2))
     dbg = ops().match_tc_debug(ws, 2, n, m, dim)
     best, second, idx = dbg['res0']
     a64, b64 = a.double(), b.double()
@@ -598,8 +623,14 @@ def test_tensor_core_scores_stay_inside_the_certification_bound(n, m, dim, norme
     t_exact = (a64 * yb).sum(-1) - 0.5 * (yb * yb).sum(-1)
     err = (best.reshape(2, n).double() - t_exact).abs()
     nbmax = b64.norm(dim=2).max(dim=1).values[:, None]
-    bound = 6.2e-5 * a64.norm(dim=2) * nbmax + 3.1e-5 * nbmax * nbmax
-    assert float((err / bound).max()) < 0.5          # observed ~0.03: the bound keeps > 10x margin
+    if bf16x3 == 1:
+        bound = 6.2e-5 * a64.norm(dim=2) * nbmax + 3.1e-5 * nbmax * nbmax
+    else:
+        dp = (dim + 63) // 64 * 64
+        bound = 2.8e-4 * a64.norm(dim=2) * nbmax + 3.1e-5 * nbmax * nbmax + 3.0e-8 * dp ** 0.5 * (a64.norm(dim=2) + nbmax)
+    ratio = float((err / bound).max())
+    print(f'tensor-core score error / bound ({"bf16 x 3" if bf16x3 == 1 else "fp16 x 2"}, D={dim}): {ratio:.3f}')
+    assert ratio < 0.5                                # observed: bf16 x 3 ~0.03; the bound keeps a wide margin
     # and the reported best really is the maximum of the exact scores up to that bound
     t_all = a64 @ b64.transpose(1, 2) - 0.5 * (b64 * b64).sum(-1)[:, None, :]
     assert bool(((t_all.max(dim=2).values - t_exact) <= 2 * bound).all())
