@@ -1082,7 +1082,8 @@ struct GateParams {
 };
 
 // pass 0: every row.  pass 1 (after the rescan of the queued columns): the rows left at -2.
-__global__ void __launch_bounds__(256) gate_kernel(GateParams p, int pass) {
+// (3 CTAs per SM: the kernel is a chain of dependent loads, its time is the number of waves)
+__global__ void __launch_bounds__(256, 3) gate_kernel(GateParams p, int pass) {
     constexpr int G = 4;                  // rows per warp, their loads issued together
     const int i0 = ((blockIdx.x * 256 + threadIdx.x) >> 5) * G, lane = threadIdx.x & 31;
     const int b = blockIdx.y;

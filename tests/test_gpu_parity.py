@@ -217,6 +217,11 @@ def _exact_pairs_or_near_tie(got, d0, d1, maxd, cc):
 
 @pytest.mark.parametrize('algo', [0, 1])
 def test_matcher_matches_reference_fixtures(golden, algo):
+    """ref_match.npz was minted by the reference's own brute_force_matcher (utils/matcher.py:206-234) -- but the matching
+    inside it is skimage.feature.match_descriptors, a third-party function that is neither in the reference tree nor
+    installable here, so the fixture ran with the oracle's restatement of its published algorithm injected
+    (oracle/_refimport.py): for the matching half this fixture is UNPINNED UPSTREAM; the sampling half and
+    the row gather around it are the reference's."""
     g = golden('ref_match.npz')
     for tag in ('small32', 'sp256', 'nocross', 'tight'):
         maxd, cc = g[f'{tag}__maxd_cc']
