@@ -581,13 +581,17 @@ __global__ void __launch_bounds__(SP_NT, 1) sparse_kernel(SparseParams p) {
     uint32_t* pos = reinterpret_cast<uint32_t*>(keys + SMEM_CAP);             // [SMEM_CAP] y << 16 | x
     uint32_t* cstart = pos + SMEM_CAP;                                        // [MAX_CELLS + 1]
     volatile uint8_t* state = reinterpret_cast<volatile uint8_t*>(cstart + MAX_CELLS + 1);   // [SMEM_CAP]
+    uint16_t* und = reinterpret_cast<uint16_t*>(const_cast<uint8_t*>(state) + SMEM_CAP);      // [SMEM_CAP] undecided slots, by band
     __shared__ int s_scan[33];
     __shared__ int s_part[SP_NT / 32];
     __shared__ int s_cut[3];
+    __shared__ int s_und[3];
+    __shared__ int s_band[33], s_fill[32];
 
     const int b = blockIdx.x;
     const int H = p.H, W = p.W, r = p.r;
     KB_SP_PROF(0);
+    if (p.prof && b == 0 && threadIdx.x == 0) { g_sparse_prof[13] = 0; g_sparse_prof[15] = 0; }
     auto fallback = [&]() {
         if (threadIdx.x == 0) { p.need_fallback[b] = 1; atomicExch(p.any_fallback, 1); }
     };
@@ -694,20 +698,40 @@ __global__ void __launch_bounds__(SP_NT, 1) sparse_kernel(SparseParams p) {
         if (c > SMEM_CAP) { fallback(); return; }
         KB_SP_PROF(2);
         // cstart[cell+1] holds the start of `cell`; bumping it while placing leaves the start of cell+1
-        for (int pass = 0; pass < 2; ++pass) {
-            const uint64_t* L = pass ? LO : LM;
-            const int n = pass ? nO : nM;
-            for (int idx = threadIdx.x; idx < n; idx += SP_NT) {
-                const uint64_t key = L[idx];
-                if (key == 0ull || (uint32_t)(key >> 32) < tkey) continue;
-                const uint32_t ras = kb::key_raster(key);
-                const uint32_t y = ras / (uint32_t)W, x = ras - y * (uint32_t)W;
-                KB_ASSERT((int)(y >> p.cell_shift) * p.gw + (int)(x >> p.cell_shift) < n_cells && y < (uint32_t)H);
-                const uint32_t slot = atomicAdd(&cstart[(int)(y >> p.cell_shift) * p.gw + (int)(x >> p.cell_shift) + 1], 1u);
-                KB_ASSERT(slot < (uint32_t)c && c <= SMEM_CAP);
-                keys[slot] = key;
-                pos[slot] = (y << 16) | x;
-                state[slot] = pass ? ST_UNDEC : ST_KEPT;            // a round-1 maximum is kept for certain
+        if (threadIdx.x == 0) { s_und[0] = 0; s_und[1] = (int)0xffffffffu; s_und[2] = 0; }
+        __syncthreads();
+        {
+            int my_und = 0;
+            uint32_t my_lo = 0xffffffffu, my_hi = 0u;
+            for (int pass = 0; pass < 2; ++pass) {
+                const uint64_t* L = pass ? LO : LM;
+                const int n = pass ? nO : nM;
+                for (int idx = threadIdx.x; idx < n; idx += SP_NT) {
+                    const uint64_t key = L[idx];
+                    if (key == 0ull || (uint32_t)(key >> 32) < tkey) continue;
+                    const uint32_t ras = kb::key_raster(key);
+                    const uint32_t y = ras / (uint32_t)W, x = ras - y * (uint32_t)W;
+                    KB_ASSERT((int)(y >> p.cell_shift) * p.gw + (int)(x >> p.cell_shift) < n_cells && y < (uint32_t)H);
+                    const uint32_t slot = atomicAdd(&cstart[(int)(y >> p.cell_shift) * p.gw + (int)(x >> p.cell_shift) + 1], 1u);
+                    KB_ASSERT(slot < (uint32_t)c && c <= SMEM_CAP);
+                    keys[slot] = key;
+                    pos[slot] = (y << 16) | x;
+                    state[slot] = pass ? ST_UNDEC : ST_KEPT;            // a round-1 maximum is kept for certain
+                    if (pass) {
+                        ++my_und;
+                        my_lo = min(my_lo, (uint32_t)(key >> 32));
+                        my_hi = max(my_hi, (uint32_t)(key >> 32));
+                    }
+                }
+            }
+            // number of undecided candidates and the range of their score bits (for the priority bands below)
+            my_und = __reduce_add_sync(0xffffffffu, my_und);
+            my_lo = __reduce_min_sync(0xffffffffu, my_lo);
+            my_hi = __reduce_max_sync(0xffffffffu, my_hi);
+            if ((threadIdx.x & 31) == 0 && my_und) {
+                atomicAdd(&s_und[0], my_und);
+                atomicMin(reinterpret_cast<unsigned int*>(&s_und[1]), my_lo);
+                atomicMax(reinterpret_cast<unsigned int*>(&s_und[2]), my_hi);
             }
         }
         __syncthreads();
@@ -720,38 +744,86 @@ __global__ void __launch_bounds__(SP_NT, 1) sparse_kernel(SparseParams p) {
         // undecided candidates until none is left -- the states are volatile shared memory, a decision made by any warp
         // is seen by the others on their next look, and the undecided candidate of highest priority can always be
         // decided, so the loops terminate.  (The round count is capped all the same: a stuck CTA must not hang the GPU.)
+        // The undecided candidates are first gathered into a dense list (a warp that walks the slots pays a full look
+        // whenever ANY of its lanes holds an undecided one, so sparse work costs as much as dense work), grouped in BANDS
+        // of descending score (linear in the score bits) when there are many: a candidate only depends on higher
+        // priorities, i.e. on earlier bands -- decided, a block-wide barrier separates the bands -- and on its own band,
+        // so a round only touches candidates that can actually be decided (r = 4, top_k = 4096: ~4 000 undecided
+        // candidates with chains of dependent decisions; 224 k -> measured in profiles/r02_sparse_phases.txt).
         bool stuck = false;
         {
-            bool pending = true;
-            int rounds = 0;
-            while (pending) {
-                pending = false;
-                for (int i = threadIdx.x; i < c; i += SP_NT) {
-                    if (state[i] != ST_UNDEC) continue;
-                    const uint32_t q = pos[i];
-                    const int x = (int)(q & 0xffffu), y = (int)(q >> 16);
-                    const uint64_t key = keys[i];
-                    const int cx = x >> p.cell_shift, cy = y >> p.cell_shift;
-                    const int cx0 = max(cx - 1, 0), cx1 = min(cx + 1, p.gw - 1);
-                    bool blocked = false, wait = false;
-                    for (int yy = max(cy - 1, 0); yy <= min(cy + 1, p.gh - 1) && !blocked; ++yy) {
-                        const int lo = (int)cstart[yy * p.gw + cx0], hi = (int)cstart[yy * p.gw + cx1 + 1];
-                        KB_ASSERT(lo >= 0 && lo <= hi && hi <= c);
-                        for (int t = lo; t < hi; ++t) {
-                            const uint32_t qj = pos[t];
-                            const uint64_t kj = keys[t];
-                            const uint8_t sj = state[t];
-                            const int dx = (int)(qj & 0xffffu) - x, dy = (int)(qj >> 16) - y;
-                            if (dx > r || dx < -r || dy > r || dy < -r || kj <= key) continue;   // far, lower priority or itself
-                            if (sj == ST_KEPT) { blocked = true; break; }
-                            wait |= (sj == ST_UNDEC);
+            const int n_und = s_und[0];
+            const uint32_t k_lo = (uint32_t)s_und[1], k_hi = (uint32_t)s_und[2];
+            int n_bands = n_und / 512;
+            n_bands = n_bands < 1 ? 1 : (n_bands > 32 ? 32 : n_bands);
+            int bshift = 0;
+            while (n_bands > 1 && ((k_hi - k_lo) >> bshift) >= (uint32_t)n_bands) ++bshift;
+            auto band_of = [&](uint64_t key) { return n_bands > 1 ? (int)(((uint32_t)(key >> 32) - k_lo) >> bshift) : 0; };
+            if (threadIdx.x < 33) s_band[threadIdx.x] = 0;
+            __syncthreads();
+            for (int i = threadIdx.x; i < c; i += SP_NT)
+                if (state[i] == ST_UNDEC) atomicAdd(&s_band[band_of(keys[i]) + 1], 1);
+            __syncthreads();
+            if (threadIdx.x == 0) {                                   // s_band[k] = first list entry of band k (ascending bands)
+                for (int k = 1; k <= 32; ++k) s_band[k] += s_band[k - 1];
+                for (int k = 0; k < 32; ++k) s_fill[k] = s_band[k];
+            }
+            __syncthreads();
+            for (int i = threadIdx.x; i < c; i += SP_NT)
+                if (state[i] == ST_UNDEC) und[atomicAdd(&s_fill[band_of(keys[i])], 1)] = (uint16_t)i;
+            __syncthreads();
+            if (p.prof && b == 0 && threadIdx.x == 0) g_sparse_prof[13] = clock64() - g_sparse_prof[3];     // list building
+            // One look = the ~5-30 candidates of the 3x3 cells around a candidate, a chain of dependent shared-memory reads
+            // and compares per entry (~200 cycles each): EIGHT lanes share one candidate and split its neighbours, so a
+            // look takes two or three such steps instead of fifteen (ncu: the serial scan of the busiest warp was the
+            // whole decision phase at r = 4, top_k = 4096).
+            const int lane = threadIdx.x & 31, grp = lane >> 3, gl = lane & 7;
+            const int team = (threadIdx.x >> 5) * 4 + grp;            // 128 teams of eight lanes
+            for (int band = n_bands - 1; band >= 0; --band) {
+                const int e0 = s_band[band], e1 = s_band[band + 1];
+                bool pending = true;
+                int rounds = 0;
+                while (pending) {
+                    bool mine_waits = false;
+                    for (int base = e0; base < e1; base += 4 * (SP_NT / 32)) {      // uniform trip count over the CTA
+                        const int e = base + team;
+                        int i = -1;
+                        if (e < e1) { i = und[e]; if (state[i] != ST_UNDEC) i = -1; }
+                        bool blocked = false, wait = false;
+                        if (i >= 0) {
+                            const uint64_t key = keys[i];
+                            const uint32_t q = pos[i];
+                            const int x = (int)(q & 0xffffu), y = (int)(q >> 16);
+                            const int cx = x >> p.cell_shift, cy = y >> p.cell_shift;
+                            const int cx0 = max(cx - 1, 0), cx1 = min(cx + 1, p.gw - 1);
+                            for (int yy = max(cy - 1, 0); yy <= min(cy + 1, p.gh - 1); ++yy) {
+                                const int lo = (int)cstart[yy * p.gw + cx0], hi = (int)cstart[yy * p.gw + cx1 + 1];
+                                KB_ASSERT(lo >= 0 && lo <= hi && hi <= c);
+                                for (int t = lo + gl; t < hi; t += 8) {
+                                    const uint32_t qj = pos[t];
+                                    const uint64_t kj = keys[t];
+                                    const uint8_t sj = state[t];
+                                    const int dx = (int)(qj & 0xffffu) - x, dy = (int)(qj >> 16) - y;
+                                    if (dx > r || dx < -r || dy > r || dy < -r || kj <= key) continue;   // far, lower priority or itself
+                                    blocked |= (sj == ST_KEPT);
+                                    wait |= (sj == ST_UNDEC);
+                                }
+                            }
+                        }
+                        // the team's verdict (all 32 lanes are here: the ballots are warp-wide, the teams read their byte)
+                        const unsigned bb = (__ballot_sync(0xffffffffu, blocked) >> (8 * grp)) & 0xffu;
+                        const unsigned ww = (__ballot_sync(0xffffffffu, wait) >> (8 * grp)) & 0xffu;
+                        if (i >= 0) {
+                            if (bb) { if (gl == 0) state[i] = ST_DEAD; }
+                            else if (!ww) { if (gl == 0) state[i] = ST_KEPT; }
+                            else mine_waits = true;
                         }
                     }
-                    if (blocked) state[i] = ST_DEAD;
-                    else if (!wait) state[i] = ST_KEPT;
-                    else pending = true;
+                    pending = __any_sync(0xffffffffu, mine_waits);
+                    if (++rounds > 100000) { stuck = true; break; }
                 }
-                if (++rounds > 100000) { stuck = true; break; }
+                if (p.prof && b == 0) { int mr = __reduce_max_sync(0xffffffffu, rounds); if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned long long*>(&g_sparse_prof[15]), (unsigned long long)mr); if (threadIdx.x == 0 && band == n_bands - 1) g_sparse_prof[14] = n_bands; }
+                if (n_bands > 1) __syncthreads();                   // the band is decided before the next one starts
             }
         }
         if (__syncthreads_or(stuck)) { fallback(); return; }
@@ -857,7 +929,7 @@ static int launch_round1(const SparseParams& p, cudaStream_t st) {
 }
 
 constexpr size_t sparse_smem_bytes() {
-    return (size_t)SMEM_CAP * 8 + (size_t)SMEM_CAP * 4 + (size_t)(MAX_CELLS + 1) * 4 + SMEM_CAP + 64;
+    return (size_t)SMEM_CAP * 8 + (size_t)SMEM_CAP * 4 + (size_t)(MAX_CELLS + 1) * 4 + SMEM_CAP + (size_t)SMEM_CAP * 2 + 64;
 }
 
 }  // namespace kbsparse

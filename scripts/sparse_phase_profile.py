@@ -24,4 +24,4 @@ for name in (sys.argv[1:] or ['cfg2', 'cfg3', 'cfg4', 'cfg5']):
     t = list(out)
     d = {nm: t[i + 1] - t[i] for i, nm in enumerate(names)}
     print(json.dumps({'config': name, 'maps': n, 'cycles': d, 'total': t[7] - t[0], 'candidates': t[8], 'kept_interior': t[9],
-                      'listM': t[10], 'listO': t[11], 'attempt': t[12]}))
+                      'listM': t[10], 'listO': t[11], 'attempt': t[12], 'decide_list_build_cycles': t[13], 'bands': t[14], 'max_rounds_any_warp_in_a_band': t[15]}))
