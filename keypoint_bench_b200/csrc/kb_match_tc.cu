@@ -1544,7 +1544,10 @@ int kb_match_tc_run(const float* d0, const float* d1, const int* n0, const int* 
     resolve_kernel<<<dim3((qmax + 255) / 256, B, cross_check ? 2 : 1), 256, 0, st>>>(rp);
     KB_LAUNCH_CHECK();
     if ((size_t)D * 4 > 48 * 1024) return KB_ERR_UNSUPPORTED;
-    rescan_kernel<<<dim3(RESCAN_SPLIT, sms), RESCAN_WARPS * 32, (size_t)D * 4, st>>>(rp);
+    // (queued rows are rare: a quarter of the SMs' worth of row slots keeps the usual, empty launch short; the kernel
+    // loops over the queue, so any number of rows is handled)
+    const int rescan_rows = sms / 4 > 1 ? sms / 4 : 1;
+    rescan_kernel<<<dim3(RESCAN_SPLIT, rescan_rows), RESCAN_WARPS * 32, (size_t)D * 4, st>>>(rp);
     KB_LAUNCH_CHECK();
 
     GateParams gp;
@@ -1560,7 +1563,7 @@ int kb_match_tc_run(const float* d0, const float* d1, const int* n0, const int* 
         // the columns that were too close to call: exact float64 rescan, then the gate for the rows waiting on them
         ResolveParams rp2 = rp;
         rp2.list = tb.list2; rp2.n_exact = n_exact + 2; rp2.n_pair = nullptr; rp2.list_cap = B * n_max;
-        rescan_kernel<<<dim3(RESCAN_SPLIT, sms), RESCAN_WARPS * 32, (size_t)D * 4, st>>>(rp2);
+        rescan_kernel<<<dim3(RESCAN_SPLIT, rescan_rows), RESCAN_WARPS * 32, (size_t)D * 4, st>>>(rp2);
         KB_LAUNCH_CHECK();
         gate_kernel<<<gate_grid, 256, 0, st>>>(gp, 1);
         KB_LAUNCH_CHECK();
