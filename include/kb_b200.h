@@ -114,9 +114,10 @@ KB_API int kb_detect(const float* score, int B, int H, int W, int nms_dist, int 
               size_t ws_bytes, kb_stream_t stream);
 /* Measurement hook: kb_detect restricted to the kernels selected by `phases` (bit 0 threshold estimate,
  * bit 1 streaming round-1 kernel, bit 2 per-map resolve + fallback) on a workspace that a full call
- * (phases = 7) has filled before.  kb_detect == phases 7.  Round 1 has two kernels with identical output (the tiled
- * kernel, which is the default, and a full-width streaming kernel): bit 3 forces the tiled one, bit 4 the streaming
- * one (tests and A/B measurements; not both). */
+ * (phases = 7) has filled before.  kb_detect == phases 7.  Round 1 has three kernels with identical output: the packed
+ * streaming kernel (pairs of maps as half2; the automatic choice for batches large enough to fill the GPU with long
+ * bands), the tiled kernel (everything else) and a full-width fp32 streaming kernel: bit 3 forces the tiled one, bit 4
+ * the fp32 streaming one, bit 5 the packed one (tests and A/B measurements; at most one of the three). */
 KB_API int kb_detect_phases(const float* score, int B, int H, int W, int nms_dist, int border_dist, float threshold,
                      float min_score, int top_k, float* xyp, int* raster, int* count, int* path, void* ws,
                      size_t ws_bytes, int phases, kb_stream_t stream);

@@ -275,7 +275,7 @@ extern "C" int kb_detect_phases(const float* score, int B, int H, int W, int nms
                          size_t ws_bytes, int phases, kb_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (!score || !xyp || !raster || !count || B <= 0 || H <= 0 || W <= 0 || nms_dist < 0 || border_dist < 0 ||
-        top_k <= 0 || phases <= 0 || phases > 31 || (phases & 24) == 24)
+        top_k <= 0 || phases <= 0 || phases > 63 || ((phases >> 3) & ((phases >> 3) - 1)) != 0)
         return KB_ERR_BAD_ARG;
     if (top_k > SORT_CAP) return KB_ERR_UNSUPPORTED;
     if (B > 2048) return KB_ERR_UNSUPPORTED;         // callers split larger batches

@@ -42,36 +42,42 @@ __device__ __forceinline__ float4 max4(float4 a, float4 b) {
 
 // out[o] = max over input rows o .. o+2R of a thread's 4 columns, o = 0..NS-1; ld(i) returns input row i (0..NS+2R-1).
 // All windows share rows NS-1 .. 2R (when there are any); the rest are suffixes of rows 0 .. NS-2 and prefixes of
-// rows 2R+1 .. : ~4 FMNMX per pixel at NS = 8, R = 6.
-template <int R, int NS, typename Load>
-__device__ __forceinline__ void window_max_rows(Load ld, float4 (&out)[NS]) {
+// rows 2R+1 .. : ~4 maximum operations per element at NS = 8, R = 6.  V / mx: the vector type and its maximum (float4 +
+// max4 for the fp32 kernels, four packed half2 pairs for the packed kernel).
+template <int R, int NS, typename V, typename Max, typename Load>
+__device__ __forceinline__ void window_max_rows_t(Load ld, Max mx, V (&out)[NS]) {
     if constexpr (2 * R >= NS - 1 && NS >= 2) {
-        float4 run = ld(NS - 2);
+        V run = ld(NS - 2);
         out[NS - 2] = run;
 #pragma unroll
-        for (int j = NS - 3; j >= 0; --j) { run = max4(run, ld(j)); out[j] = run; }
-        float4 core = ld(NS - 1);
+        for (int j = NS - 3; j >= 0; --j) { run = mx(run, ld(j)); out[j] = run; }
+        V core = ld(NS - 1);
 #pragma unroll
-        for (int i = NS; i <= 2 * R; ++i) core = max4(core, ld(i));
+        for (int i = NS; i <= 2 * R; ++i) core = mx(core, ld(i));
 #pragma unroll
-        for (int o = 0; o < NS - 1; ++o) out[o] = max4(out[o], core);
+        for (int o = 0; o < NS - 1; ++o) out[o] = mx(out[o], core);
         out[NS - 1] = core;
         run = ld(2 * R + 1);
-        out[1] = max4(out[1], run);
+        out[1] = mx(out[1], run);
 #pragma unroll
-        for (int o = 2; o < NS; ++o) { run = max4(run, ld(2 * R + o)); out[o] = max4(out[o], run); }
+        for (int o = 2; o < NS; ++o) { run = mx(run, ld(2 * R + o)); out[o] = mx(out[o], run); }
     } else {
-        float4 in[NS + 2 * R];
+        V in[NS + 2 * R];
 #pragma unroll
         for (int i = 0; i < NS + 2 * R; ++i) in[i] = ld(i);
 #pragma unroll
         for (int o = 0; o < NS; ++o) {
-            float4 m = in[o];
+            V m = in[o];
 #pragma unroll
-            for (int d = 1; d <= 2 * R; ++d) m = max4(m, in[o + d]);
+            for (int d = 1; d <= 2 * R; ++d) m = mx(m, in[o + d]);
             out[o] = m;
         }
     }
+}
+
+template <int R, int NS, typename Load>
+__device__ __forceinline__ void window_max_rows(Load ld, float4 (&out)[NS]) {
+    window_max_rows_t<R, NS, float4>(ld, [](float4 a, float4 b) { return max4(a, b); }, out);
 }
 
 // (2R+1)-window maximum along the row for a thread's 4 columns x4..x4+3; vmrow points at column 0 of a row that is
@@ -110,5 +116,10 @@ __device__ __forceinline__ float4 window_max_cols(const float* vmrow, int x4, fl
 // with identical lists.  Returns KB_ERR_UNSUPPORTED when the map is too wide for it or (without `force`) the batch
 // too small to give every CTA a long band.
 int launch_round1_stream(const SparseParams& p, bool force, cudaStream_t st);
+
+// kb_round1_packed.cu: streaming round 1 over PAIRS of maps held as packed half2 (a 16-bit monotone image of the scores
+// decides almost everything; fp32 only for the `score > tau` test and for ties at 16 bits), identical lists.  Returns
+// KB_ERR_UNSUPPORTED when the map is too wide or (without `force`) the batch too small.
+int launch_round1_packed(const SparseParams& p, bool force, cudaStream_t st);
 
 }  // namespace kbsparse

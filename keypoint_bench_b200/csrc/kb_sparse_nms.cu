@@ -1002,10 +1002,13 @@ int kb_sparse_detect(const float* score, int B, int H, int W, int nms_dist, int 
         tau_kernel<<<B, TAU_NT, 0, st>>>(p);
         KB_LAUNCH_CHECK();
     }
-    // Round 1 has two kernels with identical lists: the tiled round1_kernel (default) and the full-width streaming
-    // kernel of kb_round1_stream.cu (phases bit 4; measured equal at 480x640 r = 6, slower elsewhere -- DESIGN.md).
+    // Round 1 has three kernels with identical lists: the packed streaming kernel of kb_round1_packed.cu (pairs of maps
+    // as half2; the default whenever the batch is large enough to give every CTA a long band; phases bit 5 forces it),
+    // the tiled round1_kernel (small batches, very wide maps; bit 3) and the fp32 streaming kernel of
+    // kb_round1_stream.cu (bit 4; measured equal to the tiled one at 480x640 r = 6, slower elsewhere -- DESIGN.md).
     int rc = (phases & 2) ? KB_ERR_UNSUPPORTED : KB_OK;
     if ((phases & 2) && (phases & 16)) rc = launch_round1_stream(p, true, st);
+    else if ((phases & 2) && !(phases & 8)) rc = launch_round1_packed(p, (phases & 32) != 0, st);
     if ((phases & 2) && rc == KB_ERR_UNSUPPORTED) switch (nms_dist) {
         case 1: rc = launch_round1<1>(p, st); break;
         case 2: rc = launch_round1<2>(p, st); break;

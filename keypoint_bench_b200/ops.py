@@ -176,7 +176,8 @@ def detect_batched(score: torch.Tensor, params: dict | None = None, phases: int 
     -> xyp[B,top_k,3] (x,y,p), count[B], raster[B,top_k], path[B].
     ``phases`` / ``state`` are a measurement hook (bench.py): ``state=[]`` receives the buffers of a full call,
     a later call with the same ``state`` and ``phases`` in {1,2,4} re-runs just that kernel on them; ``phases | 8`` /
-    ``phases | 16`` force the tiled / the streaming round-1 kernel (identical output, include/kb_b200.h).
+    ``phases | 16`` / ``phases | 32`` force the tiled / the fp32 streaming / the packed streaming round-1 kernel
+    (identical output, include/kb_b200.h).
 
     Like the reference, any ``top_k`` is accepted: 0 gives no rows, and a ``top_k`` the NMS can never exceed (at least
     ``nms_keep_bound``) means raster order for every map (extracter.py:217).  Only SORT_CAP < top_k < keep bound -- a

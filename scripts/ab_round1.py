@@ -1,4 +1,4 @@
-"""A/B timing of the two round-1 kernels of the sparse detection path (tiled vs streaming) and of the whole
+"""A/B timing of the round-1 kernels of the sparse detection path (tiled / fp32 streaming / packed streaming) and of the whole
 detect stage, CUDA events on the launch stream.  python scripts/ab_round1.py [cfg2|cfg3|cfg4|cfg5] [maps]"""
 import json
 import os
@@ -30,10 +30,14 @@ def main():
     s = torch.rand(n, 1, cfg.height, cfg.width, generator=g, device='cuda')
     out = {'config': name, 'maps': n, 'bytes': s.numel() * 4}
     with ops.no_zero_fill():
-        for tag, bit in (('tiled', 8), ('stream', 16)):
+        for tag, bit in (('tiled', 8), ('stream', 16), ('packed', 32)):
             st = []
             ops.detect_batched(s, cfg.extractor_params, phases=7 | bit, state=st)
             out[f'round1_{tag}_ms'] = time_ms(lambda: ops.detect_batched(s, cfg.extractor_params, phases=2 | bit, state=st))
+            # (repeated round-1 launches alone keep growing the list counters, so later repeats skip their stores:
+            # threshold estimate + round 1 together, minus the estimate, is the unbiased figure)
+            out[f'tau_round1_{tag}_ms'] = time_ms(lambda: ops.detect_batched(s, cfg.extractor_params, phases=3 | bit, state=st))
+            ops.detect_batched(s, cfg.extractor_params, phases=7 | bit, state=st)
             out[f'resolve_after_{tag}_ms'] = time_ms(lambda: ops.detect_batched(s, cfg.extractor_params, phases=4, state=st))
             out[f'detect_{tag}_ms'] = time_ms(lambda: ops.detect_batched(s, cfg.extractor_params, phases=7 | bit, state=st))
             out[f'round1_{tag}_gbs'] = out['bytes'] / out[f'round1_{tag}_ms'] / 1e6

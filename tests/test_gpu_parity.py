@@ -61,12 +61,13 @@ def test_fast_nms_batch_is_joint_like_the_reference():
 
 # ------------------------------------------------------------------------------------------------ detection
 
-# round 1 of the sparse path has two kernels with identical output (kb_round1_stream.cu for large batches,
-# the tiled round1_kernel otherwise): phases bit 3 / bit 4 force one of them (include/kb_b200.h)
-ROUND1 = {'tiled': 7 | 8, 'stream': 7 | 16}
+# round 1 of the sparse path has three kernels with identical output (kb_round1_packed.cu for large batches, the tiled
+# round1_kernel otherwise, kb_round1_stream.cu as a tested alternative): phases bit 3 / 4 / 5 force one of them
+# (include/kb_b200.h)
+ROUND1 = {'tiled': 7 | 8, 'stream': 7 | 16, 'packed': 7 | 32}
 
 
-@pytest.fixture(params=['tiled', 'stream'])
+@pytest.fixture(params=['tiled', 'stream', 'packed'])
 def round1(request):
     return ROUND1[request.param]
 
@@ -557,12 +558,12 @@ def test_detect_sparse_randomised_against_greedy_oracle(seed, round1):
     assert np.array_equal(xyp[0, :n].cpu().numpy(), want)
 
 
-@pytest.mark.parametrize('h,w,r,top_k,nmaps', [(480, 640, 6, 1000, 96), (376, 1241, 6, 1000, 56), (480, 640, 4, 4096, 80),
-                                               (203, 517, 3, 300, 150)])
+@pytest.mark.parametrize('h,w,r,top_k,nmaps', [(480, 640, 6, 1000, 96), (376, 1241, 6, 1000, 57), (480, 640, 4, 4096, 80),
+                                               (203, 517, 3, 300, 151)])
 def test_detect_large_batch_stream_equals_tiled_and_oracle(h, w, r, top_k, nmaps):
-    """A batch large enough for the automatic choice to be the streaming round-1 kernel (CTAs walk several bands,
-    bands cross map boundaries): automatic == forced streaming == forced tiled, bit for bit, and a few maps of the
-    batch equal the greedy oracle."""
+    """A batch large enough for the automatic choice to be the packed streaming round-1 kernel (CTAs walk several bands,
+    bands cross map boundaries, an odd batch leaves the last pair half empty): automatic == forced packed == forced fp32
+    streaming == forced tiled, bit for bit, and a few maps of the batch equal the greedy oracle."""
     params = dict(nms_dist=r, threshold=0.0, border_dist=8, top_k=top_k, min_score=0.0)
     gen = torch.Generator(device=DEV).manual_seed(4242 + h)
     s = torch.rand(nmaps, 1, h, w, generator=gen, device=DEV)
@@ -571,11 +572,11 @@ def test_detect_large_batch_stream_equals_tiled_and_oracle(h, w, r, top_k, nmaps
     s[6, 0, :, w // 3] = 0.9995                               # a column of equal values
     s[7] -= 0.5                                               # negative scores -> flagged for the round-faithful kernel
     outs = {}
-    for name, ph in (('auto', 7), ('tiled', 7 | 8), ('stream', 7 | 16)):
+    for name, ph in (('auto', 7), ('tiled', 7 | 8), ('stream', 7 | 16), ('packed', 7 | 32)):
         with torch.no_grad():
             xyp, count, raster, path = ops().detect_batched(s, params, phases=ph)
         outs[name] = (xyp.cpu().numpy(), count.cpu().numpy(), raster.cpu().numpy(), path.cpu().numpy())
-    for name in ('tiled', 'stream'):
+    for name in ('tiled', 'stream', 'packed'):
         assert np.array_equal(outs['auto'][1], outs[name][1]), name
         assert np.array_equal(outs['auto'][3], outs[name][3]), name
         for b in range(nmaps):
