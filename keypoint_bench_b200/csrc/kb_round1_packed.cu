@@ -65,6 +65,34 @@ __device__ __forceinline__ uint32_t heq2_mask(uint32_t a, uint32_t b) {
     return d;
 }
 
+// Split-phase CTA barriers (mbarrier): a thread ARRIVES when its writes are done and WAITS only where it needs the other
+// threads' data, doing list / store work that touches no shared data of the others in between, so a warp that is late
+// (a few candidates more) does not idle the rest of the CTA.
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    long long t0 = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) break;
+        // a protocol bug must fail loudly, not hang the GPU: give up after ~2 s of waiting
+        const long long now = clock64();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 4000000000LL) __trap();
+    }
+}
+
 template <bool VEC>
 __device__ __forceinline__ float4 load_row4(const float* __restrict__ img, int row, int x4, int H, int W) {   // any row
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -221,24 +249,39 @@ __device__ __forceinline__ bool tie_verdict(const uint32_t* raw, int VP, uint32_
     return true;
 }
 
-// ring_col: the ring at the candidate's column (raw + PADC + x); slot0 = ring row of map row `row - R`
+// Fast part of the verdict: does any OTHER pixel of the candidate's row-buffer row (2R columns) or of its own ring
+// column (2R rows) share its packed value?  own = the candidate's word in the ring (chunk k, row o of the chunk), vrow =
+// its word in the row buffer; fix_prev / fix_next = what to add to own + d * VP when row o + d lies in chunk k-1 / k+1 and
+// that chunk's ring slot is not adjacent (the ring wraps every four chunks).  One load, one LOP3 (xor + half mask) and one
+// unsigned minimum per element: the minimum is 0 iff some element ties.
 template <int R>
-__device__ __forceinline__ bool is_round1_max(const uint32_t* raw, const uint32_t* VM, int VP, int o, int row, int x, int h,
-                                              const float* __restrict__ img, int H, int W) {
-    const uint16_t* vm16 = reinterpret_cast<const uint16_t*>(VM + o * VP + PADC + x) + h;      // stride 2 per column
-    const uint16_t* col16 = reinterpret_cast<const uint16_t*>(raw + PADC + x) + h;             // stride 2 * VP per row
-    const uint32_t qv = col16[2 * ((row & (RING - 1)) * VP)];
-    uint32_t tie_cols = 0u, tie_rows = 0u;
-    int slot = (row - R) & (RING - 1);
+__device__ __forceinline__ bool is_round1_max(const uint32_t* raw, const uint32_t* own, const uint32_t* vrow, int VP, int fix_prev,
+                                              int fix_next, int o, int row, int x, int h, const float* __restrict__ img, int H, int W) {
+    const uint32_t hmask = h ? 0xffff0000u : 0x0000ffffu;
+    const uint32_t qv2 = __byte_perm(*own, 0u, h ? 0x3232 : 0x1010);            // the candidate's value in both halves
+    uint32_t mn4[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};    // four independent chains
 #pragma unroll
     for (int d = -R; d <= R; ++d) {
-        if (d != 0) {
-            if (vm16[2 * d] == qv) tie_cols |= 1u << (d + R);
-            if (col16[2 * slot * VP] == qv) tie_rows |= 1u << (d + R);
-        }
-        slot = (slot + 1) & (RING - 1);
+        if (d == 0) continue;
+        mn4[(d + R) & 1] = min(mn4[(d + R) & 1], (vrow[d] ^ qv2) & hmask);
+        const uint32_t* a = own + d * VP;
+        if (d < 0 && o + d < 0) a += fix_prev;
+        if (d > 0 && o + d >= S) a += fix_next;
+        mn4[2 + ((d + R) & 1)] = min(mn4[2 + ((d + R) & 1)], (*a ^ qv2) & hmask);
     }
-    if ((tie_cols | tie_rows) == 0u) return true;
+    const uint32_t mn = min(min(mn4[0], mn4[1]), min(mn4[2], mn4[3]));
+    if (mn != 0u) return true;
+    // a 16-bit tie (rare): which columns / rows, then fp32
+    const uint32_t qv = qv2 & 0xffffu;
+    const uint16_t* vm16 = reinterpret_cast<const uint16_t*>(vrow) + h;
+    const uint16_t* col16 = reinterpret_cast<const uint16_t*>(raw + PADC + x) + h;
+    uint32_t tie_cols = 0u, tie_rows = 0u;
+#pragma unroll 1
+    for (int d = -R; d <= R; ++d) {
+        if (d == 0) continue;
+        if (vm16[2 * d] == qv) tie_cols |= 1u << (d + R);
+        if (col16[2 * (((row + d) & (RING - 1)) * VP)] == qv) tie_rows |= 1u << (d + R);
+    }
     return tie_verdict<R>(raw, VP, tie_cols, tie_rows, qv, row, x, h, img, H, W);
 }
 
@@ -258,6 +301,15 @@ __global__ void __launch_bounds__(NTC ? NTC : MAX_NT, (NTC && NTC <= 160) ? 2 : 
     uint32_t* const VMc = VM + PADC + x4;                         // ... and row buffer
     auto slot = [&](int chunk) { return rawc + ((chunk & 3) * S) * VP; };      // ring row 0 of a chunk
     const bool col_ok = (WC && NTC && 4 * NTC <= WC) ? true : x4 < Wd;
+    __shared__ __align__(8) uint64_t s_bar[2];                    // [0] row buffer complete, [1] chunk done everywhere
+    const uint32_t bar_rows = (uint32_t)__cvta_generic_to_shared(&s_bar[0]);
+    const uint32_t bar_done = (uint32_t)__cvta_generic_to_shared(&s_bar[1]);
+    uint32_t par_rows = 0u, par_done = 0u;
+    if (t == 0) {
+        mbar_init(bar_rows, NT);
+        mbar_init(bar_done, NT);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
 
     for (int i = t; i < (RING + S) * 2 * PADC; i += NT) {         // (raw and VM are contiguous)
         const int r = i / (2 * PADC), c = i - r * (2 * PADC);
@@ -342,6 +394,46 @@ __global__ void __launch_bounds__(NTC ? NTC : MAX_NT, (NTC && NTC <= 160) ? 2 : 
         XB[2 + t] = 0u;
         XB[XP + 2 + t] = 0u;
         __syncthreads();
+        mbar_arrive(bar_done);                                    // (the first iteration's wait)
+
+        // lists, part 2: the state part 1 left one iteration ago
+        bool q_valid = false;
+        int q_j = 0, q_base = 0, q_pre[2] = {0, 0}, q_tot[2] = {0, 0};
+        uint32_t q_both[2] = {0u, 0u}, q_emM[2] = {0u, 0u};
+        float q_sc[2][NPRE];
+        auto write_lists = [&]() {
+            if (!q_valid) return;
+            q_valid = false;
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                if (q_tot[m] == 0) continue;                      // (warp-uniform)
+                int offM = __shfl_sync(FULL, q_base, 2 * m) + (q_pre[m] & 0xffff);
+                int offO = __shfl_sync(FULL, q_base, 2 * m + 1) + (q_pre[m] >> 16);
+                uint32_t bb = q_both[m];
+                auto put = [&](int bit, float score) {
+                    const int row = S * q_j + (bit >> 2), x = x4 + (bit & 3);
+                    KB_ASSERT(row >= 0 && row < H && x < Wd);
+                    // (listed scores are > tau >= 0: their order key is the bit pattern with the top bit set)
+                    const uint64_t key = ((uint64_t)(__float_as_uint(score) | 0x80000000u) << 32) |
+                                         (uint64_t)(0xffffffffu - (uint32_t)(row * Wd + x));
+                    if ((q_emM[m] >> bit) & 1u) { if (offM < LIST_CAP) LM[m][offM] = key; ++offM; }
+                    else { if (offO < LIST_CAP) LO[m][offO] = key; ++offO; }
+                };
+#pragma unroll
+                for (int i = 0; i < NPRE; ++i) {
+                    if (bb) {
+                        const int bit = __ffs(bb) - 1;
+                        bb &= bb - 1;
+                        put(bit, q_sc[m][i]);
+                    }
+                }
+                while (bb) {                                      // more than NPRE listed pixels in one patch: rare
+                    const int bit = __ffs(bb) - 1;
+                    bb &= bb - 1;
+                    put(bit, __ldg(img[m] + (unsigned)((S * q_j + (bit >> 2)) * Wd + x4 + (bit & 3))));
+                }
+            }
+        };
 
         // iteration k: maxima of chunk k, coverage words of chunk k-1, lists of chunk k-2, rows of chunk k+2
         for (int k = c0 - 1; k <= c1 + 1; ++k) {
@@ -349,6 +441,8 @@ __global__ void __launch_bounds__(NTC ? NTC : MAX_NT, (NTC && NTC <= 160) ? 2 : 
             const bool pf = k + 2 <= c1 + 1;
             float4 f0[S / 2], f1[S / 2];
             if (pf) load_rows(k + 2, 0, f0, f1);
+            mbar_wait(bar_done, par_done);                        // chunk k-1 is done everywhere: row buffer, ring slot and
+            par_done ^= 1u;                                       // the coverage words may be reused / read
 
             // ---- lists of chunk j = k-2, part 1: what to list, where, and the scores on their way ---------------------
             const int j = k - 2;
@@ -411,7 +505,23 @@ __global__ void __launch_bounds__(NTC ? NTC : MAX_NT, (NTC && NTC <= 160) ? 2 : 
                 store_rows(k + 2, std::integral_constant<int, 0>{}, f0, f1, hot[0][4], hot[1][4]);
                 load_rows(k + 2, S / 2, f0, f1);
             }
-            __syncthreads();                                      // row buffer complete; the list words were read
+            mbar_arrive(bar_rows);                                // my part of the row buffer is written, the list words are read
+
+            // ---- lists, part 2, of the chunk part 1 prepared ONE ITERATION AGO (global memory only: in the shadow of the
+            //      barrier; the atomics and score loads of that part 1 have had a whole iteration to land) ------------
+            write_lists();
+            if (listing) {
+                q_valid = true; q_j = j; q_base = base;
+#pragma unroll
+                for (int m = 0; m < 2; ++m) {
+                    q_both[m] = both[m]; q_emM[m] = emM[m]; q_pre[m] = pre[m]; q_tot[m] = tot[m];
+#pragma unroll
+                    for (int i = 0; i < NPRE; ++i) q_sc[m][i] = sc[m][i];
+                }
+            }
+
+            mbar_wait(bar_rows, par_rows);                        // row buffer complete
+            par_rows ^= 1u;
 
             // ---- horizontal window maxima, candidates of chunk k ----------------------------------------------
             uint32_t cand[2] = {0u, 0u};
@@ -432,48 +542,19 @@ __global__ void __launch_bounds__(NTC ? NTC : MAX_NT, (NTC && NTC <= 160) ? 2 : 
                 cand[0] = __byte_perm(lo4, hi4, 0x5410) & hot[0][2];
                 cand[1] = __byte_perm(lo4, hi4, 0x7632) & hot[1][2];
             }
-            if (pf) store_rows(k + 2, std::integral_constant<int, S / 2>{}, f0, f1, hot[0][4], hot[1][4]);
-
-            // ---- lists of chunk j, part 2 (the atomics and the score loads of part 1 have had two passes to land) -----
-            if (listing) {
-#pragma unroll
-                for (int m = 0; m < 2; ++m) {
-                    if (tot[m] == 0) continue;                    // (warp-uniform)
-                    int offM = __shfl_sync(FULL, base, 2 * m) + (pre[m] & 0xffff);
-                    int offO = __shfl_sync(FULL, base, 2 * m + 1) + (pre[m] >> 16);
-                    uint32_t bb = both[m];
-                    auto put = [&](int bit, float score) {
-                        const int row = S * j + (bit >> 2), x = x4 + (bit & 3);
-                        KB_ASSERT(row >= 0 && row < H && x < Wd);
-                        const uint64_t key = kb::priority_key(score, (uint32_t)(row * Wd + x));
-                        if ((emM[m] >> bit) & 1u) { if (offM < LIST_CAP) LM[m][offM] = key; ++offM; }
-                        else { if (offO < LIST_CAP) LO[m][offO] = key; ++offO; }
-                    };
-#pragma unroll
-                    for (int i = 0; i < NPRE; ++i) {
-                        if (bb) {
-                            const int bit = __ffs(bb) - 1;
-                            bb &= bb - 1;
-                            put(bit, sc[m][i]);
-                        }
-                    }
-                    while (bb) {                                  // more than NPRE listed pixels in one patch: rare
-                        const int bit = __ffs(bb) - 1;
-                        bb &= bb - 1;
-                        put(bit, __ldg(img[m] + (unsigned)((S * j + (bit >> 2)) * Wd + x4 + (bit & 3))));
-                    }
-                }
-            }
-
             // ---- candidates -> round-1 maxima (rare: ~1 pixel in (2R+1)^2), both maps in one loop ---------------
             {
                 uint32_t ca = cand[0], cb2 = cand[1];
+                const uint32_t* cur = slot(k);
+                const int fix_prev = (k & 3) == 0 ? RING * VP : 0, fix_next = (k & 3) == 3 ? -RING * VP : 0;
                 while (ca | cb2) {
                     const int m = ca ? 0 : 1;
                     uint32_t& cc = ca ? ca : cb2;
                     const int bit = __ffs(cc) - 1;
                     cc &= cc - 1;
-                    if (is_round1_max<R>(raw, VM, VP, bit >> 2, S * k + (bit >> 2), x4 + (bit & 3), m, m ? img[1] : img[0], H, Wd)) {
+                    const int o = bit >> 2, jj = bit & 3;
+                    if (is_round1_max<R>(raw, cur + o * VP + jj, VMc + o * VP + jj, VP, fix_prev, fix_next, o, S * k + o, x4 + jj, m,
+                                         m ? img[1] : img[0], H, Wd)) {
                         if (m) mx[1][2] |= 1u << bit; else mx[0][2] |= 1u << bit;
                     }
                 }
@@ -481,13 +562,18 @@ __global__ void __launch_bounds__(NTC ? NTC : MAX_NT, (NTC && NTC <= 160) ? 2 : 
             // ---- coverage words of chunk k-1 (rows), for the neighbours ----------------------------------------
             XB[2 + t] = vdilate<R>(mx[0][0], mx[0][1], mx[0][2]);
             XB[XP + 2 + t] = vdilate<R>(mx[1][0], mx[1][1], mx[1][2]);
-            __syncthreads();                                      // chunk k done everywhere
+            mbar_arrive(bar_done);                                // chunk k done here
+            // (rows 4..7 of chunk k+2 go to a ring slot nobody reads before the next row-buffer barrier)
+            if (pf) store_rows(k + 2, std::integral_constant<int, S / 2>{}, f0, f1, hot[0][4], hot[1][4]);
 #pragma unroll
             for (int m = 0; m < 2; ++m) {
                 hot[m][0] = hot[m][1]; hot[m][1] = hot[m][2]; hot[m][2] = hot[m][3]; hot[m][3] = hot[m][4]; hot[m][4] = 0u;
                 mx[m][0] = mx[m][1]; mx[m][1] = mx[m][2]; mx[m][2] = 0u;
             }
         }
+        write_lists();                                            // the last chunk of the band
+        mbar_wait(bar_done, par_done);                            // (every arrival is waited for: the parity stays in step)
+        par_done ^= 1u;
         if (__any_sync(FULL, (neg0 >> 31) != 0u) && lane == 0) atomicOr(&p.flags[bm[0]], 1);
         if (__any_sync(FULL, (neg1 >> 31) != 0u) && lane == 0) atomicOr(&p.flags[bm[1]], 1);
     }
@@ -505,7 +591,7 @@ int launch_t(const SparseParams& p, int nt, int cpm, int total, bool force, cuda
     static bool configured = false;
     const size_t smem = packed_smem_bytes(nt);
     if (!configured) {
-        KB_CUDA_TRY(cudaFuncSetAttribute(round1_packed_kernel<R, VEC, NTC, WC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        KB_CUDA_TRY(cudaFuncSetAttribute(round1_packed_kernel<R, VEC, NTC, WC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256));   // (16 bytes of static shared memory: the barriers)
         KB_CUDA_TRY(cudaFuncSetAttribute(round1_packed_kernel<R, VEC, NTC, WC>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         configured = true;
     }
