@@ -605,12 +605,12 @@ int launch_t(const SparseParams& p, int nt, int cpm, int total, bool force, cuda
         cached_nt = nt;
     }
     // A band costs three extra iterations and the synchronous load of three chunks: bands are kept at MIN_BAND chunks
-    // or more, and when that leaves fewer than 64 CTAs (a handful of maps) the tiled kernel, whose grid is tiles x maps,
-    // is the better choice.
+    // or more, and when that leaves fewer than 96 CTAs (a handful of maps; measured: 8 maps of 1024 x 1024 take 59 us here
+    // and 42 us in the tiled kernel) the tiled kernel, whose grid is tiles x maps, is the better choice.
     int grid = total / MIN_BAND;
     if (grid > cached_grid) grid = cached_grid;
     if (force && grid < 1) grid = 1;
-    if (!force && grid < 64) return KB_ERR_UNSUPPORTED;
+    if (!force && grid < 96) return KB_ERR_UNSUPPORTED;
     round1_packed_kernel<R, VEC, NTC, WC><<<grid, nt, smem, st>>>(p, cpm, total);
     KB_LAUNCH_CHECK();
     return KB_OK;
