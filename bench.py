@@ -56,6 +56,7 @@ def parse_args():
     ap.add_argument('--cpu-pairs', type=int, default=2, help='pairs timed on the host for cpu_baseline (0 = skip)')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-others', action='store_true', help='skip the brief runs of the other four configs')
+    ap.add_argument('--fused-table', action='store_true', help='per-kernel table of the opt-in fused sampling + operand preparation (A/B)')
     ap.add_argument('--in-flight', type=int, default=3,
                     help='steps kept in flight (one CUDA graph + stream + batch per slot); 1 = strictly serial steps')
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel from Python instead of replaying a CUDA graph')
@@ -222,6 +223,9 @@ def time_ms(fn, reps=5):
     return e0.elapsed_time(e1) / reps
 
 
+FUSED_TABLE = False
+
+
 def kernel_table(cfg, inputs, res, algo, tc, pk):
     """Every kernel group of one step timed ALONE (5 back-to-back launches between CUDA events on the launch stream,
     through the library's measurement hooks), with its algorithmic bytes / flops and roofline fraction.
@@ -261,27 +265,56 @@ def kernel_table(cfg, inputs, res, algo, tc, pk):
         return k
     npts = float(n_pts.float().sum().item())
     hw = (cfg.height // cfg.desc_stride) * (cfg.width // cfg.desc_stride)
-    k['sample (bilinear descriptor sampling)'] = {
-        'ms': time_ms(lambda: ops.sample_batched(desc, pts, n_pts)), 'bound': 'hbm',
-        'algorithmic_bytes': min(16 * npts * cfg.desc_dim, 4.0 * cfg.desc_dim * hw * n_img) + 4 * npts * cfg.desc_dim + 8 * npts,
-        'sector_bytes': (64.0 * npts * cfg.desc_dim if cfg.desc_stride == 1 else None)}
+    sample_bytes = min(16 * npts * cfg.desc_dim, 4.0 * cfg.desc_dim * hw * n_img) + 4 * npts * cfg.desc_dim + 8 * npts
     dd = res['desc']
     a, b = (dd[:-1], dd[1:]) if stream else (dd[:P], dd[P:])
     na, nb = (n_pts[:-1], n_pts[1:]) if stream else (n_pts[:P], n_pts[P:])
     flops = float((2.0 * na.double() * nb.double() * cfg.desc_dim).sum().item())        # ONE pass of 2 n m D per pair
     margs = (a, b, na, nb, cfg.max_distance, cfg.cross_check)
+    search_name = 'match.search (tcgen05 Gram + fused top-3 epilogue)'
+    tail_name = 'match.tail (certify / rescan / gate / pairs)'
+    passes = ops.match_issue_factor(bool(cfg.cross_check), cfg.desc_dim) if tc else 0
+    note = f'{passes}x the one-pass flops are issued to the tensor pipe (directions x products of the split operands)'
+    fused = (FUSED_TABLE and tc and not stream and pts.shape[1] > 0 and
+             bool(ops.lib.kb_sample_desc_operands_supported(cfg.desc_dim, cfg.height // cfg.desc_stride, cfg.width // cfg.desc_stride,
+                                                            pts.shape[1])))
+    if fused:
+        # --fused-table: the opt-in form in which the sampler writes the matcher's operand rows (kb_sample_desc_operands);
+        # the step itself runs the two calls (measured faster), so this table is for A/B only
+        fst = []
+        fargs = (desc, pts, n_pts, P, cfg.max_distance, cfg.cross_check)
+        ops.sample_match_batched(*fargs, algo=1, want_dist=False, fused=True, state=fst)
+        k['sample (bilinear descriptor sampling + 16-bit operand rows of the matcher, fused)'] = {
+            'ms': time_ms(lambda: ops.sample_match_batched(*fargs, algo=1, want_dist=False, state=fst, part='sample')), 'bound': 'hbm',
+            'algorithmic_bytes': sample_bytes + 4 * npts * cfg.desc_dim,
+            'bytes_note': 'maps once + float32 rows + hi/lo 16-bit operand rows + coordinates'}
+        k['match.finish (row norms from the sampler\'s partial sums, c, padding)'] = {
+            'ms': time_ms(lambda: ops.sample_match_batched(*fargs, algo=1, want_dist=False, state=fst, part='finish')), 'bound': 'latency',
+            'algorithmic_bytes': 0.0}
+        k[search_name] = {
+            'ms': time_ms(lambda: ops.sample_match_batched(*fargs, algo=1, want_dist=False, state=fst, part='search')), 'bound': 'tensor',
+            'algorithmic_flops': flops, 'issued_flops': flops * passes, 'issued_note': note}
+        k[tail_name] = {
+            'ms': time_ms(lambda: ops.sample_match_batched(*fargs, algo=1, want_dist=False, state=fst, part='tail')), 'bound': 'latency',
+            'algorithmic_bytes': 12.0 * float(res['n_matches'].float().sum().item())}
+        k['sample + match (whole stage)'] = {
+            'ms': time_ms(lambda: ops.sample_match_batched(*fargs, algo=1, want_dist=False, state=fst)), 'bound': 'tensor',
+            'algorithmic_flops': flops, 'stage': True}
+        return k
+    k['sample (bilinear descriptor sampling)'] = {
+        'ms': time_ms(lambda: ops.sample_batched(desc, pts, n_pts)), 'bound': 'hbm',
+        'algorithmic_bytes': sample_bytes,
+        'sector_bytes': (64.0 * npts * cfg.desc_dim if cfg.desc_stride == 1 else None)}
     if tc:
         mst = []
         ops.match_batched(*margs, algo=1, state=mst, want_dist=False)
-        passes = ops.match_issue_factor(bool(cfg.cross_check), cfg.desc_dim)
         k['match.prep (hi/lo 16-bit split + norms)'] = {
             'ms': time_ms(lambda: ops.match_batched(*margs, algo=1, phases=1, state=mst, want_dist=False)), 'bound': 'hbm',
             'algorithmic_bytes': 0.0}
-        k['match.search (tcgen05 Gram + fused top-3 epilogue)'] = {
+        k[search_name] = {
             'ms': time_ms(lambda: ops.match_batched(*margs, algo=1, phases=2, state=mst, want_dist=False)), 'bound': 'tensor',
-            'algorithmic_flops': flops, 'issued_flops': flops * passes,
-            'issued_note': f'{passes}x the one-pass flops are issued to the tensor pipe (directions x products of the split operands)'}
-        k['match.tail (certify / rescan / gate / pairs)'] = {
+            'algorithmic_flops': flops, 'issued_flops': flops * passes, 'issued_note': note}
+        k[tail_name] = {
             'ms': time_ms(lambda: ops.match_batched(*margs, algo=1, phases=4, state=mst, want_dist=False)), 'bound': 'latency',
             'algorithmic_bytes': 12.0 * float(res['n_matches'].float().sum().item())}
     k['match (whole stage)'] = {'ms': time_ms(lambda: ops.match_batched(*margs, algo=algo, want_dist=False)),
@@ -578,7 +611,9 @@ def run_e2e(args, cfg, batches, step, flight, depth, P, world, device, task_rep)
 
 
 def main():
+    global FUSED_TABLE
     args = parse_args()
+    FUSED_TABLE = bool(args.fused_table)
     rank = int(os.environ.get('RANK', 0))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))

@@ -168,6 +168,18 @@ KB_API int kb_lk_track(const float* img0, const float* img1, int B, int C, int H
 KB_API int kb_sample_desc(const float* desc, int B, int C, int h, int w, const float* pts, int pts_stride,
                    const int* count, int n_max, int normalize, int coord_mode, int s, float* out,
                    kb_stream_t stream);
+/* The same sampling (normalize = 0) for the 2 * pairs maps of a batch of image pairs (maps [0, pairs) = image 0, maps
+ * [pairs, 2 * pairs) = image 1; desc [2 * pairs, C, h, w], pts / count / out as above) FUSED with the operand
+ * preparation of the kb_match_mnn(algo = 1) call that follows on (out[0 : pairs], out[pairs : 2 * pairs], n_max = m_max):
+ * besides the float32 rows it writes the 16-bit operand rows and partial row norms into that call's workspace
+ * `match_ws` (sized by kb_match_workspace_bytes(pairs, n_max, n_max, C, 1)), and the match call passes phases 6 | 8
+ * (bit 3 = operands already in place) to kb_match_mnn_phases.  Same pairs as the two separate calls; one pass over the
+ * float32 rows less.  kb_sample_desc_operands_supported: low-resolution maps sampled densely (the plane-staged sampler's
+ * case), C a multiple of 64 up to 256, n_max <= 1024; otherwise KB_ERR_UNSUPPORTED -- callers then make the two calls. */
+KB_API int kb_sample_desc_operands_supported(int C, int h, int w, int n_max);
+KB_API int kb_sample_desc_operands(const float* desc, int pairs, int C, int h, int w, const float* pts, int pts_stride,
+                            const int* count, int n_max, int coord_mode, int s, float* out, void* match_ws,
+                            size_t match_ws_bytes, kb_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Stage 3 -- mutual-nearest-neighbour matching
@@ -188,9 +200,10 @@ KB_API size_t kb_match_workspace_bytes(int B, int n_max, int m_max, int D, int a
 KB_API int kb_match_mnn(const float* d0, const float* d1, const int* n0, const int* n1, int B, int n_max,
                  int m_max, int D, double max_distance, int cross_check, int algo, int* pairs,
                  double* dist, int* count, void* ws, size_t ws_bytes, kb_stream_t stream);
-/* Measurement hook: kb_match_mnn restricted to the parts selected by `phases` (bit 0 operand preparation,
- * bit 1 tensor-core search kernel, bit 2 certification / rescans / gate / pair compaction) on a workspace that
- * a full call (phases = 7) has filled before; tensor-core path only.  kb_match_mnn == phases 7. */
+/* kb_match_mnn restricted to the parts selected by `phases` (bit 0 operand preparation, bit 1 tensor-core search
+ * kernel, bit 2 certification / rescans / gate / pair compaction) on a workspace that a full call (phases = 7) has
+ * filled before (a measurement hook); tensor-core path only.  kb_match_mnn == phases 7.  Bit 3 instead of bit 0: the
+ * operand rows were written by kb_sample_desc_operands (phases 6 | 8 is the product call after it). */
 KB_API int kb_match_mnn_phases(const float* d0, const float* d1, const int* n0, const int* n1, int B, int n_max,
                         int m_max, int D, double max_distance, int cross_check, int algo, int* pairs, double* dist,
                         int* count, void* ws, size_t ws_bytes, int phases, kb_stream_t stream);

@@ -43,6 +43,9 @@ PROTOTYPES = {
                                  c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
     'kb_sample_desc': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
                                c_int, c_void_p, c_void_p]),
+    'kb_sample_desc_operands_supported': (c_int, [c_int, c_int, c_int, c_int]),
+    'kb_sample_desc_operands': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
+                                        c_void_p, c_void_p, c_size_t, c_void_p]),
     'kb_match_workspace_bytes': (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     'kb_match_mnn': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_double, c_int,
                              c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

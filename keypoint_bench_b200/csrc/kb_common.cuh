@@ -31,6 +31,14 @@ extern int kb_knobs[8];
 // multiprocessor count of the current device (looked up once per device and process)
 int kb_sm_count(int* sms);
 
+// kb_match_tc.cu: where the fused sampler (kb_sample.cu) writes the matcher's operand rows
+struct KbOperandSinks {
+    unsigned short* S[2];     // [B*n_max, 2*Dp] 16-bit halves [hi | lo] of side 0 / side 1
+    float* part[2];           // [B*n_max, Dp/8] partial |row|^2 per group of 8 components
+    int Dp, fp16;
+};
+int kb_match_tc_operand_sinks(void* ws, size_t ws_bytes, int B, int n_max, int m_max, int D, KbOperandSinks* out);
+
 static inline size_t kb_align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // Bump allocator over the caller's workspace (the library never allocates).

@@ -225,14 +225,14 @@ extern "C" int kb_match_mnn_phases(const float* d0, const float* d1, const int* 
                                    int m_max, int D, double max_distance, int cross_check, int algo, int* pairs,
                                    double* dist, int* count, void* ws, size_t ws_bytes, int phases, kb_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    if (phases <= 0 || phases > 7) return KB_ERR_BAD_ARG;
+    if (phases <= 0 || phases > 15 || (phases & 9) == 9) return KB_ERR_BAD_ARG;      // bit 3: operands prepared by the sampler
     if (!d0 || !d1 || !pairs || !count || B <= 0 || n_max <= 0 || m_max <= 0 || D <= 0) return KB_ERR_BAD_ARG;
     if (algo < 0) algo = (D <= 256) ? 1 : 0;       // auto: tensor cores whenever the query tile fits on chip
     if (algo == 1)
         return kb_match_tc_run(d0, d1, n0, n1, B, n_max, m_max, D, max_distance, cross_check, pairs, dist, count,
                                ws, ws_bytes, phases, st);
     if (algo != 0) return KB_ERR_BAD_ARG;
-    if (phases != 7) return KB_ERR_UNSUPPORTED;      // the float64 path has no separately timed parts
+    if (phases != 7) return KB_ERR_UNSUPPORTED;      // the float64 path has no separately timed / external parts
     if (B > 65535) return KB_ERR_UNSUPPORTED;
     MatchParams p;
     p.tiles_i = (n_max + TM - 1) / TM;

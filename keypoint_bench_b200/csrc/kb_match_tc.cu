@@ -350,6 +350,50 @@ __global__ void __launch_bounds__(256) prep_kernel(PrepPair pp) {
     }
 }
 
+// Operand rows written by the fused sampler (kb_sample.cu: 16-bit halves and, per row and group of 8 components, the
+// partial |row|^2): what is left of the preparation is one thread per row -- |row|^2 summed in a fixed order, c, the
+// -inf padding and the largest |row|^2 of the batch item.
+struct PrepFinish {
+    const float* part;       // [B*n_max, Dp/8]
+    const int* cnt;
+    float* c;
+    float* norm2;
+    unsigned int* maxn;
+    int n_max, cs, nparts;
+};
+struct PrepFinishPair {
+    PrepFinish side[2];
+};
+
+__global__ void __launch_bounds__(256) prep_finish_kernel(PrepFinishPair pp) {
+    const PrepFinish& p = pp.side[blockIdx.z];
+    const int b = blockIdx.y, row = blockIdx.x * 256 + threadIdx.x;
+    __shared__ float s_max[8];
+    const int n = p.cnt ? p.cnt[b] : p.n_max;
+    float ss = 0.0f;
+    if (row < n) {
+        const float4* q = reinterpret_cast<const float4*>(p.part + ((size_t)b * p.n_max + row) * p.nparts);
+        for (int k = 0; k < p.nparts / 4; ++k) {
+            const float4 v = __ldg(q + k);
+            ss += v.x; ss += v.y; ss += v.z; ss += v.w;
+        }
+        for (int k = p.nparts / 4 * 4; k < p.nparts; ++k) ss += p.part[((size_t)b * p.n_max + row) * p.nparts + k];
+        p.c[(size_t)b * p.cs + row] = -0.5f * ss;
+        p.norm2[(size_t)b * p.n_max + row] = ss;
+    } else if (row < p.cs) {
+        p.c[(size_t)b * p.cs + row] = -CUDART_INF_F;
+        if (row < p.n_max) p.norm2[(size_t)b * p.n_max + row] = 0.0f;
+    }
+    float mx = ss;
+    for (int d = 16; d > 0; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+    if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) mx = fmaxf(mx, s_max[w]);
+        if (mx > 0.0f) atomicMax(&p.maxn[b], __float_as_uint(mx));
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // main kernel
 // ------------------------------------------------------------------------------------------------
@@ -1318,6 +1362,8 @@ static TcLayout tc_layout(int B, int n_max, int m_max, int D) {
     add((size_t)B * m_max * 16);                // per-column summary of the group maxima
     add((size_t)B * n_max * 8);                 // columns queued for the exact rescan
     add(8 * 512 * 8);                           // pipeline wait counters (KB_KNOB_TC_DEBUG & 4)
+    add((size_t)B * n_max * (L.Dp / 8) * 4);    // partial |row|^2 per 8 components (operands written by the sampler)
+    add((size_t)B * m_max * (L.Dp / 8) * 4);
     L.bytes = n + 1024;
     return L;
 }
@@ -1341,6 +1387,7 @@ struct TcBuffers {
     int4* colinfo;
     int2* list2;
     long long* prof;
+    float *part0, *part1;
     bool ok;
 };
 
@@ -1373,6 +1420,8 @@ static TcBuffers tc_carve(void* ws, size_t ws_bytes, int B, int n_max, int m_max
     t.colinfo = arena.take<int4>((size_t)B * m_max);
     t.list2 = arena.take<int2>((size_t)B * n_max);
     t.prof = arena.take<long long>(8 * 512);
+    t.part0 = arena.take<float>((size_t)B * n_max * (L.Dp / 8));
+    t.part1 = arena.take<float>((size_t)B * m_max * (L.Dp / 8));
     t.ok = arena.ok();
     return t;
 }
@@ -1386,6 +1435,26 @@ extern "C" KB_API int kb_match_tc_debug_offsets(int B, int n_max, int m_max, int
     TcBuffers t = tc_carve(base, (size_t)-1, B, n_max, m_max, L);
     off[0] = (char*)t.res0 - base; off[1] = (char*)t.res1 - base; off[2] = (char*)t.n_exact - base;
     off[3] = (char*)t.norm2_0 - base; off[4] = (char*)t.norm2_1 - base; off[5] = (char*)t.prof - base;
+    return KB_OK;
+}
+
+static int tc_operand_fp16(int Dp) {
+    // operand split: fp16 halves x 2 products where the search is MMA-bound (D > 64), bf16 halves x 3 where its
+    // epilogue is the bound anyway (D <= 64: the wider error bound would only add two-candidate checks and rescans);
+    // KB_KNOB_TC_BF16X3 = 1 / 2 forces bf16 x 3 / fp16 x 2
+    return kb_knobs[KB_KNOB_TC_BF16X3] == 1 ? 0 : (kb_knobs[KB_KNOB_TC_BF16X3] == 2 ? 1 : (Dp > 64 ? 1 : 0));
+}
+
+// Where a producer other than prep_kernel (the fused sampler, kb_sample.cu) writes the operand rows of a
+// kb_match_mnn(algo = 1) workspace; the match call that follows passes phases bit 3 instead of bit 0.
+int kb_match_tc_operand_sinks(void* ws, size_t ws_bytes, int B, int n_max, int m_max, int D, KbOperandSinks* out) {
+    if (B > 65535 || D % 8 != 0) return KB_ERR_UNSUPPORTED;
+    const TcLayout L = tc_layout(B, n_max, m_max, D);
+    if (L.KB > 4) return KB_ERR_UNSUPPORTED;
+    TcBuffers tb = tc_carve(ws, ws_bytes, B, n_max, m_max, L);
+    if (!tb.ok) return KB_ERR_WORKSPACE;
+    out->S[0] = tb.S0; out->S[1] = tb.S1; out->part[0] = tb.part0; out->part[1] = tb.part1;
+    out->Dp = L.Dp; out->fp16 = tc_operand_fp16(L.Dp);
     return KB_OK;
 }
 
@@ -1405,20 +1474,17 @@ int kb_match_tc_run(const float* d0, const float* d1, const int* n0, const int* 
     TcBuffers tb = tc_carve(ws, ws_bytes, B, n_max, m_max, L);
     if (!tb.ok) return KB_ERR_WORKSPACE;
     unsigned short *S0 = tb.S0, *S1 = tb.S1;
-    // operand split: fp16 halves x 2 products where the search is MMA-bound (D > 64), bf16 halves x 3 where its
-    // epilogue is the bound anyway (D <= 64: the wider error bound would only add two-candidate checks and rescans);
-    // KB_KNOB_TC_BF16X3 = 1 / 2 forces bf16 x 3 / fp16 x 2
-    const int fp16 = kb_knobs[KB_KNOB_TC_BF16X3] == 1 ? 0 : (kb_knobs[KB_KNOB_TC_BF16X3] == 2 ? 1 : (L.Dp > 64 ? 1 : 0));
+    const int fp16 = tc_operand_fp16(L.Dp);
     float *c0 = tb.c0, *c1 = tb.c1, *norm2_0 = tb.norm2_0, *norm2_1 = tb.norm2_1;
     unsigned int *maxn0 = tb.maxn0, *maxn1 = tb.maxn1;
     Top2 *res0 = tb.res0, *res1 = tb.res1;
     int *nn0 = tb.nn0, *nn1 = tb.nn1, *n_exact = tb.n_exact;
     double* d2_0 = tb.d2_0;
 
-    if (phases == 7) {
+    if ((phases & 7) == 7 || (phases & 15) == 14) {
         KB_CUDA_TRY(cudaMemsetAsync(maxn0, 0, tb.zero_bytes, st));      // maxn0, maxn1, n_exact, tickets in one node
     } else {
-        if (phases & 1) {
+        if (phases & 9) {
             KB_CUDA_TRY(cudaMemsetAsync(maxn0, 0, (size_t)B * 4, st));
             KB_CUDA_TRY(cudaMemsetAsync(maxn1, 0, (size_t)B * 4, st));
         }
@@ -1446,6 +1512,13 @@ int kb_match_tc_run(const float* d0, const float* d1, const int* n0, const int* 
         if (ctas < 1) ctas = 1;
         if (phases & 1) {
             prep_kernel<<<dim3(ctas, B, 2), 256, 0, st>>>(pp);
+            KB_LAUNCH_CHECK();
+        }
+        if (phases & 8) {                   // the operand rows and partial norms are in place (kb_sample_desc_operands)
+            PrepFinishPair fp;
+            fp.side[0] = PrepFinish{tb.part0, n0, c0, norm2_0, maxn0, n_max, L.cs0, L.Dp / 8};
+            fp.side[1] = PrepFinish{tb.part1, n1, c1, norm2_1, maxn1, m_max, L.cs1, L.Dp / 8};
+            prep_finish_kernel<<<dim3((cs_max + 255) / 256, B, 2), 256, 0, st>>>(fp);
             KB_LAUNCH_CHECK();
         }
     }

@@ -7,6 +7,8 @@
 // x-neighbours share a 32-byte sector), and the [n,C] output row is written coalesced.  The L2
 // norm is a warp-shuffle reduction over the lanes' partial sums.
 #include "kb_common.cuh"
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace {
 
@@ -210,6 +212,175 @@ __global__ void __launch_bounds__(PL_NT, 2) sample_planes_kernel(SampleParams p)
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Plane-staged sampling FUSED with the matcher's operand preparation (kb_match_tc.cu: prep_kernel): a CTA owns
+// EIGHT channels of one map -- four stages of two planes through two shared-memory buffers -- and every thread keeps
+// the eight samples of its (up to four) keypoints in registers, so that it can write, per keypoint, the 32-byte piece
+// of the float32 [n,C] row (a whole sector; the certification stages of the matcher read it), the 16-byte pieces of the
+// hi and lo halves of the matcher's operand row, and the partial |row|^2 of the eight components.  The float32 rows no
+// longer travel HBM -> SM -> HBM a second time just to be split.  Same sampling arithmetic as sample_kernel.
+constexpr int OP_C = 8;           // channels per CTA
+constexpr int OP_SC = 2;          // planes per stage: four stages through two buffers, the copy of stage s+2 (issued as soon
+constexpr int OP_STAGES = OP_C / OP_SC;   // as stage s has been read) overlaps the interpolation of stage s+1
+constexpr int OP_KP = 4;          // keypoints per thread: n_max <= OP_KP * PL_NT
+
+struct OperandParams {
+    SampleParams s;
+    unsigned short* S[2];         // operand rows of side 0 (maps [0, pairs)) and side 1 (maps [pairs, 2 pairs))
+    float* part[2];
+    int pairs, Dp, fp16;
+};
+
+__device__ __forceinline__ void split16_pair(float f, int fp16, unsigned short& h, unsigned short& l) {
+    if (fp16) {
+        const __half hh = __float2half_rn(f);
+        h = __half_as_ushort(hh);
+        l = __half_as_ushort(__float2half_rn(f - __half2float(hh)));
+    } else {
+        const __nv_bfloat16 hh = __float2bfloat16_rn(f);
+        h = __bfloat16_as_ushort(hh);
+        l = __bfloat16_as_ushort(__float2bfloat16_rn(f - __bfloat162float(hh)));
+    }
+}
+
+__global__ void __launch_bounds__(PL_NT, 2) sample_planes_operands_kernel(OperandParams q) {
+    const SampleParams& p = q.s;
+    extern __shared__ __align__(128) unsigned char pl_smem[];
+    __shared__ __align__(8) unsigned long long pl_bar[2];
+    float* planes = reinterpret_cast<float*>(pl_smem);
+    const int b = blockIdx.y, c0 = blockIdx.x * OP_C;
+    const int hw = p.h * p.w;
+    const int n = p.count ? p.count[b] : p.n_max;
+    const int side = b >= q.pairs ? 1 : 0, bs = b - side * q.pairs;
+    const float* src = p.desc + ((size_t)b * p.C + c0) * hw;
+    const uint32_t bytes = (uint32_t)OP_SC * hw * 4u;                // one stage (host: 16-byte aligned, a multiple of 16)
+    const uint32_t bar0 = smem_addr_u32(&pl_bar[0]);
+    auto issue = [&](int stage) {                                   // thread 0: planes c0 + OP_SC*stage .. into buffer stage & 1
+        const uint32_t bar = bar0 + 8u * (stage & 1);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        uint32_t done = 0;
+        while (done < bytes) {
+            const uint32_t piece = min(bytes - done, 32768u);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_addr_u32(pl_smem + (size_t)(stage & 1) * bytes + done)),
+                           "l"(reinterpret_cast<const char*>(src) + (size_t)stage * bytes + done), "r"(piece), "r"(bar) : "memory");
+            done += piece;
+        }
+    };
+    if (n > 0 && threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8u) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        issue(0);
+        issue(1);
+    }
+    // this thread's keypoints (k = threadIdx.x + i * PL_NT): taps and weights, while the first copy is in flight
+    float w_nw[OP_KP], w_ne[OP_KP], w_sw[OP_KP], w_se[OP_KP];
+    int o_nw[OP_KP];
+    unsigned taps[OP_KP];
+#pragma unroll
+    for (int i = 0; i < OP_KP; ++i) {
+        const int k = threadIdx.x + i * PL_NT;
+        taps[i] = 0u; o_nw[i] = 0;
+        w_nw[i] = w_ne[i] = w_sw[i] = w_se[i] = 0.0f;
+        if (k < n) {
+            const float* pt = p.pts + ((size_t)b * p.n_max + k) * p.stride;
+            const float kx = __ldg(pt), ky = __ldg(pt + 1);
+            float gx, gy;
+            if (p.coord_mode == 0) {                        // matcher.py:221-222
+                gx = (kx - 0.5f) * 2.0f;
+                gy = (ky - 0.5f) * 2.0f;
+            } else {                                        // lightglue.py:27-33
+                const float s = (float)p.s;
+                const float ax = kx - s / 2.0f + 0.5f, ay = ky - s / 2.0f + 0.5f;
+                gx = ax / ((float)p.w * s - s / 2.0f - 0.5f) * 2.0f - 1.0f;
+                gy = ay / ((float)p.h * s - s / 2.0f - 0.5f) * 2.0f - 1.0f;
+            }
+            const float ix = ((gx + 1.0f) / 2.0f) * (float)(p.w - 1);
+            const float iy = ((gy + 1.0f) / 2.0f) * (float)(p.h - 1);
+            const float fx0 = floorf(ix), fy0 = floorf(iy);
+            const float fx1 = fx0 + 1.0f, fy1 = fy0 + 1.0f;
+            w_nw[i] = (fx1 - ix) * (fy1 - iy);
+            w_ne[i] = (ix - fx0) * (fy1 - iy);
+            w_sw[i] = (fx1 - ix) * (iy - fy0);
+            w_se[i] = (ix - fx0) * (iy - fy0);
+            const bool finite = (ix > -2.0f) && (ix < (float)p.w + 1.0f) && (iy > -2.0f) && (iy < (float)p.h + 1.0f);
+            const int x0 = finite ? (int)fx0 : -8, y0 = finite ? (int)fy0 : -8;
+            const int x1 = x0 + 1, y1 = y0 + 1;
+            const bool in_x0 = x0 >= 0 && x0 < p.w, in_x1 = x1 >= 0 && x1 < p.w;
+            const bool in_y0 = y0 >= 0 && y0 < p.h, in_y1 = y1 >= 0 && y1 < p.h;
+            taps[i] = (in_x0 && in_y0 ? 1u : 0u) | (in_x1 && in_y0 ? 2u : 0u) | (in_x0 && in_y1 ? 4u : 0u) | (in_x1 && in_y1 ? 8u : 0u);
+            o_nw[i] = y0 * p.w + x0;
+            KB_ASSERT(!(taps[i] & 1u) || (o_nw[i] >= 0 && o_nw[i] < hw));
+            KB_ASSERT(!(taps[i] & 8u) || (o_nw[i] + p.w + 1 >= 0 && o_nw[i] + p.w + 1 < hw));
+        }
+    }
+    float val[OP_KP][OP_C];
+#pragma unroll
+    for (int stage = 0; stage < OP_STAGES; ++stage) {
+        if (n > 0) {
+            uint32_t ok = 0;
+            while (!ok) {
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\t"
+                    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                    "selp.u32 %0, 1, 0, p;\n\t}"
+                    : "=r"(ok) : "r"(bar0 + 8u * (stage & 1)), "r"((uint32_t)((stage >> 1) & 1)) : "memory");
+            }
+        }
+        const float* buf = planes + (size_t)(stage & 1) * OP_SC * hw;
+#pragma unroll
+        for (int i = 0; i < OP_KP; ++i) {
+#pragma unroll
+            for (int c = 0; c < OP_SC; ++c) {
+                const float* m = buf + c * hw;
+                const float nw = (taps[i] & 1u) ? m[o_nw[i]] : 0.0f;
+                const float ne = (taps[i] & 2u) ? m[o_nw[i] + 1] : 0.0f;
+                const float sw = (taps[i] & 4u) ? m[o_nw[i] + p.w] : 0.0f;
+                const float se = (taps[i] & 8u) ? m[o_nw[i] + p.w + 1] : 0.0f;
+                val[i][stage * OP_SC + c] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(nw, w_nw[i]), __fmul_rn(ne, w_ne[i])),
+                                                                 __fmul_rn(sw, w_sw[i])), __fmul_rn(se, w_se[i]));
+            }
+        }
+        if (stage + 2 < OP_STAGES && n > 0) {
+            __syncthreads();                                        // everyone is done with this buffer
+            if (threadIdx.x == 0) issue(stage + 2);
+        }
+    }
+    // rows: float32 piece, operand halves, partial |row|^2; rows beyond the count get zero operands (as prep_kernel writes them)
+    const int nparts = q.Dp / OP_C;
+#pragma unroll
+    for (int i = 0; i < OP_KP; ++i) {
+        const int k = threadIdx.x + i * PL_NT;
+        if (k >= p.n_max) continue;
+        const size_t row = (size_t)bs * p.n_max + k;
+        unsigned short* srow = (side ? q.S[1] : q.S[0]) + row * (2 * (size_t)q.Dp) + c0;
+        if (k < n) {
+            float* o = p.out + ((size_t)b * p.n_max + k) * p.C + c0;
+            *reinterpret_cast<float4*>(o) = make_float4(val[i][0], val[i][1], val[i][2], val[i][3]);
+            *reinterpret_cast<float4*>(o + 4) = make_float4(val[i][4], val[i][5], val[i][6], val[i][7]);
+            uint32_t hw2[OP_C / 2], lw2[OP_C / 2];                  // two 16-bit halves per word
+            float ss = 0.0f;
+#pragma unroll
+            for (int e = 0; e < OP_C; e += 2) {
+                unsigned short h0, l0, h1, l1;
+                split16_pair(val[i][e], q.fp16, h0, l0);
+                split16_pair(val[i][e + 1], q.fp16, h1, l1);
+                hw2[e / 2] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+                lw2[e / 2] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+                ss = fmaf(val[i][e], val[i][e], ss);
+                ss = fmaf(val[i][e + 1], val[i][e + 1], ss);
+            }
+            *reinterpret_cast<uint4*>(srow) = make_uint4(hw2[0], hw2[1], hw2[2], hw2[3]);
+            *reinterpret_cast<uint4*>(srow + q.Dp) = make_uint4(lw2[0], lw2[1], lw2[2], lw2[3]);
+            (side ? q.part[1] : q.part[0])[row * nparts + blockIdx.x] = ss;
+        } else {
+            *reinterpret_cast<uint4*>(srow) = make_uint4(0u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(srow + q.Dp) = make_uint4(0u, 0u, 0u, 0u);
+        }
+    }
+}
+
 // L2 normalisation of the sampled rows in place (lightglue.py:38-40: x / max(||x||_2, 1e-12)), one warp per row, with
 // the summation order of sample_kernel's fused norm (lanes stride over the channels, xor-shuffle tree), so that the
 // plane-staged sampler + this kernel give the same bits as the gather kernel with normalize = 1.
@@ -260,6 +431,41 @@ extern "C" int kb_sample_desc(const float* desc, int B, int C, int h, int w, con
     }
     dim3 grid((n_max * 32 + NT - 1) / NT, B);
     sample_kernel<<<grid, NT, 0, (cudaStream_t)stream>>>(p);
+    KB_LAUNCH_CHECK();
+    return KB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused entry: kb_sample_desc(normalize = 0) for the 2 * pairs maps of a batch of pairs (maps [0, pairs) are image 0,
+// maps [pairs, 2 pairs) image 1) that ALSO writes the operand rows of the kb_match_mnn(algo 1) call that follows on
+// (out[0 : pairs], out[pairs : 2 pairs]) into that call's workspace; the match call then passes phases 6 | 8.
+extern "C" int kb_sample_desc_operands_supported(int C, int h, int w, int n_max) {
+    const size_t plane_bytes = (size_t)h * w * 4;
+    return C > 0 && C % 64 == 0 && C <= 256 && n_max > 0 && n_max <= OP_KP * PL_NT && (plane_bytes % 16) == 0 &&
+           plane_bytes * PL_C <= 110 * 1024 && (size_t)n_max * 16 > (size_t)h * w;
+}
+
+extern "C" int kb_sample_desc_operands(const float* desc, int pairs, int C, int h, int w, const float* pts, int pts_stride,
+                                       const int* count, int n_max, int coord_mode, int s, float* out, void* match_ws,
+                                       size_t match_ws_bytes, kb_stream_t stream) {
+    if (!desc || !pts || !out || !match_ws || pairs <= 0 || C <= 0 || h <= 0 || w <= 0 || n_max <= 0 || pts_stride < 2)
+        return KB_ERR_BAD_ARG;
+    if (coord_mode != 0 && coord_mode != 1) return KB_ERR_BAD_ARG;
+    if (!kb_sample_desc_operands_supported(C, h, w, n_max) || 2 * pairs > 65535) return KB_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(desc) & 15u) || (reinterpret_cast<uintptr_t>(out) & 15u)) return KB_ERR_UNSUPPORTED;
+    KbOperandSinks sinks;
+    const int rc = kb_match_tc_operand_sinks(match_ws, match_ws_bytes, pairs, n_max, n_max, C, &sinks);
+    if (rc != KB_OK) return rc;
+    if (sinks.Dp != C) return KB_ERR_UNSUPPORTED;
+    OperandParams q;
+    q.s.desc = desc; q.s.pts = pts; q.s.count = count; q.s.out = out;
+    q.s.B = 2 * pairs; q.s.C = C; q.s.h = h; q.s.w = w; q.s.n_max = n_max; q.s.stride = pts_stride;
+    q.s.normalize = 0; q.s.coord_mode = coord_mode; q.s.s = s;
+    q.S[0] = sinks.S[0]; q.S[1] = sinks.S[1]; q.part[0] = sinks.part[0]; q.part[1] = sinks.part[1];
+    q.pairs = pairs; q.Dp = sinks.Dp; q.fp16 = sinks.fp16;
+    const size_t smem = (size_t)h * w * 4 * PL_C;
+    KB_CUDA_TRY(cudaFuncSetAttribute(sample_planes_operands_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sample_planes_operands_kernel<<<dim3(C / OP_C, 2 * pairs), PL_NT, smem, (cudaStream_t)stream>>>(q);
     KB_LAUNCH_CHECK();
     return KB_OK;
 }

@@ -322,6 +322,61 @@ def match_batched(d0: torch.Tensor, d1: torch.Tensor, n0: torch.Tensor | None = 
     return pairs, dist, count
 
 
+def sample_match_batched(desc: torch.Tensor, pts: torch.Tensor, count: torch.Tensor | None, pairs: int,
+                         max_distance: float = math.inf, cross_check: bool = True, algo: int = -1, want_dist: bool = True,
+                         fused: bool | None = None, state=None, part: str | None = None):
+    """``sample_batched`` for the 2 * pairs maps of a batch of image pairs (first ``pairs`` maps = image 0) followed by
+    ``match_batched(d[:pairs], d[pairs:], count[:pairs], count[pairs:])`` -- what brute_force_matcher does per pair
+    (utils/matcher.py:221-234).  Where the library supports it (low-resolution maps sampled densely, C a multiple of 64 up
+    to 256, at most 1024 keypoints per map) the sampler writes the tensor-core matcher's operand rows itself
+    (kb_sample_desc_operands) and the matcher skips its preparation pass; otherwise the two calls are made as they are.
+    ``fused=True`` asks for the fused form (an error where unsupported); the default is the two calls, which measured
+    faster on B200.  -> (d [2P,n,C], pairs, dist, count).
+    ``state`` / ``part`` are a measurement hook (bench.py, fused form only): ``state=[]`` receives the buffers of a full
+    call; a later call with the same ``state`` and ``part`` in {'sample', 'finish', 'search', 'tail'} re-runs that part."""
+    _require_cuda(desc, 'desc')
+    _require_cuda(pts, 'pts')
+    d = _f32(desc)
+    p = _f32(pts)
+    b, c, h, w = d.shape
+    n = p.shape[1] if p.dim() == 3 else 0
+    P = int(pairs)
+    ok = (p.dim() == 3 and b == 2 * P and p.shape[0] == b and p.shape[2] >= 2 and n > 0 and algo in (-1, 1)
+          and bool(lib.kb_sample_desc_operands_supported(c, h, w, n)))
+    if fused is True and not ok:
+        raise _lib.KbError('kb_sample_desc_operands: unsupported shape')
+    if not ok or not fused:                 # (measured slower than the two calls on B200, DESIGN.md section 5: opt-in)
+        dd = sample_batched(desc, pts, count)
+        cnt = _i32(count)
+        pr, dist, cm = match_batched(dd[:P], dd[P:], None if cnt is None else cnt[:P], None if cnt is None else cnt[P:],
+                                     max_distance, cross_check, algo=algo, want_dist=want_dist)
+        return dd, pr, dist, cm
+    cnt = _i32(count)
+    if state:
+        out, mpairs, dist, mcount, ws = state
+    else:
+        out = _out(b, n, c, dtype=torch.float32, device=d.device)
+        ws = _ws(lib.kb_match_workspace_bytes(P, n, n, c, 1), d.device)
+        mpairs = _out(P, n, 2, dtype=torch.int32, device=d.device)
+        dist = _out(P, n, dtype=torch.float64, device=d.device) if want_dist else None
+        mcount = _out(P, dtype=torch.int32, device=d.device)
+        if state is not None:
+            state.extend([out, mpairs, dist, mcount, ws])
+    c0 = None if cnt is None else cnt[:P]
+    c1 = None if cnt is None else cnt[P:]
+    phases = {None: 6 | 8, 'finish': 8, 'search': 2, 'tail': 4}.get(part)
+    with torch.cuda.device(d.device):
+        if part in (None, 'sample'):
+            check(lib.kb_sample_desc_operands(d.data_ptr(), P, c, h, w, p.data_ptr(), p.shape[2], _ptr(cnt), n, 0, 8,
+                                              out.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), 'kb_sample_desc_operands')
+        if phases is not None:
+            check(lib.kb_match_mnn_phases(out[:P].data_ptr(), out[P:].data_ptr(), _ptr(c0), _ptr(c1), P, n, n, c,
+                                          float(max_distance), int(bool(cross_check)), 1, mpairs.data_ptr(), _ptr(dist),
+                                          mcount.data_ptr(), ws.data_ptr(), ws.numel(), phases, _stream()), 'kb_match_mnn')
+    _count(1 + 8 if part is None else 1)        # fused sampler; finish, search, resolve, rescan, gate, pairs (+ the zeroing memset)
+    return out, mpairs, dist, mcount
+
+
 def _knob(k: int) -> int:
     v = lib.kb_debug_knob(k, 0)
     lib.kb_debug_knob(k, v)

@@ -43,7 +43,10 @@ def _extract_match(batch, cfg, algo, covisible_only, timer) -> dict:
         t('sample')
         d = ops.sample_batched(batch.desc, pts, n_pts)        # utils/matcher.py:221-226
         t('match')
-        # the reference returns matched rows only (utils/matcher.py:227-233): no distances are requested
+        # the reference returns matched rows only (utils/matcher.py:227-233): no distances are requested.
+        # (ops.sample_match_batched(fused=True) is the form in which the sampler writes the matcher's operand rows itself:
+        # identical pairs, measured SLOWER on B200 -- 222 + 12 us against 157 + 53 us at cfg2, DESIGN.md section 5 -- so the
+        # two calls stay the default)
         pairs, _, n_m = ops.match_batched(d[:P], d[P:], n_pts[:P], n_pts[P:], cfg.max_distance, cfg.cross_check,
                                           algo=algo, want_dist=False)
         out.update(desc=d, matches=pairs, n_matches=n_m)

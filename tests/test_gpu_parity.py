@@ -661,6 +661,49 @@ def test_sampling_plane_staged_path_cfg2_shape():
     assert float(out[1, 873:].abs().max()) == 0.0          # rows beyond the count stay untouched (zero)
 
 
+@pytest.mark.parametrize('pairs,c,h,w,n,seed', [(3, 256, 60, 80, 1000, 5), (2, 64, 30, 40, 517, 6), (1, 128, 16, 24, 1024, 7),
+                                                (5, 192, 15, 20, 300, 8)])
+def test_fused_sampling_and_operand_preparation_equals_the_two_calls(pairs, c, h, w, n, seed):
+    """kb_sample_desc_operands + kb_match_mnn(phases 6 | 8): the sampler writes the matcher's operand rows (fp16 halves
+    for C > 64, bf16 for C = 64) and partial norms itself.  Same float32 rows bit for bit, same pairs and distances
+    as sampling and matching separately, and the pairs equal the float64 oracle on the sampled rows (ragged counts
+    incl. an empty map, duplicated keypoints = exact ties)."""
+    gen = torch.Generator().manual_seed(seed)
+    d = torch.randn(2 * pairs, c, h, w, generator=gen)
+    pt = torch.rand(2 * pairs, n, 3, generator=gen)
+    pt[0, 10:20, :2] = pt[0, 0:10, :2]                     # duplicated keypoints: identical descriptor rows
+    pt[pairs, :4, :2] = torch.tensor([[0.0, 0.0], [1.0, 1.0], [-0.01, 0.5], [0.5, 1.02]])
+    cnt = torch.randint(n // 2, n + 1, (2 * pairs,), generator=gen).to(torch.int32)
+    cnt[0] = n
+    if pairs > 2:
+        cnt[pairs + 1] = 0                                  # an empty image 1
+    dd, pp, nn = d.to(DEV), pt.to(DEV), cnt.to(DEV)
+    for md in (math.inf, 0.9 * math.sqrt(2.0 * c)):
+        o = ops()
+        f_d, f_pairs, f_dist, f_cnt = o.sample_match_batched(dd, pp, nn, pairs, md, True, want_dist=True, fused=True)
+        u_d, u_pairs, u_dist, u_cnt = o.sample_match_batched(dd, pp, nn, pairs, md, True, want_dist=True, fused=False)
+        assert torch.equal(f_cnt, u_cnt)
+        for b in range(2 * pairs):
+            k = int(cnt[b])
+            assert torch.equal(f_d[b, :k], u_d[b, :k]), b
+        for b in range(pairs):
+            k = int(f_cnt[b])
+            assert torch.equal(f_pairs[b, :k], u_pairs[b, :k]), b
+            assert torch.equal(f_dist[b, :k], u_dist[b, :k]), b
+            n0, n1 = int(cnt[b]), int(cnt[pairs + b])
+            if n0 and n1:
+                _exact_pairs_or_near_tie(f_pairs[b, :k].cpu().numpy().astype(np.int64), u_d[b, :n0].cpu().numpy(),
+                                         u_d[pairs + b, :n1].cpu().numpy(), md, True)
+            else:
+                assert k == 0
+        # without distances (what the pipeline asks for)
+        g_d, g_pairs, _, g_cnt = o.sample_match_batched(dd, pp, nn, pairs, md, True, want_dist=False, fused=True)
+        assert torch.equal(g_cnt, f_cnt)
+        for b in range(pairs):
+            k = int(f_cnt[b])
+            assert torch.equal(g_pairs[b, :k], f_pairs[b, :k]), b
+
+
 # ------------------------------------------------------------------------------------------------ full-size configs
 
 @pytest.mark.parametrize('kind,h,w,r,top_k,want_path', [
