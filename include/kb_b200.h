@@ -56,6 +56,7 @@ KB_API const char* kb_error_string(int code);
 #define KB_KNOB_TC_BF16X3 6   /* operand split of the tensor-core Gram: 0 = automatic (fp16 halves and two products,
                                * (hi_x + lo_x).hi_y, for D > 64; bf16 halves and three products hi.hi + lo.hi + hi.lo for
                                * D <= 64), 1 = bf16 x 3 always, 2 = fp16 x 2 always; same pairs */
+#define KB_KNOB_SAMPLE_4CH 7  /* 1 = kb_sample_desc stages low-resolution maps four channels per CTA (the older kernel; same bits) */
 #define KB_KNOB_SPARSE_PROF 5 /* 1 = the per-map resolve kernel of kb_detect records clock64 at its phase boundaries */
 KB_API int kb_debug_knob(int knob, int value);
 /* Diagnostics: the 16 values map 0's CTA of the last kb_detect recorded under KB_KNOB_SPARSE_PROF (synchronises):

@@ -18,6 +18,7 @@ KB_ERR_BAD_ARG = -1
 KB_ERR_WORKSPACE = -2
 KB_ERR_UNSUPPORTED = -3
 KB_KNOB_TC_CLUSTER, KB_KNOB_TC_DEBUG, KB_KNOB_REP_NO_SORT, KB_KNOB_TC_ONE_PASS, KB_KNOB_SPARSE_PROF, KB_KNOB_TC_BF16X3 = 1, 2, 3, 4, 5, 6
+KB_KNOB_SAMPLE_4CH = 7
 
 # name -> (restype, argtypes); mirrors include/kb_b200.h one to one
 PROTOTYPES = {

@@ -18,7 +18,7 @@ extern "C" const char* kb_error_string(int code) {
 int kb_knobs[8] = {0, 1, 0, 0, 0, 0, 0, 0};
 
 extern "C" int kb_debug_knob(int knob, int value) {
-    if (knob < 1 || knob > 6) return KB_ERR_BAD_ARG;
+    if (knob < 1 || knob > 7) return KB_ERR_BAD_ARG;
     const int prev = kb_knobs[knob];
     kb_knobs[knob] = value;
     return prev;

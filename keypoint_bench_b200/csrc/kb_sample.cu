@@ -213,15 +213,16 @@ __global__ void __launch_bounds__(PL_NT, 2) sample_planes_kernel(SampleParams p)
 }
 
 // ------------------------------------------------------------------------------------------------
-// Plane-staged sampling FUSED with the matcher's operand preparation (kb_match_tc.cu: prep_kernel): a CTA owns
+// Plane-staged sampling, eight channels per CTA -- the default for low-resolution maps (OPERANDS = false) -- and the same
+// FUSED with the matcher's operand preparation (OPERANDS = true; kb_match_tc.cu: prep_kernel): a CTA owns
 // EIGHT channels of one map -- four stages of two planes through two shared-memory buffers -- and every thread keeps
 // the eight samples of its (up to four) keypoints in registers, so that it can write, per keypoint, the 32-byte piece
 // of the float32 [n,C] row (a whole sector; the certification stages of the matcher read it), the 16-byte pieces of the
 // hi and lo halves of the matcher's operand row, and the partial |row|^2 of the eight components.  The float32 rows no
 // longer travel HBM -> SM -> HBM a second time just to be split.  Same sampling arithmetic as sample_kernel.
 constexpr int OP_C = 8;           // channels per CTA
-constexpr int OP_SC = 2;          // planes per stage: four stages through two buffers, the copy of stage s+2 (issued as soon
-constexpr int OP_STAGES = OP_C / OP_SC;   // as stage s has been read) overlaps the interpolation of stage s+1
+// planes per stage (SC) and buffers (NBUF): OP_C / SC stages through NBUF buffers of SC planes, the copy of stage s+NBUF is
+// issued as soon as stage s has been read and overlaps the interpolation of the stages in between
 constexpr int OP_KP = 4;          // keypoints per thread: n_max <= OP_KP * PL_NT
 
 struct OperandParams {
@@ -243,10 +244,12 @@ __device__ __forceinline__ void split16_pair(float f, int fp16, unsigned short& 
     }
 }
 
+template <bool OPERANDS, int OP_SC, int NBUF>
 __global__ void __launch_bounds__(PL_NT, 2) sample_planes_operands_kernel(OperandParams q) {
+    constexpr int OP_STAGES = OP_C / OP_SC;
     const SampleParams& p = q.s;
     extern __shared__ __align__(128) unsigned char pl_smem[];
-    __shared__ __align__(8) unsigned long long pl_bar[2];
+    __shared__ __align__(8) unsigned long long pl_bar[NBUF];
     float* planes = reinterpret_cast<float*>(pl_smem);
     const int b = blockIdx.y, c0 = blockIdx.x * OP_C;
     const int hw = p.h * p.w;
@@ -255,24 +258,24 @@ __global__ void __launch_bounds__(PL_NT, 2) sample_planes_operands_kernel(Operan
     const float* src = p.desc + ((size_t)b * p.C + c0) * hw;
     const uint32_t bytes = (uint32_t)OP_SC * hw * 4u;                // one stage (host: 16-byte aligned, a multiple of 16)
     const uint32_t bar0 = smem_addr_u32(&pl_bar[0]);
-    auto issue = [&](int stage) {                                   // thread 0: planes c0 + OP_SC*stage .. into buffer stage & 1
-        const uint32_t bar = bar0 + 8u * (stage & 1);
+    auto issue = [&](int stage) {                                   // thread 0: planes c0 + OP_SC*stage .. into buffer stage % NBUF
+        const uint32_t bar = bar0 + 8u * (stage % NBUF);
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
         uint32_t done = 0;
         while (done < bytes) {
             const uint32_t piece = min(bytes - done, 32768u);
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(smem_addr_u32(pl_smem + (size_t)(stage & 1) * bytes + done)),
+                         ::"r"(smem_addr_u32(pl_smem + (size_t)(stage % NBUF) * bytes + done)),
                            "l"(reinterpret_cast<const char*>(src) + (size_t)stage * bytes + done), "r"(piece), "r"(bar) : "memory");
             done += piece;
         }
     };
     if (n > 0 && threadIdx.x == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0) : "memory");
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8u) : "memory");
+#pragma unroll
+        for (int i = 0; i < NBUF; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8u * i) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        issue(0);
-        issue(1);
+#pragma unroll
+        for (int i = 0; i < NBUF && i < OP_STAGES; ++i) issue(i);
     }
     // this thread's keypoints (k = threadIdx.x + i * PL_NT): taps and weights, while the first copy is in flight
     float w_nw[OP_KP], w_ne[OP_KP], w_sw[OP_KP], w_se[OP_KP];
@@ -325,10 +328,10 @@ __global__ void __launch_bounds__(PL_NT, 2) sample_planes_operands_kernel(Operan
                     "{\n\t.reg .pred p;\n\t"
                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
                     "selp.u32 %0, 1, 0, p;\n\t}"
-                    : "=r"(ok) : "r"(bar0 + 8u * (stage & 1)), "r"((uint32_t)((stage >> 1) & 1)) : "memory");
+                    : "=r"(ok) : "r"(bar0 + 8u * (stage % NBUF)), "r"((uint32_t)((stage / NBUF) & 1)) : "memory");
             }
         }
-        const float* buf = planes + (size_t)(stage & 1) * OP_SC * hw;
+        const float* buf = planes + (size_t)(stage % NBUF) * OP_SC * hw;
 #pragma unroll
         for (int i = 0; i < OP_KP; ++i) {
 #pragma unroll
@@ -342,9 +345,9 @@ __global__ void __launch_bounds__(PL_NT, 2) sample_planes_operands_kernel(Operan
                                                                  __fmul_rn(sw, w_sw[i])), __fmul_rn(se, w_se[i]));
             }
         }
-        if (stage + 2 < OP_STAGES && n > 0) {
+        if (stage + NBUF < OP_STAGES && n > 0) {
             __syncthreads();                                        // everyone is done with this buffer
-            if (threadIdx.x == 0) issue(stage + 2);
+            if (threadIdx.x == 0) issue(stage + NBUF);
         }
     }
     // rows: float32 piece, operand halves, partial |row|^2; rows beyond the count get zero operands (as prep_kernel writes them)
@@ -354,11 +357,14 @@ __global__ void __launch_bounds__(PL_NT, 2) sample_planes_operands_kernel(Operan
         const int k = threadIdx.x + i * PL_NT;
         if (k >= p.n_max) continue;
         const size_t row = (size_t)bs * p.n_max + k;
-        unsigned short* srow = (side ? q.S[1] : q.S[0]) + row * (2 * (size_t)q.Dp) + c0;
         if (k < n) {
             float* o = p.out + ((size_t)b * p.n_max + k) * p.C + c0;
             *reinterpret_cast<float4*>(o) = make_float4(val[i][0], val[i][1], val[i][2], val[i][3]);
             *reinterpret_cast<float4*>(o + 4) = make_float4(val[i][4], val[i][5], val[i][6], val[i][7]);
+        }
+        if (!OPERANDS) continue;
+        unsigned short* srow = (side ? q.S[1] : q.S[0]) + row * (2 * (size_t)q.Dp) + c0;
+        if (k < n) {
             uint32_t hw2[OP_C / 2], lw2[OP_C / 2];                  // two 16-bit halves per word
             float ss = 0.0f;
 #pragma unroll
@@ -416,6 +422,25 @@ extern "C" int kb_sample_desc(const float* desc, int B, int C, int h, int w, con
     p.normalize = normalize; p.coord_mode = coord_mode; p.s = s;
     // low-resolution, densely sampled maps: stage whole planes (see sample_planes_kernel)
     const size_t plane_bytes = (size_t)h * w * 4;
+    // ... eight channels per CTA through double-buffered two-plane stages with 32-byte output pieces where the shapes
+    // allow it (138 us against 158 us for the four-channel kernel at cfg2; kb_debug_knob(KB_KNOB_SAMPLE_4CH, 1) forces
+    // the four-channel kernel; identical bits)
+    if (!kb_knobs[KB_KNOB_SAMPLE_4CH] && C % OP_C == 0 && n_max <= OP_KP * PL_NT && (plane_bytes % 16) == 0 &&
+        plane_bytes * PL_C <= 110 * 1024 && (size_t)n_max * 16 > (size_t)h * w &&
+        ((reinterpret_cast<uintptr_t>(desc) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0) {
+        OperandParams q;
+        q.s = p; q.s.normalize = 0;           // the staged kernels write raw samples; rows are normalised afterwards
+        q.S[0] = q.S[1] = nullptr; q.part[0] = q.part[1] = nullptr; q.pairs = B; q.Dp = 0; q.fp16 = 0;
+        const size_t smem = plane_bytes * PL_C;
+        KB_CUDA_TRY(cudaFuncSetAttribute(sample_planes_operands_kernel<false, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        sample_planes_operands_kernel<false, 2, 2><<<dim3(C / OP_C, B), PL_NT, smem, (cudaStream_t)stream>>>(q);
+        KB_LAUNCH_CHECK();
+        if (normalize) {
+            normalize_rows_kernel<<<dim3((n_max + 7) / 8, B), 256, 0, (cudaStream_t)stream>>>(out, count, n_max, C);
+            KB_LAUNCH_CHECK();
+        }
+        return KB_OK;
+    }
     if (plane_bytes * PL_C + (size_t)n_max * 8 <= 110 * 1024 && (size_t)n_max * 16 > (size_t)h * w) {
         const size_t smem = plane_bytes * PL_C + (size_t)n_max * 8;
         KB_CUDA_TRY(cudaFuncSetAttribute(sample_planes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -464,8 +489,8 @@ extern "C" int kb_sample_desc_operands(const float* desc, int pairs, int C, int 
     q.S[0] = sinks.S[0]; q.S[1] = sinks.S[1]; q.part[0] = sinks.part[0]; q.part[1] = sinks.part[1];
     q.pairs = pairs; q.Dp = sinks.Dp; q.fp16 = sinks.fp16;
     const size_t smem = (size_t)h * w * 4 * PL_C;
-    KB_CUDA_TRY(cudaFuncSetAttribute(sample_planes_operands_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    sample_planes_operands_kernel<<<dim3(C / OP_C, 2 * pairs), PL_NT, smem, (cudaStream_t)stream>>>(q);
+    KB_CUDA_TRY(cudaFuncSetAttribute(sample_planes_operands_kernel<true, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sample_planes_operands_kernel<true, 2, 2><<<dim3(C / OP_C, 2 * pairs), PL_NT, smem, (cudaStream_t)stream>>>(q);
     KB_LAUNCH_CHECK();
     return KB_OK;
 }

@@ -26,15 +26,15 @@ keep = ['dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__dram_throughput.a
         'smsp__inst_executed.sum', 'smsp__issue_active.avg.pct_of_peak_sustained_active']
 units = rows[1]
 seen, text, traffic = set(), [], {}
-key_of = {'round1_kernel': 'detect.round1', 'sample_planes_kernel': 'sample', 'nn_top2_kernel': 'match.search',
+key_of = {'round1_packed_kernel': 'detect.round1', 'round1_kernel': 'detect.round1', 'sample_planes_kernel': 'sample', 'nn_top2_kernel': 'match.search',
           'prep_kernel': 'match.prep', 'sparse_kernel': 'detect.resolve'}
 for r in rows[2:]:
     rec = dict(zip(hdr, r))
     name = rec.get('Kernel Name', '')
     short = next((k for k in key_of if k in name), None)
-    if short is None or short in seen:
+    if short is None or key_of[short] in seen:
         continue
-    seen.add(short)
+    seen.add(key_of[short])
     text.append('---')
     text.append(f'  Kernel Name {name}')
     for k in keep:

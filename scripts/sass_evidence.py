@@ -8,7 +8,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, 'keypoint_bench_b200', 'csrc', 'libkb_b200.so')
-PATTERNS = ['UTCHMMA', 'UTCHMMA.2CTA', 'LDTM', 'UTMALDG', 'UBLKCP', 'LDGSTS', 'SYNCS', 'UTCBAR', 'FMNMX3', 'REDUX', 'ATOMS', 'DFMA']
+PATTERNS = ['UTCHMMA', 'UTCHMMA.2CTA', 'LDTM', 'UTMALDG', 'UBLKCP', 'LDGSTS', 'SYNCS', 'UTCBAR', 'FMNMX3', 'HMNMX2', 'VHMNMX', 'REDUX', 'ATOMS', 'DFMA']
 
 
 def main():

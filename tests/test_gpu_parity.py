@@ -659,6 +659,13 @@ def test_sampling_plane_staged_path_cfg2_shape():
         ref = ref_ops.sample_brute_force(d[b].numpy(), p[b, :n].numpy())
         assert np.allclose(out[b, :n].cpu().numpy(), ref, rtol=1e-5, atol=1e-5)
     assert float(out[1, 873:].abs().max()) == 0.0          # rows beyond the count stay untouched (zero)
+    # the eight-channel staged kernel (the default here) and the four-channel one give the same bits, also normalised
+    from keypoint_bench_b200 import _lib
+    for norm in (False, True):
+        a = ops().sample_batched(d.to(DEV), p.to(DEV), cnt.to(DEV), normalize=norm)
+        with ops().debug_knob(_lib.KB_KNOB_SAMPLE_4CH, 1):
+            b4 = ops().sample_batched(d.to(DEV), p.to(DEV), cnt.to(DEV), normalize=norm)
+        assert torch.equal(a, b4), norm
 
 
 @pytest.mark.parametrize('pairs,c,h,w,n,seed', [(3, 256, 60, 80, 1000, 5), (2, 64, 30, 40, 517, 6), (1, 128, 16, 24, 1024, 7),
