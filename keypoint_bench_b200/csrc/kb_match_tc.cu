@@ -239,7 +239,7 @@ struct PrepParams {
     int B, n_max, D, Dp, cs;
 };
 
-constexpr int PREP_ROWS = 4;          // rows per warp: independent 16-byte loads in flight
+constexpr int PREP_ROWS = 2;          // rows per warp in flight (measured at cfg2: 8 rows 72 us, 4 rows 61 us, 2 rows 53 us, 1 row 51 us)
 
 // returns |row|^2 (all lanes)
 __device__ __forceinline__ float prep_finish_row(const PrepParams& p, int b, int row, float ss, int lane) {
@@ -296,7 +296,9 @@ __global__ void __launch_bounds__(256) prep_kernel(PrepPair pp) {
         // fast path: four valid rows, 4 components per lane and step
         const float* x = p.d + ((size_t)b * p.n_max + row0) * p.D;
         unsigned short* out = p.S + ((size_t)b * p.n_max + row0) * (2 * p.Dp);
-        float ss[PREP_ROWS] = {0.f, 0.f, 0.f, 0.f};
+        float ss[PREP_ROWS];
+#pragma unroll
+        for (int r = 0; r < PREP_ROWS; ++r) ss[r] = 0.f;
         for (int k = 4 * lane; k < p.Dp; k += 128) {
             float4 v[PREP_ROWS];
 #pragma unroll
@@ -1504,10 +1506,10 @@ int kb_match_tc_run(const float* d0, const float* d1, const int* n0, const int* 
         q1 = q0;
         q1.d = d1; q1.cnt = n1; q1.S = S1; q1.c = c1; q1.norm2 = norm2_1; q1.maxn = maxn1;
         q1.n_max = m_max; q1.cs = L.cs1;
-        // one wave of CTAs: every warp walks over groups of PREP_ROWS rows
+        // a few waves of CTAs: every warp walks over groups of PREP_ROWS rows
         const int cs_max = L.cs0 > L.cs1 ? L.cs0 : L.cs1;
         int ctas = (cs_max / PREP_ROWS + 7) / 8;                     // CTAs that give every warp one group
-        const int wave = (sms * 8 + 2 * B - 1) / (2 * B);               // CTAs per (batch, side) in one resident wave
+        const int wave = 4 * ((sms * 8 + 2 * B - 1) / (2 * B));         // CTAs per (batch, side): four resident waves (49.9 us against 52.8 us with one)
         if (ctas > wave) ctas = wave;
         if (ctas < 1) ctas = 1;
         if (phases & 1) {
