@@ -277,6 +277,7 @@ __global__ void __launch_bounds__(PL_NT, 2) sample_planes_operands_kernel(Operan
 #pragma unroll
         for (int i = 0; i < NBUF && i < OP_STAGES; ++i) issue(i);
     }
+    __syncthreads();                                                // nobody polls a barrier before it is initialised
     // this thread's keypoints (k = threadIdx.x + i * PL_NT): taps and weights, while the first copy is in flight
     float w_nw[OP_KP], w_ne[OP_KP], w_sw[OP_KP], w_se[OP_KP];
     int o_nw[OP_KP];

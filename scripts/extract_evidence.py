@@ -26,7 +26,8 @@ keep = ['dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__dram_throughput.a
         'smsp__inst_executed.sum', 'smsp__issue_active.avg.pct_of_peak_sustained_active']
 units = rows[1]
 seen, text, traffic = set(), [], {}
-key_of = {'round1_packed_kernel': 'detect.round1', 'round1_kernel': 'detect.round1', 'sample_planes_kernel': 'sample', 'nn_top2_kernel': 'match.search',
+key_of = {'round1_packed_kernel': 'detect.round1', 'round1_kernel': 'detect.round1', 'sample_planes_operands_kernel': 'sample',
+          'sample_planes_kernel': 'sample', 'nn_top2_kernel': 'match.search',
           'prep_kernel': 'match.prep', 'sparse_kernel': 'detect.resolve'}
 for r in rows[2:]:
     rec = dict(zip(hdr, r))

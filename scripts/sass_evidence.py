@@ -27,7 +27,7 @@ def main():
             continue
         if cur is None:
             continue
-        m = re.match(r'\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\w+\s+)?([A-Z0-9_.]+)', line)
+        m = re.match(r'\s+/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\w+\s+)?([A-Z0-9_.]+)', line)
         if not m:
             continue
         op = m.group(1)
