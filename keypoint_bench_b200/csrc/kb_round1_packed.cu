@@ -220,10 +220,9 @@ __device__ __forceinline__ uint32_t hdilate(const uint32_t (&N)[5]) {
 // maximum unless another pixel of the window shares its packed value AND beats it in fp32 (larger, or equal and
 // earlier in raster order).
 template <int R>
-__device__ __forceinline__ bool tie_verdict(const uint32_t* raw, int VP, uint32_t tie_cols, uint32_t tie_rows, uint32_t qv, int row,
-                                         int x, int h, const float* __restrict__ img, int H, int W) {
+__device__ __forceinline__ bool tie_verdict(const uint32_t* raw, int VP, uint32_t tie_cols, uint32_t tie_rows, uint32_t qv, float v,
+                                         int row, int x, int h, const float* __restrict__ img, int H, int W) {
     const uint16_t* rw16 = reinterpret_cast<const uint16_t*>(raw) + h;
-    const float v = __ldg(img + (size_t)row * W + x);
     // own column
     while (tie_rows) {
         const int dy = __ffs(tie_rows) - 1 - R;
@@ -259,6 +258,10 @@ __device__ __forceinline__ bool is_round1_max(const uint32_t* raw, const uint32_
                                               int fix_next, int o, int row, int x, int h, const float* __restrict__ img, int H, int W) {
     const uint32_t hmask = h ? 0xffff0000u : 0x0000ffffu;
     const uint32_t qv2 = __byte_perm(*own, 0u, h ? 0x3232 : 0x1010);            // the candidate's value in both halves
+    // the candidate's fp32 score, needed only on a 16-bit tie: fetched now (volatile: not sunk into the rare branch) so
+    // that its L2 latency runs under the scan instead of in front of the verdict
+    float v;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(img + (size_t)row * W + x));
     uint32_t mn4[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};    // four independent chains
 #pragma unroll
     for (int d = -R; d <= R; ++d) {
@@ -269,20 +272,27 @@ __device__ __forceinline__ bool is_round1_max(const uint32_t* raw, const uint32_
         if (d > 0 && o + d >= S) a += fix_next;
         mn4[2 + ((d + R) & 1)] = min(mn4[2 + ((d + R) & 1)], (*a ^ qv2) & hmask);
     }
-    const uint32_t mn = min(min(mn4[0], mn4[1]), min(mn4[2], mn4[3]));
-    if (mn != 0u) return true;
-    // a 16-bit tie (rare): which columns / rows, then fp32
+    const uint32_t mn_cols = min(mn4[0], mn4[1]), mn_rows = min(mn4[2], mn4[3]);
+    if (min(mn_cols, mn_rows) != 0u) return true;
+    // a 16-bit tie (rare): which columns of the row buffer / which rows of the own column, then fp32
     const uint32_t qv = qv2 & 0xffffu;
-    const uint16_t* vm16 = reinterpret_cast<const uint16_t*>(vrow) + h;
-    const uint16_t* col16 = reinterpret_cast<const uint16_t*>(raw + PADC + x) + h;
     uint32_t tie_cols = 0u, tie_rows = 0u;
-#pragma unroll 1
-    for (int d = -R; d <= R; ++d) {
-        if (d == 0) continue;
-        if (vm16[2 * d] == qv) tie_cols |= 1u << (d + R);
-        if (col16[2 * (((row + d) & (RING - 1)) * VP)] == qv) tie_rows |= 1u << (d + R);
+    if (mn_cols == 0u) {
+#pragma unroll
+        for (int d = -R; d <= R; ++d)
+            if (d != 0 && ((vrow[d] ^ qv2) & hmask) == 0u) tie_cols |= 1u << (d + R);
     }
-    return tie_verdict<R>(raw, VP, tie_cols, tie_rows, qv, row, x, h, img, H, W);
+    if (mn_rows == 0u) {
+#pragma unroll
+        for (int d = -R; d <= R; ++d) {
+            if (d == 0) continue;
+            const uint32_t* a = own + d * VP;
+            if (d < 0 && o + d < 0) a += fix_prev;
+            if (d > 0 && o + d >= S) a += fix_next;
+            if (((*a ^ qv2) & hmask) == 0u) tie_rows |= 1u << (d + R);
+        }
+    }
+    return tie_verdict<R>(raw, VP, tie_cols, tie_rows, qv, v, row, x, h, img, H, W);
 }
 
 // NTC: threads per CTA as a compile-time constant (0 = blockDim.x): with it the row pitch of the shared arrays is an
