@@ -484,6 +484,8 @@ def run_config(args, name, rank, local_rank, world, device, full):
     out['roofline'] = {
         'kernel': dom, 'bound': 'tensor' if d['bound'] == 'tensor' else 'hbm', 'achieved': d['achieved'], 'peak': d['peak'],
         'unit': d['unit'], 'frac': d['frac'], 'traffic': traffic, 'kernels': kernels,
+        **({'bound_note': 'the largest kernel group of this step is LATENCY-bound (a chain of small launches over KB-sized '
+                          'inputs): its fraction of the HBM peak says nothing about it'} if d['bound'] == 'latency' else {}),
         'note': f'dominant = the kernel group with the largest CUDA-event time when launched alone 5x back to back (every '
                 f'group of the step is timed); achieved = algorithmic bytes, or ONE pass of 2nmD flops per pair, per launch / '
                 f'that time; peaks {pk["source"]}: HBM copy {pk["hbm_gbs"]:.0f} GB/s, bf16 burst {pk["bf16_tflops"]:.0f} TFLOP/s '
