@@ -3,8 +3,10 @@
 // The fp32 round-1 kernels (tiled: kb_sparse_nms.cu, streaming: kb_round1_stream.cu) spend ~50-100 thread-instructions
 // per pixel finding the pixels that win their (2r+1)^2 window (the reference's first fast_nms round,
 // utils/extracter.py:54-70).  Almost all of that work only has to establish "some pixel of the window is larger", for
-// which a MONOTONE 16-bit image of the score is enough: q = fp16(score), round to nearest, so u >= v implies
-// q(u) >= q(v).  This kernel therefore
+// which a MONOTONE 16-bit image of the score is enough: q = fp16(max((score - tau) * qscale, 0)), one FFMA and one
+// round-to-nearest conversion, so u >= v implies q(u) >= q(v); the subtraction spends fp16's 11 bits on the range the
+// candidates live in and qscale (a power of two from tau_kernel: the largest sampled score lands at 2^15) keeps the
+// image inside fp16's range whatever the scale of the scores.  This kernel therefore
 //
 //   * processes TWO maps at once: a CTA owns full-width bands of 8-row chunks of a PAIR of maps; thread t owns columns
 //     4t..4t+3 of both; every value it keeps on chip is a half2 (low half = map 2i, high half = map 2i+1), so each
@@ -339,6 +341,9 @@ __global__ void __launch_bounds__(NTC ? NTC : MAX_NT, (NTC && NTC <= 160) ? 2 : 
         const size_t map_stride4 = ((size_t)H * Wd) >> 2;          // (VEC: Wd % 4 == 0) float4s between the maps of a pair
         const float* __restrict__ img[2] = {p.score + (size_t)bm[0] * H * Wd, p.score + (size_t)bm[1] * H * Wd};
         const float tau[2] = {p.tau[bm[0]], p.tau[bm[1]]};
+        // 16-bit image: fp16(max((score - tau) * qs, 0)) as one FFMA per pixel (monotone in the score: one rounding)
+        const float qs[2] = {p.qscale[bm[0]], p.qscale[bm[1]]};
+        const float qc[2] = {-tau[0] * qs[0], -tau[1] * qs[1]};
         uint64_t* LM[2] = {p.listM + (size_t)bm[0] * LIST_CAP, p.listM + (size_t)bm[1] * LIST_CAP};
         uint64_t* LO[2] = {p.listO + (size_t)bm[0] * LIST_CAP, p.listO + (size_t)bm[1] * LIST_CAP};
 
@@ -352,10 +357,11 @@ __global__ void __launch_bounds__(NTC ? NTC : MAX_NT, (NTC && NTC <= 160) ? 2 : 
             constexpr int o = decltype(O)::value;
             hot4<o>(h0, a, tau[0]);
             hot4<o>(h1, b, tau[1]);
-            // the 16-bit image is taken of score - tau (monotone; pixels at or below tau become 0): fp16 spends its 11
-            // bits on the range the candidates live in, so two pixels of a window rarely share the largest packed value
-            const uint4 q = make_uint4(pack2(a.x - tau[0], b.x - tau[1]), pack2(a.y - tau[0], b.y - tau[1]),
-                                       pack2(a.z - tau[0], b.z - tau[1]), pack2(a.w - tau[0], b.w - tau[1]));
+            // the 16-bit image is taken of (score - tau) * qscale (monotone; pixels at or below tau become 0): fp16 spends
+            // its 11 bits on the range the candidates live in, so two pixels of a window rarely share the largest packed
+            // value, and qscale (tau_kernel: the largest sample at 2^15) keeps it inside fp16's range whatever the scores' scale
+            const uint4 q = make_uint4(pack2(fmaf(a.x, qs[0], qc[0]), fmaf(b.x, qs[1], qc[1])), pack2(fmaf(a.y, qs[0], qc[0]), fmaf(b.y, qs[1], qc[1])),
+                                       pack2(fmaf(a.z, qs[0], qc[0]), fmaf(b.z, qs[1], qc[1])), pack2(fmaf(a.w, qs[0], qc[0]), fmaf(b.w, qs[1], qc[1])));
             neg0 |= __float_as_uint(a.x) | __float_as_uint(a.y) | __float_as_uint(a.z) | __float_as_uint(a.w);
             neg1 |= __float_as_uint(b.x) | __float_as_uint(b.y) | __float_as_uint(b.z) | __float_as_uint(b.w);
             *reinterpret_cast<uint4*>(dst + o * VP) = q;

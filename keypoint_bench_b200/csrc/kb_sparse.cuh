@@ -15,6 +15,7 @@ constexpr int SMEM_CAP = 12288;                   // candidates resolved in shar
 struct SparseParams {
     const float* score;       // [B,H,W]
     float* tau;               // [B]
+    float* qscale;            // [B] scale of the packed kernel's 16-bit score image: fp16((score - tau) * qscale)
     uint64_t* listM;          // [B,LIST_CAP] round-1 maxima above tau
     uint64_t* listO;          // [B,LIST_CAP] uncovered pixels above tau
     int* cntM;                // [B]

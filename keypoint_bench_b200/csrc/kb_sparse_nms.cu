@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(TAU_NT) tau_kernel(SparseParams p) {
     if (b == 0 && threadIdx.x == 0) *p.any_fallback = 0;
     const long long rank = ((long long)p.c_pix * SAMPLES + npx - 1) / npx;
     if (npx <= 4 * SAMPLES || rank >= SAMPLES / 2) {        // small map / dense request: list everything
-        if (threadIdx.x == 0) p.tau[b] = theta;
+        if (threadIdx.x == 0) { p.tau[b] = theta; p.qscale[b] = 1.0f; }
         return;
     }
     const float* img = p.score + (size_t)b * npx;
@@ -74,9 +74,28 @@ __global__ void __launch_bounds__(TAU_NT) tau_kernel(SparseParams p) {
         __syncthreads();
         if (tot >= (int)rank) v = t;
     }
+    // the largest sample (for the packed round-1 kernel's 16-bit image, which must neither overflow nor underflow on
+    // maps whose scores live far from 1: it takes fp16((score - tau) * qscale) with the largest SAMPLE at 2^15, so only
+    // pixels more than twice the largest sample above tau saturate)
+    uint32_t kmax = 0u;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) kmax = max(kmax, keys[i]);
+    kmax = __reduce_max_sync(0xffffffffu, kmax);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = (int)kmax;
+    __syncthreads();
     if (threadIdx.x == 0) {
         const float t = kb::float_from_order_key(v);
-        p.tau[b] = (t > theta) ? t : theta;                 // NaN-safe: falls back to theta
+        const float tau = (t > theta) ? t : theta;          // NaN-safe: falls back to theta
+        p.tau[b] = tau;
+        uint32_t km = 0u;
+#pragma unroll
+        for (int w = 0; w < TAU_NT / 32; ++w) km = max(km, (uint32_t)s_part[w]);
+        const float span = kb::float_from_order_key(km) - tau;
+        // (a power of two: the scaling itself is then exact; NaN / inf / non-positive spans fall back to 1)
+        float sc = 1.0f;
+        if (span > 1e-30f && span < 1e30f) sc = exp2f(15.0f - ceilf(log2f(span)));
+        p.qscale[b] = sc;
     }
 }
 
@@ -966,7 +985,7 @@ bool kb_sparse_supported(int H, int W, int nms_dist, int top_k) { return kb_spar
 
 size_t kb_sparse_workspace_bytes(int B, int H, int W, int nms_dist, int top_k) {
     if (!kb_sparse_plan(H, W, nms_dist, top_k).ok) return 0;
-    return 2 * kb_align_up((size_t)B * kbsparse::LIST_CAP * sizeof(uint64_t), 256) + 7 * kb_align_up((size_t)B * 4, 256) + 1024;
+    return 2 * kb_align_up((size_t)B * kbsparse::LIST_CAP * sizeof(uint64_t), 256) + 8 * kb_align_up((size_t)B * 4, 256) + 1024;
 }
 
 // Runs the sparse path for all B maps.  need_fallback[B] / any_fallback[1] (device) report what is left.
@@ -983,6 +1002,7 @@ int kb_sparse_detect(const float* score, int B, int H, int W, int nms_dist, int 
     p.listM = arena.take<uint64_t>((size_t)B * LIST_CAP);
     p.listO = arena.take<uint64_t>((size_t)B * LIST_CAP);
     p.tau = arena.take<float>(B);
+    p.qscale = arena.take<float>(B);
     p.cntM = arena.take<int>(B);
     p.cntO = arena.take<int>(B);
     p.flags = arena.take<int>(B);

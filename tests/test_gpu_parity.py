@@ -592,6 +592,32 @@ def test_detect_large_batch_stream_equals_tiled_and_oracle(h, w, r, top_k, nmaps
         assert np.array_equal(outs['auto'][0][b, :n], want), b
 
 
+@pytest.mark.parametrize('scale', [1e-12, 3e-7, 1.0, 7e4, 1e12])
+def test_detect_packed_kernel_is_scale_free(scale):
+    """The packed round-1 kernel decides on a 16-bit image of (score - tau) * qscale, qscale from the largest sampled score:
+    maps whose scores live far from 1 (fp16 would underflow to 0 or overflow to inf without it) give the tiled kernel's
+    rows bit for bit, and the greedy oracle's on one map."""
+    params = dict(nms_dist=6, threshold=0.0, border_dist=8, top_k=400, min_score=0.0)
+    gen = torch.Generator(device=DEV).manual_seed(99)
+    s = torch.rand(6, 1, 240, 320, generator=gen, device=DEV) * scale
+    s[1, 0, 100:140, 100:160] = 0.0                          # an exact-zero region
+    s[2] = s[2] * 1e-3                                        # a map three decades below its pair partner
+    out = {}
+    for name, ph in (('tiled', 7 | 8), ('packed', 7 | 32)):
+        xyp, count, raster, path = ops().detect_batched(s, params, phases=ph)
+        out[name] = (xyp.cpu().numpy(), count.cpu().numpy(), raster.cpu().numpy(), path.cpu().numpy())
+    assert np.array_equal(out['tiled'][1], out['packed'][1])
+    assert (out['packed'][3] == 1).all()
+    for b in range(6):
+        n = int(out['tiled'][1][b])
+        assert np.array_equal(out['tiled'][2][b, :n], out['packed'][2][b, :n]), b
+        assert np.array_equal(out['tiled'][0][b, :n], out['packed'][0][b, :n]), b
+    want, want_r = ref_ops.detection(s[2:3].cpu(), params, nms='greedy')
+    n = int(out['packed'][1][2])
+    assert np.array_equal(out['packed'][2][2, :n].astype(np.int64), want_r)
+    assert np.array_equal(out['packed'][0][2, :n], want)
+
+
 # ------------------------------------------------------------------------------------------------ tensor-core matcher internals
 
 def test_matcher_auto_falls_back_beyond_256_dims():
