@@ -57,7 +57,7 @@ def parse_args():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-others', action='store_true', help='skip the brief runs of the other four configs')
     ap.add_argument('--fused-table', action='store_true', help='per-kernel table of the opt-in fused sampling + operand preparation (A/B)')
-    ap.add_argument('--in-flight', type=int, default=3,
+    ap.add_argument('--in-flight', type=int, default=4,
                     help='steps kept in flight (one CUDA graph + stream + batch per slot); 1 = strictly serial steps')
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel from Python instead of replaying a CUDA graph')
     return ap.parse_args()
