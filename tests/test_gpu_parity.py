@@ -694,6 +694,25 @@ def test_sampling_plane_staged_path_cfg2_shape():
         assert torch.equal(a, b4), norm
 
 
+def test_sampling_staged_kernels_agree_beyond_1024_keypoints():
+    """cfg3's shape ([.,64,60,80] maps, 4096 keypoints): the eight-channel staged kernel takes one CTA per 1024
+    keypoints; same bits as the four-channel kernel, ragged counts incl. counts below a batch boundary, and the oracle."""
+    from keypoint_bench_b200 import _lib
+    gen = torch.Generator().manual_seed(33)
+    d = torch.randn(4, 64, 60, 80, generator=gen)
+    p = torch.rand(4, 4096, 3, generator=gen)
+    cnt = torch.tensor([4096, 1024, 1025, 3000], dtype=torch.int32)
+    a = ops().sample_batched(d.to(DEV), p.to(DEV), cnt.to(DEV))
+    with ops().debug_knob(_lib.KB_KNOB_SAMPLE_4CH, 1):
+        b4 = ops().sample_batched(d.to(DEV), p.to(DEV), cnt.to(DEV))
+    assert torch.equal(a, b4)
+    for b in (0, 2):
+        n = int(cnt[b])
+        ref = ref_ops.sample_brute_force(d[b].numpy(), p[b, :n].numpy())
+        assert np.allclose(a[b, :n].cpu().numpy(), ref, rtol=1e-5, atol=1e-5)
+    assert float(a[1, 1024:].abs().max()) == 0.0 and float(a[2, 1025:].abs().max()) == 0.0
+
+
 @pytest.mark.parametrize('pairs,c,h,w,n,seed', [(3, 256, 60, 80, 1000, 5), (2, 64, 30, 40, 517, 6), (1, 128, 16, 24, 1024, 7),
                                                 (5, 192, 15, 20, 300, 8)])
 def test_fused_sampling_and_operand_preparation_equals_the_two_calls(pairs, c, h, w, n, seed):
