@@ -35,6 +35,7 @@ namespace kbsparse {
 // tau: the rank-th largest of 4096 sampled pixels (bitwise counting select, no atomics)
 __global__ void __launch_bounds__(TAU_NT) tau_kernel(SparseParams p) {
     __shared__ int s_part[TAU_NT / 32];
+    __shared__ int s_part2[2][TAU_NT / 32];
     const int b = blockIdx.x;
     const long long npx = (long long)p.H * p.W;
     const float theta = fmaxf(p.threshold, 0.0f);
@@ -66,12 +67,12 @@ __global__ void __launch_bounds__(TAU_NT) tau_kernel(SparseParams p) {
 #pragma unroll
         for (int i = 0; i < PER; ++i) c += keys[i] >= t ? 1 : 0;
         c = __reduce_add_sync(0xffffffffu, c);
-        if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = c;
+        int* part = s_part2[bit & 1];                       // two buffers: one barrier per bit instead of two
+        if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = c;
         __syncthreads();
         int tot = 0;
 #pragma unroll
-        for (int w = 0; w < TAU_NT / 32; ++w) tot += s_part[w];
-        __syncthreads();
+        for (int w = 0; w < TAU_NT / 32; ++w) tot += part[w];
         if (tot >= (int)rank) v = t;
     }
     // the largest sample (for the packed round-1 kernel's 16-bit image, which must neither overflow nor underflow on
